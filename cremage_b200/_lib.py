@@ -1,0 +1,103 @@
+"""ctypes binding of libcremage_b200.so (the C ABI declared in include/cremage_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc, and if it cannot be built or loaded the
+import of any compute entry point fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import build as _build
+
+_LIB = None
+
+
+class IGemmDesc(C.Structure):
+    """Mirror of `cb_igemm_desc` (include/cremage_b200.h)."""
+
+    _fields_ = [
+        ("a0", C.c_void_p), ("c0", C.c_int64), ("a0_ld", C.c_int64),
+        ("a1", C.c_void_p), ("c1", C.c_int64), ("a1_ld", C.c_int64),
+        ("a_n", C.c_int64), ("a_h", C.c_int64), ("a_w", C.c_int64),
+        ("n", C.c_int64), ("h", C.c_int64), ("w", C.c_int64),
+        ("tw", C.c_int), ("th", C.c_int), ("tn", C.c_int),
+        ("taps", C.c_int),
+        ("tap_dw", C.c_int * 9), ("tap_dh", C.c_int * 9), ("tap_dn", C.c_int * 9),
+        ("wgt", C.c_void_p), ("wgt_rows", C.c_int64),
+        ("cout", C.c_int64),
+        ("mode", C.c_int), ("act", C.c_int),
+        ("bias", C.c_void_p),
+        ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int64),
+        ("residual", C.c_void_p), ("res_ld", C.c_int64),
+        ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_f32", C.c_int),
+        ("out_scale", C.c_float),
+        ("heads_d", C.c_int), ("heads_dpad", C.c_int), ("heads_h", C.c_int), ("heads_tokens", C.c_int),
+        ("heads_which_stride", C.c_int64),
+        ("bn", C.c_int), ("stages", C.c_int),
+    ]
+
+
+_i64, _int, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+
+# name -> argtypes (every function returns int unless listed in _RESTYPES)
+SIGNATURES = {
+    "cb_last_error": [],
+    "cb_version": [],
+    "cb_launch_count": [],
+    "cb_igemm": [C.POINTER(IGemmDesc), _vp],
+    "cb_attention": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp],
+    "cb_softmax_rows": [_vp, _i64, _i64, _i64, _f32, _vp],
+    "cb_groupnorm_nhwc": [_vp, _i64, _vp, _i64, _i64, _i64, _int, _f32, _vp, _vp, _int, _vp, _vp, _vp],
+    "cb_layernorm": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp],
+    "cb_nchw_to_nhwc": [_vp, _int, _i64, _i64, _i64, _i64, _f32, _vp, _vp],
+    "cb_nhwc_to_nchw_f32": [_vp, _int, _i64, _i64, _i64, _i64, _vp, _vp],
+    "cb_upsample2x_nhwc": [_vp, _i64, _i64, _i64, _i64, _vp, _vp],
+    "cb_parity_split_nhwc": [_vp, _i64, _i64, _i64, _i64, _vp, _vp],
+    "cb_timestep_embedding": [_vp, _i64, _int, _vp, _vp, _vp],
+    "cb_conv3x3_small_cin": [_vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _i64, _vp, _vp],
+    "cb_silu_add": [_vp, _vp, _i64, _vp, _vp],
+    "cb_cfg_scale_input": [_vp, _i64, _i64, _f32, _vp, _vp],
+    "cb_step_euler_ancestral": [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "cb_step_dpmpp_2m": [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "cb_step_ddim": [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "cb_image_to_u8": [_vp, _i64, _i64, _i64, _vp, _vp],
+}
+_RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64}
+
+
+def lib_path() -> Path:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (building first if needed) the CUDA library. Raises if that is impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if not path.exists():
+        _build.build()
+    lib = C.CDLL(str(path))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    _LIB = lib
+    return lib
+
+
+class CremageB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().cb_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise CremageB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().cb_launch_count())

@@ -1,0 +1,289 @@
+// Layout conversions and small elementwise kernels of the denoising path (all HBM/latency bound).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "cremage_b200.h"
+
+namespace cb {
+
+// NCHW (fp32 / fp16 / bf16) -> NHWC bf16, zero padding channels [c, c_pad). One thread per (n, pixel).
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, long long n, int c, long long hw, int c_pad, float scale,
+                                    __nv_bfloat16* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * hw) return;
+  const long long b = i / hw, p = i - b * hw;
+  const T* s = src + b * c * hw + p;
+  __nv_bfloat16* d = dst + i * c_pad;
+  for (int ch = 0; ch < c_pad; ++ch) {
+    float v = ch < c ? float(s[(long long)ch * hw]) * scale : 0.f;
+    d[ch] = __float2bfloat16(v);
+  }
+}
+
+// generic tiled transpose for wide channel counts: [n][c][hw] -> [n][hw][c_pad]
+template <typename T>
+__global__ void nchw_to_nhwc_tiled_kernel(const T* __restrict__ src, int c, long long hw, int c_pad, float scale,
+                                          __nv_bfloat16* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int ch = c0 + j;
+    const long long p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (ch < c && p < hw) ? float(src[(b * c + ch) * hw + p]) * scale : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long p = p0 + j;
+    const int ch = c0 + threadIdx.x;
+    if (p < hw && ch < c_pad) dst[(b * hw + p) * c_pad + ch] = __float2bfloat16(tile[threadIdx.x][j]);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int c, long long hw, long long c_ld,
+                                    float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long p = p0 + j;
+    const int ch = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < hw && ch < c) ? float(src[(b * hw + p) * c_ld + ch]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int ch = c0 + j;
+    const long long p = p0 + threadIdx.x;
+    if (ch < c && p < hw) dst[(b * c + ch) * hw + p] = tile[threadIdx.x][j];
+  }
+}
+
+// nearest 2x upsample, one thread per 16-byte channel vector of an OUTPUT pixel
+__global__ void upsample2x_kernel(const uint4* __restrict__ src, long long n, int h, int w, int cv,
+                                  uint4* __restrict__ dst) {
+  const long long total = n * (2LL * h) * (2LL * w) * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = int(i % cv);
+    long long t = i / cv;
+    const int ox = int(t % (2 * w));
+    t /= (2 * w);
+    const int oy = int(t % (2 * h));
+    const long long b = t / (2 * h);
+    dst[i] = src[((b * h + (oy >> 1)) * w + (ox >> 1)) * cv + v];
+  }
+}
+
+// parity split: dst[2*ph+pw][n][h/2][w/2][c] = src[n][2y+ph][2x+pw][c]
+__global__ void parity_split_kernel(const uint4* __restrict__ src, long long n, int h, int w, int cv,
+                                    uint4* __restrict__ dst) {
+  const long long total = n * h * w * cv;
+  const int h2 = h >> 1, w2 = w >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = int(i % cv);
+    long long t = i / cv;
+    const int x = int(t % w);
+    t /= w;
+    const int y = int(t % h);
+    const long long b = t / h;
+    const int plane = ((y & 1) << 1) | (x & 1);
+    dst[(((plane * n + b) * h2 + (y >> 1)) * w2 + (x >> 1)) * cv + v] = src[i];
+  }
+}
+
+// sinusoidal timestep embedding, out[n][dim] = [cos(t*f) | sin(t*f)]; the frequency table f (fp32 [dim/2]) is built
+// on the host with the reference's own expression so it is bit-identical to the reference's.
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, long long n, int dim,
+                                          const float* __restrict__ freqs, __nv_bfloat16* __restrict__ out) {
+  const int half = dim / 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const long long b = i / half;
+  const int k = int(i - b * half);
+  const float arg = t[b] * freqs[k];
+  out[b * dim + k] = __float2bfloat16(cosf(arg));
+  out[b * dim + half + k] = __float2bfloat16(sinf(arg));
+  if ((dim & 1) && k == 0) out[b * dim + dim - 1] = __float2bfloat16(0.f);
+}
+
+// direct 3x3 conv (pad 1, stride 1) for tiny cin; wgt fp32 [3][3][cin][cout]; thread = (pixel, 8 output channels)
+template <int CIN>
+__global__ void conv3x3_small_cin_kernel(const __nv_bfloat16* __restrict__ src, long long n, int h, int w, int cin_ld,
+                                         const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
+                                         __nv_bfloat16* __restrict__ out) {
+  const int cg = cout >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * h * w * cg) return;
+  const int g = int(i % cg);
+  long long t = i / cg;
+  const int x = int(t % w);
+  t /= w;
+  const int y = int(t % h);
+  const long long b = t / h;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[g * 8 + e] : 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= h) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= w) continue;
+      const __nv_bfloat16* s = src + ((b * h + yy) * w + xx) * cin_ld;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float a = __bfloat162float(s[ci]);
+        const float* wp = wgt + ((ky * 3 + kx) * CIN + ci) * cout + g * 8;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]);
+        acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
+        acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
+        acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+      }
+    }
+  }
+  __nv_bfloat16* o = out + ((b * h + y) * w + x) * (long long)cout + g * 8;
+  *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                            pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+}
+
+__global__ void silu_add_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ add,
+                                long long count, __nv_bfloat16* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float v = __bfloat162float(x[i]);
+  if (add) v += __bfloat162float(add[i]);
+  out[i] = __float2bfloat16(silu_f(v));
+}
+
+__global__ void image_to_u8_kernel(const float* __restrict__ src, long long npix, long long c_ld,
+                                   uint8_t* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = (src[i * c_ld + ch] + 1.0f) / 2.0f;
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    dst[i * 3 + ch] = (uint8_t)(255.f * v);  // truncating, like numpy astype(uint8)
+  }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_t c, int64_t hw, int64_t c_pad,
+                               float scale, void* dst, cudaStream_t stream) {
+  CB_REQUIRE(src && dst && n > 0 && c > 0 && hw > 0 && c_pad >= c, "cb_nchw_to_nhwc: bad arguments");
+  CB_REQUIRE(src_dtype >= 0 && src_dtype <= 2, "cb_nchw_to_nhwc: src_dtype must be 0 (f32), 1 (f16) or 2 (bf16)");
+  auto D = (__nv_bfloat16*)dst;
+  if (c_pad <= 16) {
+    const long long total = n * hw;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (src_dtype == 0) nchw_to_nhwc_kernel<float><<<grid, 256, 0, stream>>>((const float*)src, n, (int)c, hw, (int)c_pad, scale, D);
+    else if (src_dtype == 1) nchw_to_nhwc_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)src, n, (int)c, hw, (int)c_pad, scale, D);
+    else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, n, (int)c, hw, (int)c_pad, scale, D);
+  } else {
+    dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c_pad + 31) / 32), (unsigned)n), block(32, 8);
+    if (src_dtype == 0) nchw_to_nhwc_tiled_kernel<float><<<grid, block, 0, stream>>>((const float*)src, (int)c, hw, (int)c_pad, scale, D);
+    else if (src_dtype == 1) nchw_to_nhwc_tiled_kernel<__half><<<grid, block, 0, stream>>>((const __half*)src, (int)c, hw, (int)c_pad, scale, D);
+    else nchw_to_nhwc_tiled_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (int)c, hw, (int)c_pad, scale, D);
+  }
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_nhwc_to_nchw_f32(const void* src, int src_f32, int64_t n, int64_t c, int64_t hw, int64_t c_ld,
+                                   float* dst, cudaStream_t stream) {
+  CB_REQUIRE(src && dst && n > 0 && c > 0 && hw > 0 && c_ld >= c, "cb_nhwc_to_nchw_f32: bad arguments");
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
+  if (src_f32) nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const float*)src, (int)c, hw, c_ld, dst);
+  else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (int)c, hw, c_ld, dst);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+static unsigned grid_for(long long total, int threads) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+extern "C" int cb_upsample2x_nhwc(const void* src, int64_t n, int64_t h, int64_t w, int64_t c, void* dst,
+                                  cudaStream_t stream) {
+  CB_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "cb_upsample2x_nhwc: bad arguments");
+  const long long total = n * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const uint4*)src, n, (int)h, (int)w, (int)(c / 8), (uint4*)dst);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_parity_split_nhwc(const void* src, int64_t n, int64_t h, int64_t w, int64_t c, void* dst,
+                                    cudaStream_t stream) {
+  CB_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && h % 2 == 0 && w % 2 == 0,
+             "cb_parity_split_nhwc: bad arguments (even h, w; c %% 8 == 0)");
+  const long long total = n * h * w * (c / 8);
+  parity_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const uint4*)src, n, (int)h, (int)w, (int)(c / 8), (uint4*)dst);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_timestep_embedding(const float* t, int64_t n, int dim, const float* freqs, void* out,
+                                     cudaStream_t stream) {
+  CB_REQUIRE(t && freqs && out && n > 0 && dim >= 2, "cb_timestep_embedding: bad arguments");
+  const long long total = n * (dim / 2);
+  timestep_embedding_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(t, n, dim, freqs, (__nv_bfloat16*)out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64_t w, int cin, int64_t cin_ld,
+                                    const float* wgt, const float* bias, int64_t cout, void* out, cudaStream_t stream) {
+  CB_REQUIRE(src && wgt && out && n > 0 && h > 0 && w > 0, "cb_conv3x3_small_cin: bad arguments");
+  CB_REQUIRE(cout % 8 == 0, "cb_conv3x3_small_cin: cout must be a multiple of 8");
+  CB_REQUIRE(cin_ld >= cin, "cb_conv3x3_small_cin: cin_ld < cin");
+  const long long total = n * h * w * (cout / 8);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  auto S = (const __nv_bfloat16*)src;
+  auto O = (__nv_bfloat16*)out;
+  switch (cin) {
+    case 3: conv3x3_small_cin_kernel<3><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
+    case 4: conv3x3_small_cin_kernel<4><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
+    case 8: conv3x3_small_cin_kernel<8><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
+    case 9: conv3x3_small_cin_kernel<9><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
+    default: CB_REQUIRE(false, "cb_conv3x3_small_cin: cin %d unsupported (3, 4, 8, 9)", cin);
+  }
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream) {
+  CB_REQUIRE(x && out && count > 0, "cb_silu_add: bad arguments");
+  silu_add_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)add, count, (__nv_bfloat16*)out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_image_to_u8(const void* src, int64_t n, int64_t hw, int64_t c_ld, uint8_t* dst, cudaStream_t stream) {
+  CB_REQUIRE(src && dst && n > 0 && hw > 0 && c_ld >= 3, "cb_image_to_u8: bad arguments");
+  const long long npix = n * hw;
+  image_to_u8_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>((const float*)src, npix, c_ld, dst);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}

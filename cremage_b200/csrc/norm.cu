@@ -1,0 +1,327 @@
+// Bandwidth-bound normalisation kernels: GroupNorm(+SiLU) over NHWC bf16 (two-source capable), LayerNorm,
+// row softmax.  All statistics in fp32; 16-byte vector loads/stores; warp-shuffle / smem reductions.
+#include "common.cuh"
+#include "cremage_b200.h"
+
+namespace cb {
+
+struct alignas(16) Vec8 { uint32_t u[4]; };
+
+CB_DEVINL Vec8 ld_vec8(const __nv_bfloat16* p) {
+  Vec8 v;
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  v.u[0] = t.x; v.u[1] = t.y; v.u[2] = t.z; v.u[3] = t.w;
+  return v;
+}
+CB_DEVINL void st_vec8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) =
+      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+CB_DEVINL void unpack8(const Vec8& v, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = unpack_bf16x2(v.u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GroupNorm pass 1: per-(image, group) sum and sum of squares.
+// grid = (splits, n); block = CV * P threads where CV = C/8 channel vectors; a thread keeps a FIXED channel vector
+// and walks pixels p0 + lane_p, +P, ... so it accumulates 8 per-channel sums in registers.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1,
+                                int c1, long long hw, int groups, int P, long long pix_per_cta,
+                                float* __restrict__ stats) {
+  extern __shared__ float s_acc[];  // [2][C]
+  const int C = c0 + c1;
+  const int CV = C >> 3;
+  const int cv = threadIdx.x % CV;
+  const int lp = threadIdx.x / CV;
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+
+  const int c = cv << 3;
+  const __nv_bfloat16* src;
+  long long ld;
+  if (c < c0) { src = x0 + (long long)n * hw * c0 + c; ld = c0; }
+  else        { src = x1 + (long long)n * hw * c1 + (c - c0); ld = c1; }
+
+  const long long p_begin = (long long)blockIdx.x * pix_per_cta;
+  long long p_end = p_begin + pix_per_cta;
+  if (p_end > hw) p_end = hw;
+
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  long long p = p_begin + lp;
+  // 4 independent 16-byte loads in flight per thread
+  for (; p + 3LL * P < p_end; p += 4LL * P) {
+    Vec8 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld_vec8(src + (p + (long long)u * P) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+  }
+  for (; p < p_end; p += P) {
+    float f[8];
+    unpack8(ld_vec8(src + p * ld), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(&s_acc[c + i], s[i]);
+    atomicAdd(&s_acc[C + c + i], q[i]);
+  }
+  __syncthreads();
+  const int gs = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < gs; ++i) { a += s_acc[g * gs + i]; b += s_acc[C + g * gs + i]; }
+    atomicAdd(&stats[((long long)n * groups + g) * 2 + 0], a);
+    atomicAdd(&stats[((long long)n * groups + g) * 2 + 1], b);
+  }
+}
+
+// GroupNorm pass 2: y = silu?((x - mean) * rstd * gamma + beta) -> bf16 [n][hw][C]
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1,
+                                int c1, long long hw, int groups, int P, long long pix_per_cta, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                const float* __restrict__ stats, __nv_bfloat16* __restrict__ out) {
+  const int C = c0 + c1;
+  const int CV = C >> 3;
+  const int cv = threadIdx.x % CV;
+  const int lp = threadIdx.x / CV;
+  const int n = blockIdx.y;
+  const int c = cv << 3;
+  const int gs = C / groups;
+  const float inv_cnt = 1.f / (float(gs) * float(hw));
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c + i) / gs;
+    const float sum = stats[((long long)n * groups + g) * 2 + 0];
+    const float sq = stats[((long long)n * groups + g) * 2 + 1];
+    const float mean = sum * inv_cnt;
+    const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    a[i] = rstd * gamma[c + i];
+    b[i] = beta[c + i] - mean * a[i];
+  }
+  const __nv_bfloat16* src;
+  long long ld;
+  if (c < c0) { src = x0 + (long long)n * hw * c0 + c; ld = c0; }
+  else        { src = x1 + (long long)n * hw * c1 + (c - c0); ld = c1; }
+  __nv_bfloat16* dst = out + (long long)n * hw * C + c;
+
+  const long long p_begin = (long long)blockIdx.x * pix_per_cta;
+  long long p_end = p_begin + pix_per_cta;
+  if (p_end > hw) p_end = hw;
+  long long p = p_begin + lp;
+  for (; p + 3LL * P < p_end; p += 4LL * P) {
+    Vec8 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld_vec8(src + (p + (long long)u * P) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf(f[i], a[i], b[i]);
+        f[i] = silu ? silu_f(y) : y;
+      }
+      st_vec8(dst + (p + (long long)u * P) * C, f);
+    }
+  }
+  for (; p < p_end; p += P) {
+    float f[8];
+    unpack8(ld_vec8(src + p * ld), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = fmaf(f[i], a[i], b[i]);
+      f[i] = silu ? silu_f(y) : y;
+    }
+    st_vec8(dst + p * C, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the row lives in registers (two-pass mean / variance, exact in fp32).
+// ------------------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, float eps,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 __nv_bfloat16* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int CV = C >> 3;
+  const __nv_bfloat16* src = x + row * C;
+  float f[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < CV) {
+      unpack8(ld_vec8(src + v * 8), f[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += f[i][e];
+    }
+  }
+  sum = warp_sum(sum);
+  const float mean = sum / float(C);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < CV) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; sq = fmaf(d, d, sq); }
+    }
+  }
+  sq = warp_sum(sq);
+  const float rstd = rsqrtf(sq / float(C) + eps);
+  __nv_bfloat16* dst = out + row * C;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < CV) {
+      float y[8];
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = fmaf((f[i][e] - mean) * rstd, gg[e], bb[e]);
+      st_vec8(dst + v * 8, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Row softmax (in place, bf16 storage, fp32 math); one CTA per row, the row is staged in shared memory.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void softmax_rows_kernel(__nv_bfloat16* __restrict__ s, long long cols, long long ld, float scale) {
+  extern __shared__ float s_row[];
+  __shared__ float red[32];
+  __nv_bfloat16* row = s + (long long)blockIdx.x * ld;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (long long v = tid; v < (cols >> 3); v += blockDim.x) {
+    float f[8];
+    unpack8(ld_vec8(row + v * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { f[e] *= scale; s_row[v * 8 + e] = f[e]; m = fmaxf(m, f[e]); }
+  }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (long long i = tid; i < cols; i += blockDim.x) {
+    const float e = __expf(s_row[i] - m);
+    s_row[i] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (long long v = tid; v < (cols >> 3); v += blockDim.x) {
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = s_row[v * 8 + e] * inv;
+    st_vec8(row + v * 8, f);
+  }
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int64_t c1, int64_t n, int64_t hw,
+                                 int groups, float eps, const float* gamma, const float* beta, int silu, void* out,
+                                 float* stats, cudaStream_t stream) {
+  CB_REQUIRE(x0 && out && stats && gamma && beta, "cb_groupnorm_nhwc: null pointer");
+  const int64_t C = c0 + c1;
+  CB_REQUIRE(c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0, "cb_groupnorm_nhwc: channels must be multiples of 8");
+  CB_REQUIRE(c1 == 0 || x1, "cb_groupnorm_nhwc: c1 > 0 but x1 is null");
+  CB_REQUIRE(groups > 0 && C % groups == 0, "cb_groupnorm_nhwc: %lld channels not divisible into %d groups", (long long)C, groups);
+  CB_REQUIRE(n > 0 && hw > 0, "cb_groupnorm_nhwc: empty input");
+  const int CV = int(C / 8);
+  CB_REQUIRE(CV <= 1024, "cb_groupnorm_nhwc: more than 8192 channels unsupported");
+  int P = 384 / CV;
+  if (P < 1) P = 1;
+  if ((int64_t)P > hw) P = (int)hw;
+  const int threads = CV * P;
+  // enough CTAs to fill 148 SMs a few times over, at least ~32 pixels per thread-lane when the image is large
+  long long splits = (148LL * 4 + n - 1) / n;
+  long long max_splits = (hw + (long long)P * 8 - 1) / ((long long)P * 8);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long pix_per_cta = (hw + splits - 1) / splits;
+  pix_per_cta = ((pix_per_cta + P - 1) / P) * P;
+  splits = (hw + pix_per_cta - 1) / pix_per_cta;
+  CB_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
+  dim3 grid((unsigned)splits, (unsigned)n);
+  const size_t smem = sizeof(float) * 2 * C;
+  gn_stats_kernel<<<grid, threads, smem, stream>>>((const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1, (int)c1,
+                                                   hw, groups, P, pix_per_cta, stats);
+  CB_CHECK_CUDA(cudaGetLastError());
+  gn_apply_kernel<<<grid, threads, 0, stream>>>((const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1, (int)c1, hw,
+                                                groups, P, pix_per_cta, eps, gamma, beta, silu, stats,
+                                                (__nv_bfloat16*)out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(2);
+  return CB_OK;
+}
+
+extern "C" int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, const float* gamma, const float* beta,
+                            void* out, cudaStream_t stream) {
+  CB_REQUIRE(x && out && gamma && beta, "cb_layernorm: null pointer");
+  CB_REQUIRE(c > 0 && c % 8 == 0 && c <= 4096, "cb_layernorm: width %lld unsupported (multiple of 8, <= 4096)", (long long)c);
+  CB_REQUIRE(rows > 0, "cb_layernorm: empty input");
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  const int maxv = int((c / 8 + 31) / 32);
+  auto X = (const __nv_bfloat16*)x;
+  auto O = (__nv_bfloat16*)out;
+  if (maxv <= 2)       layernorm_kernel<2><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
+  else if (maxv <= 4)  layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
+  else if (maxv <= 8)  layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
+  else                 layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_softmax_rows(void* s, int64_t rows, int64_t cols, int64_t ld, float scale, cudaStream_t stream) {
+  CB_REQUIRE(s, "cb_softmax_rows: null pointer");
+  CB_REQUIRE(cols > 0 && cols % 8 == 0 && cols <= 48 * 1024, "cb_softmax_rows: cols %lld unsupported (multiple of 8, <= 49152)", (long long)cols);
+  CB_REQUIRE(ld % 8 == 0 && ld >= cols && rows > 0, "cb_softmax_rows: bad ld / rows");
+  const size_t smem = sizeof(float) * cols;
+  static thread_local bool configured = false;
+  if (!configured) {
+    CB_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  softmax_rows_kernel<<<(unsigned)rows, 256, smem, stream>>>((__nv_bfloat16*)s, cols, ld, scale);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}

@@ -1,0 +1,368 @@
+"""Torch-tensor front end of the C ABI (include/cremage_b200.h): argument marshalling only, no arithmetic.
+
+Every function here enqueues hand-written sm_100a kernels on the current CUDA stream through ctypes. Activations are
+NHWC bf16. Weight repacking helpers (pure layout work done once at load time) live here too.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import IGemmDesc, check
+
+EPI_LINEAR, EPI_GEGLU, EPI_HEADS = 0, 1, 2
+ACT_NONE, ACT_SILU = 0, 1
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cremage_b200 has no CPU path: tensors must live on a CUDA device")
+
+
+def ceil64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# weight repacking (host side, once per load)
+# ------------------------------------------------------------------------------------------------------------------
+def pack_weight(w: torch.Tensor, splits: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """OIHW conv weight or [O, I] linear weight -> bf16 [O][tap][pad64(c0) | pad64(c1)] (K-major, zero padded)."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    o, i, kh, kw = w.shape
+    c0, c1 = (i, 0) if splits is None else splits
+    assert c0 + c1 == i, (c0, c1, i)
+    wt = w.detach().permute(0, 2, 3, 1).reshape(o, kh * kw, i).float()  # [O][tap][I]
+    parts = []
+    for lo, n in ((0, c0), (c0, c1)):
+        if n == 0:
+            continue
+        blk = torch.zeros(o, kh * kw, ceil64(n), dtype=torch.float32, device=w.device)
+        blk[:, :, :n] = wt[:, :, lo:lo + n]
+        parts.append(blk)
+    return torch.cat(parts, dim=2).reshape(o, -1).to(BF16).contiguous()
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor, bn: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Interleave GEGLU projection rows per N tile: tile t holds x rows [t*bn/2, (t+1)*bn/2) then the matching gates.
+
+    Reference: GEGLU.forward chunks proj(x) into (x, gate) halves (ldm/modules/attention.py:59-60,94-96).
+    """
+    two_inner, _ = w.shape
+    inner = two_inner // 2
+    half = bn // 2
+    assert inner % half == 0, (inner, bn)
+    idx = []
+    for t in range(inner // half):
+        idx.extend(range(t * half, (t + 1) * half))
+        idx.extend(range(inner + t * half, inner + (t + 1) * half))
+    idx = torch.tensor(idx, device=w.device)
+    return w.detach()[idx].contiguous(), b.detach()[idx].float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tiling heuristics
+# ------------------------------------------------------------------------------------------------------------------
+def _pow2_floor(x: int) -> int:
+    return 1 << (x.bit_length() - 1)
+
+
+def _pow2_ceil(x: int) -> int:
+    return 1 << (x - 1).bit_length()
+
+
+def choose_tile(n: int, h: int, w: int) -> Tuple[int, int, int]:
+    """128-row tile {tw, th, tn} over an (n, h, w) pixel grid; overhang is masked by the kernel."""
+    if h == 1 and n == 1:
+        return 128, 1, 1
+    tw = min(128, w & -w)  # largest power of two dividing w
+    th = min(128 // tw, _pow2_ceil(h))
+    tn = 128 // (tw * th)
+    return tw, th, tn
+
+
+def choose_bn(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
+    """N tile: largest of (160, 128, 64, 32) with little padding waste that still yields >= 2 CTAs per SM."""
+    best = None
+    for want_tiles in (296, 148, 1):
+        for bn in (160, 128, 64, 32):
+            if bn % multiple:
+                continue
+            nt = -(-cout_cols // bn)
+            waste = nt * bn / cout_cols
+            if waste <= 1.1 and nt * m_tiles >= want_tiles:
+                return bn
+            if best is None or waste < best[0]:
+                best = (waste, bn)
+    return best[1]
+
+
+TAPS_1X1 = ([0], [0], [0])
+TAPS_3X3 = ([kw - 1 for kh in range(3) for kw in range(3)], [kh - 1 for kh in range(3) for kw in range(3)], [0] * 9)
+
+
+def taps_3x3_stride2(n: int):
+    """stride 2, pad 1 over the parity-split input [2*ph+pw][n][h/2][w/2][c]: input row 2*oy+kh-1."""
+    par = {0: (1, -1), 1: (0, 0), 2: (1, 0)}  # k -> (parity, shift)
+    dw, dh, dn = [], [], []
+    for kh in range(3):
+        for kw in range(3):
+            ph, sh = par[kh]
+            pw, sw = par[kw]
+            dw.append(sw)
+            dh.append(sh)
+            dn.append((2 * ph + pw) * n)
+    return dw, dh, dn
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# implicit GEMM
+# ------------------------------------------------------------------------------------------------------------------
+def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.Tensor] = None,
+          out_grid: Optional[Tuple[int, int, int]] = None, taps=TAPS_1X1, bias: Optional[torch.Tensor] = None,
+          rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+          mode: int = EPI_LINEAR, out: Optional[torch.Tensor] = None, out_f32: bool = False, out_ld: Optional[int] = None,
+          out_scale: float = 1.0, heads: Optional[Tuple[int, int, int, int, int]] = None, bn: Optional[int] = None,
+          stages: int = 0) -> torch.Tensor:
+    """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
+
+    out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
+    heads: (d, dpad, n_heads, tokens_per_batch, which_stride) for EPI_HEADS (then `out` must be given).
+    """
+    _need_cuda(a0, a1, wgt, bias, rowbias, residual, out)
+    assert a0.dtype == BF16 and wgt.dtype == BF16 and a0.is_contiguous() and wgt.is_contiguous()
+    if a0.dim() == 2:
+        a_n, a_h, a_w, c0 = 1, 1, a0.shape[0], a0.shape[1]
+    else:
+        a_n, a_h, a_w, c0 = a0.shape
+    c1 = 0
+    if a1 is not None:
+        assert a1.dtype == BF16 and a1.is_contiguous() and tuple(a1.shape[:-1]) == tuple(a0.shape[:-1])
+        c1 = a1.shape[-1]
+    n, h, w = out_grid if out_grid is not None else (a_n, a_h, a_w)
+    rows = n * h * w
+    tw, th, tn = choose_tile(n, h, w)
+    m_tiles = (-(-w // tw)) * (-(-h // th)) * (-(-n // tn))
+    ncols = 2 * cout if mode == EPI_GEGLU else cout
+    if bn is None:
+        bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
+    if out is None:
+        ld = out_ld if out_ld is not None else cout
+        out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else BF16, device=a0.device)
+    ld = out_ld if out_ld is not None else (out.shape[-1] if mode != EPI_HEADS else 0)
+
+    d = IGemmDesc()
+    d.a0, d.c0, d.a0_ld = _p(a0), c0, 0
+    d.a1, d.c1, d.a1_ld = _p(a1), c1, 0
+    d.a_n, d.a_h, d.a_w = a_n, a_h, a_w
+    d.n, d.h, d.w = n, h, w
+    d.tw, d.th, d.tn = tw, th, tn
+    dw, dh, dn = taps
+    d.taps = len(dw)
+    for i in range(len(dw)):
+        d.tap_dw[i], d.tap_dh[i], d.tap_dn[i] = dw[i], dh[i], dn[i]
+    d.wgt, d.wgt_rows = _p(wgt), wgt.shape[0]
+    d.cout = cout
+    d.mode, d.act = mode, act
+    d.bias = _p(bias)
+    d.rowbias, d.rowbias_ld = _p(rowbias), (rowbias.shape[-1] if rowbias is not None else 0)
+    if rowbias is not None:
+        assert rowbias.dtype == torch.float32
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    d.residual, d.res_ld = _p(residual), (residual.shape[-1] if residual is not None else 0)
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.is_contiguous()
+    d.out, d.out_ld, d.out_f32 = _p(out), ld, int(out.dtype == torch.float32)
+    d.out_scale = out_scale
+    if heads is not None:
+        d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
+    d.bn, d.stages = bn, stages
+    check(_lib.load().cb_igemm(C.byref(d), _stream()), "cb_igemm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# attention / norms
+# ------------------------------------------------------------------------------------------------------------------
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, heads: int, nq: int, nk: int, d: int,
+              dpad: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q,k,v: bf16 [batch*heads, tokens, dpad] -> out bf16 [batch*nq, heads*d]."""
+    _need_cuda(q, k, v)
+    if out is None:
+        out = torch.empty((batch * nq, heads * d), dtype=BF16, device=q.device)
+    check(_lib.load().cb_attention(_p(q), _p(k), _p(v), _p(out), batch, heads, nq, nk, d, dpad, scale, _stream()),
+          "cb_attention")
+    return out
+
+
+def softmax_rows_(s: torch.Tensor, scale: float) -> torch.Tensor:
+    _need_cuda(s)
+    assert s.dtype == BF16 and s.dim() == 2 and s.stride(1) == 1
+    check(_lib.load().cb_softmax_rows(_p(s), s.shape[0], s.shape[1], s.stride(0), scale, _stream()), "cb_softmax_rows")
+    return s
+
+
+def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+              x1: Optional[torch.Tensor] = None, groups: int = 32) -> torch.Tensor:
+    """GroupNorm(+SiLU) over NHWC bf16 [N,H,W,C0] (+ [N,H,W,C1] concatenated on channels) -> [N,H,W,C0+C1]."""
+    _need_cuda(x0, x1, gamma, beta)
+    assert x0.dtype == BF16 and x0.is_contiguous() and gamma.dtype == torch.float32
+    n = x0.shape[0]
+    hw = x0.numel() // (n * x0.shape[-1])
+    c0 = x0.shape[-1]
+    c1 = 0 if x1 is None else x1.shape[-1]
+    out = torch.empty((*x0.shape[:-1], c0 + c1), dtype=BF16, device=x0.device)
+    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x0.device)
+    check(_lib.load().cb_groupnorm_nhwc(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(gamma), _p(beta), int(silu),
+                                        _p(out), _p(stats), _stream()), "cb_groupnorm_nhwc")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _need_cuda(x, gamma, beta)
+    assert x.dtype == BF16 and x.is_contiguous()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    out = torch.empty_like(x)
+    check(_lib.load().cb_layernorm(_p(x), rows, c, eps, _p(gamma), _p(beta), _p(out), _stream()), "cb_layernorm")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# layout / elementwise
+# ------------------------------------------------------------------------------------------------------------------
+_SRC_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None, scale: float = 1.0) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    c_pad = c if c_pad is None else c_pad
+    out = torch.empty((n, h, w, c_pad), dtype=BF16, device=x.device)
+    check(_lib.load().cb_nchw_to_nhwc(_p(x), _SRC_DTYPE[x.dtype], n, c, h * w, c_pad, scale, _p(out), _stream()),
+          "cb_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    """x: [N,H,W,C_ld] bf16 or fp32 -> fp32 [N,c,H,W]."""
+    _need_cuda(x)
+    assert x.is_contiguous()
+    n, h, w, c_ld = x.shape
+    c = c_ld if c is None else c
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.load().cb_nhwc_to_nchw_f32(_p(x), int(x.dtype == torch.float32), n, c, h * w, c_ld, _p(out), _stream()),
+          "cb_nhwc_to_nchw_f32")
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+    check(_lib.load().cb_upsample2x_nhwc(_p(x), n, h, w, c, _p(out), _stream()), "cb_upsample2x_nhwc")
+    return out
+
+
+def parity_split(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    n, h, w, c = x.shape
+    out = torch.empty((4, n, h // 2, w // 2, c), dtype=BF16, device=x.device)
+    check(_lib.load().cb_parity_split_nhwc(_p(x), n, h, w, c, _p(out), _stream()), "cb_parity_split_nhwc")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, freqs: torch.Tensor) -> torch.Tensor:
+    _need_cuda(t, freqs)
+    assert t.dtype == torch.float32 and freqs.dtype == torch.float32 and freqs.numel() == dim // 2
+    out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
+    check(_lib.load().cb_timestep_embedding(_p(t), t.shape[0], dim, _p(freqs), _p(out), _stream()),
+          "cb_timestep_embedding")
+    return out
+
+
+def conv3x3_small_cin(x: torch.Tensor, cin: int, wgt: torch.Tensor, bias: Optional[torch.Tensor], cout: int) -> torch.Tensor:
+    """x: NHWC bf16 [N,H,W,cin_ld]; wgt fp32 [3,3,cin,cout]."""
+    _need_cuda(x, wgt, bias)
+    n, h, w, cin_ld = x.shape
+    out = torch.empty((n, h, w, cout), dtype=BF16, device=x.device)
+    check(_lib.load().cb_conv3x3_small_cin(_p(x), n, h, w, cin, cin_ld, _p(wgt), _p(bias), cout, _p(out), _stream()),
+          "cb_conv3x3_small_cin")
+    return out
+
+
+def silu_add(x: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, add)
+    out = torch.empty_like(x)
+    check(_lib.load().cb_silu_add(_p(x), _p(add), x.numel(), _p(out), _stream()), "cb_silu_add")
+    return out
+
+
+def image_to_u8(x: torch.Tensor) -> torch.Tensor:
+    """x: fp32 NHWC [N,H,W,C_ld>=3] in [-1,1] -> uint8 [N,H,W,3]."""
+    _need_cuda(x)
+    n, h, w, c_ld = x.shape
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device)
+    check(_lib.load().cb_image_to_u8(_p(x), n, h * w, c_ld, _p(out), _stream()), "cb_image_to_u8")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sampler steps (fp32 NCHW latents)
+# ------------------------------------------------------------------------------------------------------------------
+def cfg_scale_input(x: torch.Tensor, c_in: float) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    b = x.shape[0]
+    out = torch.empty((2 * b, *x.shape[1:]), dtype=torch.float32, device=x.device)
+    check(_lib.load().cb_cfg_scale_input(_p(x), x.numel() // b, b, c_in, _p(out), _stream()), "cb_cfg_scale_input")
+    return out
+
+
+def step_euler_ancestral(x, eps2, noise, cfg_scale, sigma, sigma_down, sigma_up, want_denoised=False):
+    _need_cuda(x, eps2, noise)
+    b = x.shape[0]
+    x_out = torch.empty_like(x)
+    den = torch.empty_like(x) if want_denoised else None
+    check(_lib.load().cb_step_euler_ancestral(_p(x), _p(eps2), _p(noise), x.numel() // b, b, cfg_scale, sigma,
+                                              sigma_down, sigma_up, _p(x_out), _p(den), _stream()),
+          "cb_step_euler_ancestral")
+    return x_out, den
+
+
+def step_dpmpp_2m(x, eps2, old_denoised, cfg_scale, sigma, ratio, em1, c_new, c_old):
+    _need_cuda(x, eps2, old_denoised)
+    b = x.shape[0]
+    x_out = torch.empty_like(x)
+    den = torch.empty_like(x)
+    check(_lib.load().cb_step_dpmpp_2m(_p(x), _p(eps2), _p(old_denoised), x.numel() // b, b, cfg_scale, sigma, ratio,
+                                       em1, c_new, c_old, _p(x_out), _p(den), _stream()), "cb_step_dpmpp_2m")
+    return x_out, den
+
+
+def step_ddim(x, eps2, noise, cfg_scale, sqrt_at, sqrt_one_minus_at, sqrt_aprev, dir_coef, sigma_t, want_x0=True):
+    _need_cuda(x, eps2, noise)
+    b = x.shape[0]
+    x_out = torch.empty_like(x)
+    x0 = torch.empty_like(x) if want_x0 else None
+    check(_lib.load().cb_step_ddim(_p(x), _p(eps2), _p(noise), x.numel() // b, b, cfg_scale, sqrt_at, sqrt_one_minus_at,
+                                   sqrt_aprev, dir_coef, sigma_t, _p(x_out), _p(x0), _stream()), "cb_step_ddim")
+    return x_out, x0

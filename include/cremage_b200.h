@@ -1,0 +1,162 @@
+/* cremage_b200 -- C ABI of the B200-native (sm_100a) Stable Diffusion denoising hot path.
+ *
+ * The reference (HowToSD/cremage) has no native boundary: its hot path is a tree of torch.nn modules selected by
+ * `target:` strings (ldm/util.py:81-96).  This header is the boundary the B200 implementation creates underneath
+ * those modules; each entry point names the reference operator(s) it replaces (paths relative to the reference
+ * root, `modules/` prefix omitted).  The Python mirror of the reference operator API lives in cremage_b200/ and
+ * binds these symbols with ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *  - every call enqueues work on `stream` and returns immediately (no synchronisation, no allocation ->
+ *    CUDA-graph capturable);
+ *  - return value: 0 = ok, negative = error (cb_last_error() gives a thread-local message);
+ *  - activations are NHWC bf16 ("pixel rows x channels"), statistics / latents / schedules are fp32.
+ */
+#ifndef CREMAGE_B200_H_
+#define CREMAGE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * library
+ * ------------------------------------------------------------------------------------------------------------- */
+const char* cb_last_error(void);
+int cb_version(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+int64_t cb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * implicit GEMM on tcgen05/TMEM, operands by TMA
+ *   replaces nn.Conv2d 3x3 / 1x1 and nn.Linear on the path:
+ *     ResBlock in_layers/out_layers/skip_connection   ldm/modules/diffusionmodules/openaimodel.py:205-245
+ *     Downsample.op / Upsample.conv                   openaimodel.py:111,155
+ *     SpatialTransformer.proj_in/proj_out             ldm/modules/attention.py:1017-1021,1048
+ *     CrossAttention to_q/to_k/to_v/to_out            ldm/modules/attention.py:571-578
+ *     GEGLU proj + FeedForward net[2]                 ldm/modules/attention.py:78,96,145
+ *     time_embed / emb_layers                         openaimodel.py:538-543,222-228
+ *     VAE Decoder convs, AttnBlock q/k/v/proj_out     ldm/modules/diffusionmodules/model.py:89-209,469-575
+ * ------------------------------------------------------------------------------------------------------------- */
+enum { CB_EPI_LINEAR = 0, CB_EPI_GEGLU = 1, CB_EPI_HEADS = 2 };
+enum { CB_ACT_NONE = 0, CB_ACT_SILU = 1 };
+
+typedef struct cb_igemm_desc {
+  /* A operand: one or two NHWC bf16 tensors [a_n][a_h][a_w][c] sharing the pixel grid; channels of source 1
+   * follow those of source 0 in the K order (the UNet skip concat).  A plain [M,K] matrix is n=h=1, w=M. */
+  const void* a0; int64_t c0; int64_t a0_ld; /* a0_ld: elements between pixels (0 = c0) */
+  const void* a1; int64_t c1; int64_t a1_ld;
+  int64_t a_n, a_h, a_w;
+  /* output pixel grid (rows = n*h*w) and its 128-row tile {tw, th, tn} */
+  int64_t n, h, w;
+  int tw, th, tn;
+  /* taps: A box of tap t is read at pixel offset (tap_dw, tap_dh, tap_dn)[t] from the output pixel */
+  int taps;
+  int tap_dw[9], tap_dh[9], tap_dn[9];
+  /* weights: bf16 [wgt_rows][taps * (ceil64(c0) + ceil64(c1))], K-major, zero padded */
+  const void* wgt; int64_t wgt_rows;
+  int64_t cout;          /* valid output columns (GEGLU: columns of the gated output = wgt_rows / 2) */
+  /* epilogue */
+  int mode;              /* CB_EPI_* */
+  int act;               /* CB_ACT_* applied after bias + rowbias, before the residual */
+  const float* bias;     /* [cout] fp32 or NULL (GEGLU: [2*cout], permuted like the weight rows) */
+  const float* rowbias;  /* [n][rowbias_ld] fp32 per-image bias (timestep embedding) or NULL */
+  int64_t rowbias_ld;
+  const void* residual;  /* bf16 [rows][res_ld] added last, or NULL */
+  int64_t res_ld;
+  void* out; int64_t out_ld; int out_f32; /* bf16 (0) or fp32 (1) output, row stride out_ld */
+  float out_scale;       /* multiplies the final value (0 = 1.0) */
+  /* CB_EPI_HEADS: column -> (which, head, j), row -> (batch, token); out[which][batch*heads+head][token][dpad] */
+  int heads_d, heads_dpad, heads_h, heads_tokens;
+  int64_t heads_which_stride;
+  /* tiling */
+  int bn;                /* N tile, multiple of 32, <= 256 */
+  int stages;            /* smem pipeline depth, 0 = auto */
+} cb_igemm_desc;
+
+int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * fused flash-style attention on tcgen05 (QK^T -> online softmax -> PV), replaces
+ *   CrossAttention / CrossAttentionOriginal / MemoryEfficientCrossAttention cores  ldm/modules/attention.py:418-423,646-657,811
+ * q,k,v: bf16 [bh][tokens][dpad] (dpad multiple of 64, pad columns zero); out: bf16 [b][nq][heads*d]
+ * ------------------------------------------------------------------------------------------------------------- */
+int cb_attention(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads, int64_t nq,
+                 int64_t nk, int d, int dpad, float scale, cudaStream_t stream);
+
+/* row softmax over fp32-scaled bf16 scores, in place: s[r][:] = softmax(scale * s[r][:]) (VAE AttnBlock,
+ * ldm/modules/diffusionmodules/model.py:196-198) */
+int cb_softmax_rows(void* s, int64_t rows, int64_t cols, int64_t ld, float scale, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) over NHWC bf16, fp32 statistics; replaces GroupNorm32+SiLU (ldm/modules/diffusionmodules/
+ * util.py:214-216, openaimodel.py:205-207,229-231), Normalize (attention.py:189, model.py:45) + nonlinearity
+ * (model.py:40-42).  Two sources = normalise the channel concat without materialising it.
+ *   stats: fp32 [n][groups][2] workspace (sum, sum of squares), zeroed by the call.
+ * ------------------------------------------------------------------------------------------------------------- */
+int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int64_t c1, int64_t n, int64_t hw, int groups,
+                      float eps, const float* gamma, const float* beta, int silu, void* out, float* stats,
+                      cudaStream_t stream);
+
+/* LayerNorm over the last dim of bf16 [rows][c] (nn.LayerNorm, ldm/modules/attention.py:900-902) */
+int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, const float* gamma, const float* beta, void* out,
+                 cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * layout / small elementwise kernels
+ * ------------------------------------------------------------------------------------------------------------- */
+/* NCHW (fp32, or fp16/bf16 when src_dtype = 1/2) -> NHWC bf16 with channel padding to c_pad (zeros), times scale */
+int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_t c, int64_t hw, int64_t c_pad, float scale,
+                    void* dst, cudaStream_t stream);
+/* NHWC (bf16, or fp32 when src_f32) [n][hw][c_ld] -> NCHW fp32 [n][c][hw], first c channels */
+int cb_nhwc_to_nchw_f32(const void* src, int src_f32, int64_t n, int64_t c, int64_t hw, int64_t c_ld, float* dst,
+                        cudaStream_t stream);
+/* nearest-neighbour 2x upsample NHWC bf16 (F.interpolate(scale_factor=2, 'nearest'), openaimodel.py:120, model.py:61) */
+int cb_upsample2x_nhwc(const void* src, int64_t n, int64_t h, int64_t w, int64_t c, void* dst, cudaStream_t stream);
+/* parity split for stride-2 convs: src [n][h][w][c] -> dst [2*ph+pw][n][h/2][w/2][c] */
+int cb_parity_split_nhwc(const void* src, int64_t n, int64_t h, int64_t w, int64_t c, void* dst, cudaStream_t stream);
+/* sinusoidal timestep embedding (ldm/modules/diffusionmodules/util.py:151-171): t fp32 [n], freqs fp32 [dim/2]
+ * (host-built with the reference's expression) -> bf16 [n][dim] = [cos(t*f) | sin(t*f)] */
+int cb_timestep_embedding(const float* t, int64_t n, int dim, const float* freqs, void* out, cudaStream_t stream);
+/* direct 3x3 conv for tiny channel counts (UNet conv_in 4->320, VAE conv_in 4->512): src NHWC bf16 [n][h][w][cin_ld],
+ * wgt fp32 [3][3][cin][cout], out NHWC bf16 */
+int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64_t w, int cin, int64_t cin_ld, const float* wgt,
+                         const float* bias, int64_t cout, void* out, cudaStream_t stream);
+/* y = silu(x) or y = silu(x + add) over bf16 vectors (SDXL label_emb path) */
+int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * sampler latent updates, fp32 NCHW latents, one launch per step.  `eps` is the CFG-doubled UNet output
+ * [2b][c][h][w] (uncond first: ldm/models/diffusion/ldm_wrapper_for_k_diffusion.py:67-99, ddim.py:538-561).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* x_in = x * c_in for both CFG halves: out [2b] <- x [b]   (k_diffusion/external.py:111-114) */
+int cb_cfg_scale_input(const float* x, int64_t per_batch, int64_t b, float c_in, float* out, cudaStream_t stream);
+/* Euler-ancestral (k_diffusion/sampling.py:147-163): denoised = x - sigma*(eu + s*(ec-eu));
+ *   x' = x + (x-denoised)/sigma*(sigma_down - sigma) + noise*sigma_up ; writes x_out (and denoised if non-null) */
+int cb_step_euler_ancestral(const float* x, const float* eps2, const float* noise, int64_t per_batch, int64_t b,
+                            float cfg_scale, float sigma, float sigma_down, float sigma_up, float* x_out,
+                            float* denoised_out, cudaStream_t stream);
+/* DPM++ 2M (k_diffusion/sampling.py:593-615): x' = ratio*x - em1*(c_new*denoised + c_old*old_denoised) */
+int cb_step_dpmpp_2m(const float* x, const float* eps2, const float* old_denoised, int64_t per_batch, int64_t b,
+                     float cfg_scale, float sigma, float ratio, float em1, float c_new, float c_old, float* x_out,
+                     float* denoised_out, cudaStream_t stream);
+/* DDIM (ldm/models/diffusion/ddim.py:590-611): e = eu + s*(ec-eu); pred_x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);
+ *   x' = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) e + sigma*noise */
+int cb_step_ddim(const float* x, const float* eps2, const float* noise, int64_t per_batch, int64_t b, float cfg_scale,
+                 float sqrt_at, float sqrt_one_minus_at, float sqrt_aprev, float dir_coef, float sigma_t, float* x_out,
+                 float* pred_x0_out, cudaStream_t stream);
+/* image post-process (sd/image_generator.py:1017-1018,1151-1152): NHWC fp32 [n][hw][c_ld] -> uint8 HWC [n][hw][3],
+ * clamp((x+1)/2,0,1)*255 truncated */
+int cb_image_to_u8(const void* src, int64_t n, int64_t hw, int64_t c_ld, uint8_t* dst, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CREMAGE_B200_H_ */
