@@ -47,7 +47,9 @@ SIGNATURES = {
     "cb_launch_count": [],
     "cb_igemm": [C.POINTER(IGemmDesc), _vp],
     "cb_attention": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp],
-    "cb_softmax_rows": [_vp, _i64, _i64, _i64, _f32, _vp],
+    "cb_softmax_rows": [_vp, _int, _i64, _vp, _i64, _i64, _i64, _f32, _vp],
+    "cb_pointwise_nchw_to_nhwc": [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _vp, _vp],
+    "cb_groupnorm_workspace_bytes": [_i64, _i64, _i64, _int],
     "cb_groupnorm_nhwc": [_vp, _i64, _vp, _i64, _i64, _i64, _int, _f32, _vp, _vp, _int, _vp, _vp, _vp],
     "cb_layernorm": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp],
     "cb_nchw_to_nhwc": [_vp, _int, _i64, _i64, _i64, _i64, _f32, _vp, _vp],
@@ -58,12 +60,14 @@ SIGNATURES = {
     "cb_conv3x3_small_cin": [_vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _i64, _vp, _vp],
     "cb_silu_add": [_vp, _vp, _i64, _vp, _vp],
     "cb_cfg_scale_input": [_vp, _i64, _i64, _f32, _vp, _vp],
-    "cb_step_euler_ancestral": [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
-    "cb_step_dpmpp_2m": [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
-    "cb_step_ddim": [_vp, _vp, _vp, _i64, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "cb_axpby_f32": [_vp, _f32, _vp, _f32, _i64, _vp, _vp],
+    "cb_cfg_mix_f32": [_vp, _vp, _f32, _i64, _vp, _vp],
+    "cb_step_euler_ancestral": [_vp, _vp, _vp, _int, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "cb_step_dpmpp_2m": [_vp, _vp, _vp, _int, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "cb_step_ddim": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
     "cb_image_to_u8": [_vp, _i64, _i64, _i64, _vp, _vp],
 }
-_RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64}
+_RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64, "cb_groupnorm_workspace_bytes": C.c_int64}
 
 
 def lib_path() -> Path:

@@ -21,6 +21,27 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, long long n, int 
   }
 }
 
+// 1x1 channel mix (tiny c, cout <= 16) fused with NCHW fp32 -> NHWC bf16. One thread per (n, pixel).
+__global__ void pointwise_nchw_to_nhwc_kernel(const float* __restrict__ src, long long n, int c, long long hw,
+                                              const float* __restrict__ w, const float* __restrict__ b, int cout,
+                                              int c_pad, float scale, __nv_bfloat16* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * hw) return;
+  const long long bi = i / hw, p = i - bi * hw;
+  const float* s = src + bi * c * hw + p;
+  float xin[16];
+  for (int ci = 0; ci < c; ++ci) xin[ci] = s[(long long)ci * hw] * scale;
+  __nv_bfloat16* d = dst + i * c_pad;
+  for (int co = 0; co < c_pad; ++co) {
+    float acc = 0.f;
+    if (co < cout) {
+      acc = b ? b[co] : 0.f;
+      for (int ci = 0; ci < c; ++ci) acc = fmaf(w[co * c + ci], xin[ci], acc);
+    }
+    d[co] = __float2bfloat16(acc);
+  }
+}
+
 // generic tiled transpose for wide channel counts: [n][c][hw] -> [n][hw][c_pad]
 template <typename T>
 __global__ void nchw_to_nhwc_tiled_kernel(const T* __restrict__ src, int c, long long hw, int c_pad, float scale,
@@ -195,6 +216,18 @@ extern "C" int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_
     else if (src_dtype == 1) nchw_to_nhwc_tiled_kernel<__half><<<grid, block, 0, stream>>>((const __half*)src, (int)c, hw, (int)c_pad, scale, D);
     else nchw_to_nhwc_tiled_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (int)c, hw, (int)c_pad, scale, D);
   }
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_pointwise_nchw_to_nhwc(const float* src, int64_t n, int64_t c, int64_t hw, const float* w,
+                                         const float* b, int64_t cout, int64_t c_pad, float scale, void* dst,
+                                         cudaStream_t stream) {
+  CB_REQUIRE(src && w && dst && n > 0 && hw > 0, "cb_pointwise_nchw_to_nhwc: bad arguments");
+  CB_REQUIRE(c > 0 && c <= 16 && cout > 0 && cout <= c_pad && c_pad <= 16, "cb_pointwise_nchw_to_nhwc: c, cout, c_pad must be <= 16");
+  const long long total = n * hw;
+  pointwise_nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, n, (int)c, hw, w, b, (int)cout, (int)c_pad, scale, (__nv_bfloat16*)dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

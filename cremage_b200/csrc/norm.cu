@@ -27,21 +27,25 @@ CB_DEVINL void unpack8(const Vec8& v, float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// GroupNorm pass 1: per-(image, group) sum and sum of squares.
+// GroupNorm pass 1: per-(image, group) sum and sum of squares -- DETERMINISTIC (no floating-point atomics):
 // grid = (splits, n); block = CV * P threads where CV = C/8 channel vectors; a thread keeps a FIXED channel vector
-// and walks pixels p0 + lane_p, +P, ... so it accumulates 8 per-channel sums in registers.
+// and walks pixels p0 + lane_p, +P, ... accumulating 8 per-channel sums in registers; the CTA reduces them per group
+// in a fixed order and writes one partial per (image, split, group); the last CTA of an image to finish (ticket
+// counter) folds the partials in split order into stats[n][group][2].
 // ------------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1,
                                 int c1, long long hw, int groups, int P, long long pix_per_cta,
-                                float* __restrict__ stats) {
-  extern __shared__ float s_acc[];  // [2][C]
+                                float* __restrict__ stats, float* __restrict__ partials,
+                                unsigned int* __restrict__ counters) {
+  extern __shared__ float s_part[];  // [2][P][C]
+  __shared__ int s_is_last;
   const int C = c0 + c1;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
   const int lp = threadIdx.x / CV;
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+  const int splits = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;  // blockDim % 32 == 0
 
   const int c = cv << 3;
   const __nv_bfloat16* src;
@@ -52,6 +56,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
   const long long p_begin = (long long)blockIdx.x * pix_per_cta;
   long long p_end = p_begin + pix_per_cta;
   if (p_end > hw) p_end = hw;
+  if (lp >= P) p_end = p_begin;  // block is padded to whole warps; the padding threads only help reduce
 
   float s[8], q[8];
 #pragma unroll
@@ -76,19 +81,51 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
   }
+  if (lp < P) {
+    float* sp_s = s_part + (long long)lp * C + c;
+    float* sp_q = s_part + (long long)(P + lp) * C + c;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    atomicAdd(&s_acc[c + i], s[i]);
-    atomicAdd(&s_acc[C + c + i], q[i]);
+    for (int i = 0; i < 8; ++i) { sp_s[i] = s[i]; sp_q[i] = q[i]; }
   }
   __syncthreads();
+  // per group: a warp sums the gs*P per-channel partials lane-strided, then a fixed-order shuffle tree
   const int gs = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  float* my_partials = partials + ((long long)n * splits + blockIdx.x) * groups * 2;
+  for (int g = warp; g < groups; g += nwarps) {
     float a = 0.f, b = 0.f;
-    for (int i = 0; i < gs; ++i) { a += s_acc[g * gs + i]; b += s_acc[C + g * gs + i]; }
-    atomicAdd(&stats[((long long)n * groups + g) * 2 + 0], a);
-    atomicAdd(&stats[((long long)n * groups + g) * 2 + 1], b);
+    for (int e = lane; e < gs * P; e += 32) {
+      const int l = e / gs, ch = g * gs + (e - l * gs);
+      a += s_part[(long long)l * C + ch];
+      b += s_part[(long long)(P + l) * C + ch];
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) { my_partials[g * 2] = a; my_partials[g * 2 + 1] = b; }
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&counters[n], 1u);
+    s_is_last = (ticket == (unsigned int)splits - 1u);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  const float* img_partials = partials + (long long)n * splits * groups * 2;
+  for (int g = warp; g < groups; g += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int sp = lane; sp < splits; sp += 32) {
+      a += __ldcg(img_partials + ((long long)sp * groups + g) * 2);
+      b += __ldcg(img_partials + ((long long)sp * groups + g) * 2 + 1);
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      stats[((long long)n * groups + g) * 2 + 0] = a;
+      stats[((long long)n * groups + g) * 2 + 1] = b;
+    }
+  }
+  if (threadIdx.x == 0) counters[n] = 0u;  // self-reset for the next call
 }
 
 // GroupNorm pass 2: y = silu?((x - mean) * rstd * gamma + beta) -> bf16 [n][hw][C]
@@ -101,6 +138,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
   const int cv = threadIdx.x % CV;
   const int lp = threadIdx.x / CV;
   const int n = blockIdx.y;
+  if (lp >= P) return;  // padding threads of the warp-rounded block
   const int c = cv << 3;
   const int gs = C / groups;
   const float inv_cnt = 1.f / (float(gs) * float(hw));
@@ -210,19 +248,32 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Row softmax (in place, bf16 storage, fp32 math); one CTA per row, the row is staged in shared memory.
+// Row softmax: dst[r][:] = softmax(scale * src[r][:]), src fp32 or bf16, dst bf16 (may alias a bf16 src), fp32 math;
+// one CTA per row, the row is staged in shared memory.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void softmax_rows_kernel(__nv_bfloat16* __restrict__ s, long long cols, long long ld, float scale) {
+template <bool SRC_F32>
+__global__ void softmax_rows_kernel(const void* __restrict__ src, long long src_ld, __nv_bfloat16* __restrict__ dst,
+                                    long long dst_ld, long long cols, float scale) {
   extern __shared__ float s_row[];
   __shared__ float red[32];
-  __nv_bfloat16* row = s + (long long)blockIdx.x * ld;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   float m = -INFINITY;
-  for (long long v = tid; v < (cols >> 3); v += blockDim.x) {
-    float f[8];
-    unpack8(ld_vec8(row + v * 8), f);
+  if (SRC_F32) {
+    const float* row = reinterpret_cast<const float*>(src) + (long long)blockIdx.x * src_ld;
+    for (long long v = tid; v < (cols >> 2); v += blockDim.x) {
+      const float4 t = *reinterpret_cast<const float4*>(row + v * 4);
+      const float f[4] = {t.x * scale, t.y * scale, t.z * scale, t.w * scale};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { f[e] *= scale; s_row[v * 8 + e] = f[e]; m = fmaxf(m, f[e]); }
+      for (int e = 0; e < 4; ++e) { s_row[v * 4 + e] = f[e]; m = fmaxf(m, f[e]); }
+    }
+  } else {
+    const __nv_bfloat16* row = reinterpret_cast<const __nv_bfloat16*>(src) + (long long)blockIdx.x * src_ld;
+    for (long long v = tid; v < (cols >> 3); v += blockDim.x) {
+      float f[8];
+      unpack8(ld_vec8(row + v * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { f[e] *= scale; s_row[v * 8 + e] = f[e]; m = fmaxf(m, f[e]); }
+    }
   }
   m = warp_max(m);
   if (lane == 0) red[warp] = m;
@@ -242,17 +293,49 @@ __global__ void softmax_rows_kernel(__nv_bfloat16* __restrict__ s, long long col
   sum = 0.f;
   for (int i = 0; i < nw; ++i) sum += red[i];
   const float inv = 1.f / sum;
+  __nv_bfloat16* orow = dst + (long long)blockIdx.x * dst_ld;
   for (long long v = tid; v < (cols >> 3); v += blockDim.x) {
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = s_row[v * 8 + e] * inv;
-    st_vec8(row + v * 8, f);
+    st_vec8(orow + v * 8, f);
   }
 }
 
 }  // namespace cb
 
 using namespace cb;
+
+namespace {
+struct GnPlan { int CV, P, threads; long long splits, pix_per_cta; size_t smem; };
+GnPlan gn_plan(int64_t n, int64_t hw, int64_t C) {
+  GnPlan g;
+  g.CV = int(C / 8);
+  g.P = 384 / g.CV;
+  if (g.P < 1) g.P = 1;
+  if ((int64_t)g.P > hw) g.P = (int)hw;
+  g.threads = (g.CV * g.P + 31) / 32 * 32;  // whole warps: the reductions shuffle with a full mask
+  // enough CTAs to fill 148 SMs a few times over, at least ~8 pixels per thread-lane when the image is large
+  long long splits = (148LL * 4 + n - 1) / n;
+  long long max_splits = (hw + (long long)g.P * 8 - 1) / ((long long)g.P * 8);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  long long ppc = (hw + splits - 1) / splits;
+  ppc = ((ppc + g.P - 1) / g.P) * g.P;
+  g.splits = (hw + ppc - 1) / ppc;
+  g.pix_per_cta = ppc;
+  g.smem = sizeof(float) * 2 * (size_t)g.P * (size_t)C;
+  return g;
+}
+size_t gn_ws_floats(const GnPlan& g, int64_t n, int groups) {
+  return (size_t)n * groups * 2 + (size_t)n * g.splits * groups * 2 + (size_t)n;
+}
+}  // namespace
+
+extern "C" int64_t cb_groupnorm_workspace_bytes(int64_t c, int64_t n, int64_t hw, int groups) {
+  if (c <= 0 || n <= 0 || hw <= 0 || groups <= 0 || c % 8) return 0;
+  return (int64_t)(gn_ws_floats(gn_plan(n, hw, c), n, groups) * sizeof(float));
+}
 
 extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int64_t c1, int64_t n, int64_t hw,
                                  int groups, float eps, const float* gamma, const float* beta, int silu, void* out,
@@ -263,29 +346,25 @@ extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int
   CB_REQUIRE(c1 == 0 || x1, "cb_groupnorm_nhwc: c1 > 0 but x1 is null");
   CB_REQUIRE(groups > 0 && C % groups == 0, "cb_groupnorm_nhwc: %lld channels not divisible into %d groups", (long long)C, groups);
   CB_REQUIRE(n > 0 && hw > 0, "cb_groupnorm_nhwc: empty input");
-  const int CV = int(C / 8);
-  CB_REQUIRE(CV <= 1024, "cb_groupnorm_nhwc: more than 8192 channels unsupported");
-  int P = 384 / CV;
-  if (P < 1) P = 1;
-  if ((int64_t)P > hw) P = (int)hw;
-  const int threads = CV * P;
-  // enough CTAs to fill 148 SMs a few times over, at least ~32 pixels per thread-lane when the image is large
-  long long splits = (148LL * 4 + n - 1) / n;
-  long long max_splits = (hw + (long long)P * 8 - 1) / ((long long)P * 8);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  long long pix_per_cta = (hw + splits - 1) / splits;
-  pix_per_cta = ((pix_per_cta + P - 1) / P) * P;
-  splits = (hw + pix_per_cta - 1) / pix_per_cta;
-  CB_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * groups * n, stream));
-  dim3 grid((unsigned)splits, (unsigned)n);
-  const size_t smem = sizeof(float) * 2 * C;
-  gn_stats_kernel<<<grid, threads, smem, stream>>>((const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1, (int)c1,
-                                                   hw, groups, P, pix_per_cta, stats);
+  CB_REQUIRE(C / 8 <= 1024, "cb_groupnorm_nhwc: more than 8192 channels unsupported");
+  const GnPlan g = gn_plan(n, hw, C);
+  CB_REQUIRE(g.smem <= 160 * 1024, "cb_groupnorm_nhwc: needs %zu bytes of shared memory", g.smem);
+  // workspace: [n][groups][2] final sums | [n][splits][groups][2] partials | [n] ticket counters
+  float* partials = stats + (size_t)n * groups * 2;
+  unsigned int* counters = reinterpret_cast<unsigned int*>(partials + (size_t)n * g.splits * groups * 2);
+  CB_CHECK_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * n, stream));
+  static thread_local bool configured = false;
+  if (!configured) {
+    CB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
+  dim3 grid((unsigned)g.splits, (unsigned)n);
+  gn_stats_kernel<<<grid, g.threads, g.smem, stream>>>((const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1,
+                                                       (int)c1, hw, groups, g.P, g.pix_per_cta, stats, partials, counters);
   CB_CHECK_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<grid, threads, 0, stream>>>((const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1, (int)c1, hw,
-                                                groups, P, pix_per_cta, eps, gamma, beta, silu, stats,
-                                                (__nv_bfloat16*)out);
+  gn_apply_kernel<<<grid, g.threads, 0, stream>>>((const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1, (int)c1, hw,
+                                                  groups, g.P, g.pix_per_cta, eps, gamma, beta, silu, stats,
+                                                  (__nv_bfloat16*)out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(2);
   return CB_OK;
@@ -310,17 +389,20 @@ extern "C" int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, c
   return CB_OK;
 }
 
-extern "C" int cb_softmax_rows(void* s, int64_t rows, int64_t cols, int64_t ld, float scale, cudaStream_t stream) {
-  CB_REQUIRE(s, "cb_softmax_rows: null pointer");
+extern "C" int cb_softmax_rows(const void* src, int src_f32, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
+                               int64_t cols, float scale, cudaStream_t stream) {
+  CB_REQUIRE(src && dst, "cb_softmax_rows: null pointer");
   CB_REQUIRE(cols > 0 && cols % 8 == 0 && cols <= 48 * 1024, "cb_softmax_rows: cols %lld unsupported (multiple of 8, <= 49152)", (long long)cols);
-  CB_REQUIRE(ld % 8 == 0 && ld >= cols && rows > 0, "cb_softmax_rows: bad ld / rows");
+  CB_REQUIRE(src_ld % 8 == 0 && dst_ld % 8 == 0 && src_ld >= cols && dst_ld >= cols && rows > 0, "cb_softmax_rows: bad ld / rows");
   const size_t smem = sizeof(float) * cols;
   static thread_local bool configured = false;
   if (!configured) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  softmax_rows_kernel<<<(unsigned)rows, 256, smem, stream>>>((__nv_bfloat16*)s, cols, ld, scale);
+  if (src_f32) softmax_rows_kernel<true><<<(unsigned)rows, 256, smem, stream>>>(src, src_ld, (__nv_bfloat16*)dst, dst_ld, cols, scale);
+  else softmax_rows_kernel<false><<<(unsigned)rows, 256, smem, stream>>>(src, src_ld, (__nv_bfloat16*)dst, dst_ld, cols, scale);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

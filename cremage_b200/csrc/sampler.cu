@@ -21,16 +21,40 @@ __global__ void cfg_scale_input_kernel(const float4* __restrict__ x, long long n
   }
 }
 
-struct EulerA { float cfg, sigma, sigma_down, sigma_up; };
-__global__ void step_euler_ancestral_kernel(const float* __restrict__ x, const float* __restrict__ eps2,
-                                            const float* __restrict__ noise, long long total, EulerA a,
-                                            float* __restrict__ x_out, float* __restrict__ den_out) {
+// out = a * x + b * y (y may be null)
+__global__ void axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float b, long long total,
+                             float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    out[i] = y ? (a * x[i] + b * y[i]) : a * x[i];
+}
+
+// out = u + s * (c - u)
+__global__ void cfg_mix_kernel(const float* __restrict__ u, const float* __restrict__ c, float s, long long total,
+                               float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float uu = u[i];
+    out[i] = uu + s * (c[i] - uu);
+  }
+}
+
+// guided denoised prediction from the two eps halves, or pass-through when `a` already is the denoised tensor
+__device__ __forceinline__ float guided_denoised(float xv, const float* a, const float* b, long long i, float cfg,
+                                                 float sigma, int is_denoised) {
+  if (is_denoised) return a[i];
+  // CompVisDenoiser on each half: denoised = input + eps * c_out, c_out = -sigma
+  const float du = xv + a[i] * (-sigma);
+  const float dc = xv + b[i] * (-sigma);
+  return du + cfg * (dc - du);
+}
+
+struct EulerA { float cfg, sigma, sigma_down, sigma_up; int is_denoised; };
+__global__ void step_euler_ancestral_kernel(const float* __restrict__ x, const float* __restrict__ eu,
+                                            const float* __restrict__ ec, const float* __restrict__ noise,
+                                            long long total, EulerA a, float* __restrict__ x_out,
+                                            float* __restrict__ den_out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float xv = x[i];
-    // CompVisDenoiser on each half: denoised = input + eps * c_out, c_out = -sigma
-    const float du = xv + eps2[i] * (-a.sigma);
-    const float dc = xv + eps2[total + i] * (-a.sigma);
-    const float den = du + a.cfg * (dc - du);
+    const float den = guided_denoised(xv, eu, ec, i, a.cfg, a.sigma, a.is_denoised);
     const float d = (xv - den) / a.sigma;
     float xn = xv + d * (a.sigma_down - a.sigma);
     if (noise) xn = xn + noise[i] * a.sigma_up;
@@ -39,15 +63,13 @@ __global__ void step_euler_ancestral_kernel(const float* __restrict__ x, const f
   }
 }
 
-struct Dpm2m { float cfg, sigma, ratio, em1, c_new, c_old; };
-__global__ void step_dpmpp_2m_kernel(const float* __restrict__ x, const float* __restrict__ eps2,
-                                     const float* __restrict__ old_den, long long total, Dpm2m a,
-                                     float* __restrict__ x_out, float* __restrict__ den_out) {
+struct Dpm2m { float cfg, sigma, ratio, em1, c_new, c_old; int is_denoised; };
+__global__ void step_dpmpp_2m_kernel(const float* __restrict__ x, const float* __restrict__ eu,
+                                     const float* __restrict__ ec, const float* __restrict__ old_den, long long total,
+                                     Dpm2m a, float* __restrict__ x_out, float* __restrict__ den_out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float xv = x[i];
-    const float du = xv + eps2[i] * (-a.sigma);
-    const float dc = xv + eps2[total + i] * (-a.sigma);
-    const float den = du + a.cfg * (dc - du);
+    const float den = guided_denoised(xv, eu, ec, i, a.cfg, a.sigma, a.is_denoised);
     float dd = den;
     if (old_den) dd = a.c_new * den - a.c_old * old_den[i];
     x_out[i] = a.ratio * xv - a.em1 * dd;
@@ -56,17 +78,17 @@ __global__ void step_dpmpp_2m_kernel(const float* __restrict__ x, const float* _
 }
 
 struct Ddim { float cfg, sqrt_at, sqrt_1mat, sqrt_aprev, dir_coef, sigma_t; };
-__global__ void step_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps2,
+__global__ void step_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eu, const float* __restrict__ ec,
                                  const float* __restrict__ noise, long long total, Ddim a, float* __restrict__ x_out,
                                  float* __restrict__ x0_out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float xv = x[i];
-    const float eu = eps2[i], ec = eps2[total + i];
-    const float e = eu + a.cfg * (ec - eu);
+    const float u = eu[i];
+    const float e = u + a.cfg * (ec[i] - u);
     const float pred_x0 = (xv - a.sqrt_1mat * e) / a.sqrt_at;
     const float dir = a.dir_coef * e;
     float xn = a.sqrt_aprev * pred_x0 + dir;
-    // reference adds sigma_t * noise unconditionally (zero when eta == 0)
+    // the reference adds sigma_t * noise unconditionally (identically zero when eta == 0)
     xn = xn + (noise ? a.sigma_t * noise[i] : 0.f);
     x_out[i] = xn;
     if (x0_out) x0_out[i] = pred_x0;
@@ -95,37 +117,54 @@ extern "C" int cb_cfg_scale_input(const float* x, int64_t per_batch, int64_t b, 
   return CB_OK;
 }
 
-extern "C" int cb_step_euler_ancestral(const float* x, const float* eps2, const float* noise, int64_t per_batch,
-                                       int64_t b, float cfg_scale, float sigma, float sigma_down, float sigma_up,
-                                       float* x_out, float* denoised_out, cudaStream_t stream) {
-  CB_REQUIRE(x && eps2 && x_out && per_batch > 0 && b > 0, "cb_step_euler_ancestral: bad arguments");
-  const long long total = per_batch * b;
-  EulerA a{cfg_scale, sigma, sigma_down, sigma_up};
-  step_euler_ancestral_kernel<<<ew_grid(total), 256, 0, stream>>>(x, eps2, noise, total, a, x_out, denoised_out);
+extern "C" int cb_axpby_f32(const float* x, float a, const float* y, float b, int64_t count, float* out,
+                            cudaStream_t stream) {
+  CB_REQUIRE(x && out && count > 0, "cb_axpby_f32: bad arguments");
+  axpby_kernel<<<ew_grid(count), 256, 0, stream>>>(x, a, y, b, count, out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
 }
 
-extern "C" int cb_step_dpmpp_2m(const float* x, const float* eps2, const float* old_denoised, int64_t per_batch,
-                                int64_t b, float cfg_scale, float sigma, float ratio, float em1, float c_new,
-                                float c_old, float* x_out, float* denoised_out, cudaStream_t stream) {
-  CB_REQUIRE(x && eps2 && x_out && per_batch > 0 && b > 0, "cb_step_dpmpp_2m: bad arguments");
-  const long long total = per_batch * b;
-  Dpm2m a{cfg_scale, sigma, ratio, em1, c_new, c_old};
-  step_dpmpp_2m_kernel<<<ew_grid(total), 256, 0, stream>>>(x, eps2, old_denoised, total, a, x_out, denoised_out);
+extern "C" int cb_cfg_mix_f32(const float* uncond, const float* cond, float scale, int64_t count, float* out,
+                              cudaStream_t stream) {
+  CB_REQUIRE(uncond && cond && out && count > 0, "cb_cfg_mix_f32: bad arguments");
+  cfg_mix_kernel<<<ew_grid(count), 256, 0, stream>>>(uncond, cond, scale, count, out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
 }
 
-extern "C" int cb_step_ddim(const float* x, const float* eps2, const float* noise, int64_t per_batch, int64_t b,
+extern "C" int cb_step_euler_ancestral(const float* x, const float* eps_u, const float* eps_c, int is_denoised,
+                                       const float* noise, int64_t count, float cfg_scale, float sigma,
+                                       float sigma_down, float sigma_up, float* x_out, float* denoised_out,
+                                       cudaStream_t stream) {
+  CB_REQUIRE(x && eps_u && x_out && count > 0 && (is_denoised || eps_c), "cb_step_euler_ancestral: bad arguments");
+  EulerA a{cfg_scale, sigma, sigma_down, sigma_up, is_denoised};
+  step_euler_ancestral_kernel<<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, noise, count, a, x_out, denoised_out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_step_dpmpp_2m(const float* x, const float* eps_u, const float* eps_c, int is_denoised,
+                                const float* old_denoised, int64_t count, float cfg_scale, float sigma, float ratio,
+                                float em1, float c_new, float c_old, float* x_out, float* denoised_out,
+                                cudaStream_t stream) {
+  CB_REQUIRE(x && eps_u && x_out && count > 0 && (is_denoised || eps_c), "cb_step_dpmpp_2m: bad arguments");
+  Dpm2m a{cfg_scale, sigma, ratio, em1, c_new, c_old, is_denoised};
+  step_dpmpp_2m_kernel<<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, old_denoised, count, a, x_out, denoised_out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_step_ddim(const float* x, const float* eps_u, const float* eps_c, const float* noise, int64_t count,
                             float cfg_scale, float sqrt_at, float sqrt_one_minus_at, float sqrt_aprev, float dir_coef,
                             float sigma_t, float* x_out, float* pred_x0_out, cudaStream_t stream) {
-  CB_REQUIRE(x && eps2 && x_out && per_batch > 0 && b > 0, "cb_step_ddim: bad arguments");
-  const long long total = per_batch * b;
+  CB_REQUIRE(x && eps_u && eps_c && x_out && count > 0, "cb_step_ddim: bad arguments");
   Ddim a{cfg_scale, sqrt_at, sqrt_one_minus_at, sqrt_aprev, dir_coef, sigma_t};
-  step_ddim_kernel<<<ew_grid(total), 256, 0, stream>>>(x, eps2, noise, total, a, x_out, pred_x0_out);
+  step_ddim_kernel<<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, noise, count, a, x_out, pred_x0_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

@@ -1,0 +1,262 @@
+"""Drop-in mirror of the reference's `ldm.modules.attention` for the denoising path, running on the sm_100a kernels.
+
+Same class names, constructor arguments, parameter (state-dict) names and forward signatures as
+`modules/ldm/modules/attention.py` in HowToSD/cremage:
+  CrossAttention (:265; CrossAttentionOriginal :537 and MemoryEfficientCrossAttention :696 are aliases -- all three
+  compute softmax(q k^T / sqrt(d)) v), GEGLU (:57) / GEGLU_with_lora (:66), FeedForward (:119),
+  BasicTransformerBlock (:862), SpatialTransformer (:915).
+LoRA side branches and IP-adapter tokens are constructor-compatible but must be empty (they are no-ops in the
+reference when `lora_ranks=[]`, `ipa_num_tokens=0`); anything else raises instead of silently falling back.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...engine import BF16, PackedModule, f32, head_pad, packw, require_cuda, zero_workspace
+
+GEGLU_BN = 128  # N tile of the fused GEGLU projection (x / gate rows interleaved per 64 output columns)
+
+
+def _check_extras(lora_ranks, ipa_num_tokens):
+    if lora_ranks:
+        raise NotImplementedError("cremage_b200: LoRA side branches are not implemented; merge LoRA deltas into the "
+                                  "base weights before loading (lora_ranks must be empty)")
+    if ipa_num_tokens:
+        raise NotImplementedError("cremage_b200: IP-Adapter tokens are not implemented (ipa_num_tokens must be 0)")
+
+
+def Normalize(in_channels):
+    """attention.py:189 -- GroupNorm(32, eps=1e-6, affine)."""
+    return nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+
+
+class GEGLU(nn.Module):
+    """Parameter container for `ff.net.0.proj` (attention.py:57-62,66-96); computed fused inside FeedForward."""
+
+    def __init__(self, dim_in, dim_out, lora_ranks: List[int] = None, lora_weights: List[float] = None):
+        super().__init__()
+        _check_extras(lora_ranks, 0)
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+GEGLU_with_lora = GEGLU
+
+
+class FeedForward(PackedModule):
+    """attention.py:119-168: Linear(d, 8d) -> x * gelu(gate) -> Linear(4d, d). Only the gated (glu=True) form is on
+    the path (BasicTransformerBlock passes gated_ff=True)."""
+
+    def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0., lora_ranks: List[int] = None,
+                 lora_weights: List[float] = None):
+        super().__init__()
+        _check_extras(lora_ranks, 0)
+        if not glu:
+            raise NotImplementedError("cremage_b200: FeedForward without GEGLU is not on the SD path")
+        inner_dim = int(dim * mult)
+        dim_out = dim if dim_out is None else dim_out
+        self.dim, self.inner_dim, self.dim_out = dim, inner_dim, dim_out
+        self.net = nn.ModuleList([GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out)])
+
+    def _pack(self, device):
+        wq, bq = ops.pack_geglu(self.net[0].proj.weight.to(device).float(), self.net[0].proj.bias.to(device).float(),
+                                GEGLU_BN)
+        return {"w1": ops.pack_weight(wq), "b1": bq.contiguous(),
+                "w2": packw(self.net[2].weight, device), "b2": f32(self.net[2].bias, device)}
+
+    def _run(self, x2d: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        p = self.packed(x2d.device)
+        h = ops.igemm(x2d, p["w1"], self.inner_dim, bias=p["b1"], mode=ops.EPI_GEGLU, bn=GEGLU_BN)
+        return ops.igemm(h, p["w2"], self.dim_out, bias=p["b2"], residual=residual)
+
+    def forward(self, x):
+        require_cuda(x, "FeedForward.forward")
+        shp = x.shape
+        y = self._run(x.reshape(-1, shp[-1]).to(BF16).contiguous())
+        return y.view(*shp[:-1], self.dim_out).to(x.dtype)
+
+
+class CrossAttention(PackedModule):
+    """attention.py:265-534 / :537-693 / :696-861. q/k/v projections write the per-head padded layout straight from
+    the GEMM epilogue; the core is one fused flash-style kernel; to_out fuses bias (+ the block residual)."""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0., lora_ranks: List[int] = None,
+                 lora_weights: List[float] = None, ipa_scale=1.0, ipa_num_tokens=0):
+        super().__init__()
+        _check_extras(lora_ranks, ipa_num_tokens)
+        inner_dim = dim_head * heads
+        self.is_self = context_dim is None
+        context_dim = query_dim if context_dim is None else context_dim
+        if dim_head % 8 != 0 or dim_head > 192:
+            raise ValueError(f"cremage_b200: head dim {dim_head} unsupported (multiple of 8, <= 192)")
+        self.query_dim, self.context_dim, self.inner_dim = query_dim, context_dim, inner_dim
+        self.scale = dim_head ** -0.5
+        self.heads, self.dim_head = heads, dim_head
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+
+    def _pack(self, device):
+        p = {"wq": packw(self.to_q.weight, device),
+             "wkv": packw(torch.cat([self.to_k.weight, self.to_v.weight], 0), device),
+             "wo": packw(self.to_out[0].weight, device), "bo": f32(self.to_out[0].bias, device)}
+        if self.context_dim == self.query_dim:
+            p["wqkv"] = packw(torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0), device)
+        return p
+
+    def _run(self, x2d: torch.Tensor, batch: int, nq: int, ctx2d: Optional[torch.Tensor], nk: int,
+             residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x2d: bf16 [batch*nq, query_dim]; ctx2d: bf16 [batch*nk, context_dim] or None for self-attention."""
+        p = self.packed(x2d.device)
+        h, d = self.heads, self.dim_head
+        dpad = head_pad(d)
+        dev = x2d.device
+        if ctx2d is None:
+            if "wqkv" not in p:
+                raise ValueError("self-attention requested on a CrossAttention built with a different context_dim")
+            nk = nq
+            qkv = zero_workspace("qkv", (3, batch * h, nq, dpad), dev)
+            ops.igemm(x2d, p["wqkv"], 3 * self.inner_dim, mode=ops.EPI_HEADS, out=qkv,
+                      heads=(d, dpad, h, nq, batch * h * nq * dpad))
+            q, k, v = qkv[0], qkv[1], qkv[2]
+        else:
+            qb = zero_workspace("q", (1, batch * h, nq, dpad), dev)
+            kv = zero_workspace("kv", (2, batch * h, nk, dpad), dev)
+            ops.igemm(x2d, p["wq"], self.inner_dim, mode=ops.EPI_HEADS, out=qb, heads=(d, dpad, h, nq, 0))
+            ops.igemm(ctx2d, p["wkv"], 2 * self.inner_dim, mode=ops.EPI_HEADS, out=kv,
+                      heads=(d, dpad, h, nk, batch * h * nk * dpad))
+            q, k, v = qb[0], kv[0], kv[1]
+        a = ops.attention(q, k, v, batch, h, nq, nk, d, dpad, self.scale)
+        return ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
+
+    def forward(self, x, context=None, mask=None):
+        require_cuda(x, "CrossAttention.forward")
+        if mask is not None:
+            raise NotImplementedError("cremage_b200: attention masks are not used on the SD path")
+        b, n, _ = x.shape
+        x2d = x.reshape(b * n, -1).to(BF16).contiguous()
+        ctx2d, nk = None, n
+        if context is not None:
+            nk = context.shape[1]
+            ctx2d = context.reshape(b * nk, -1).to(BF16).contiguous()
+        elif not self.is_self and self.context_dim != self.query_dim:
+            raise ValueError("context is required for this CrossAttention")
+        return self._run(x2d, b, n, ctx2d, nk).view(b, n, self.query_dim).to(x.dtype)
+
+
+CrossAttentionOriginal = CrossAttention
+MemoryEfficientCrossAttention = CrossAttention
+
+
+class BasicTransformerBlock(PackedModule):
+    """attention.py:862-912: x = attn1(LN1 x) + x; x = attn2(LN2 x, ctx) + x; x = ff(LN3 x) + x (LayerNorm eps 1e-5)."""
+
+    def __init__(self, dim, n_heads, d_head, dropout=0., context_dim=None, gated_ff=True, checkpoint=True,
+                 disable_self_attn=False, lora_ranks: List[int] = None, lora_weights: List[float] = None, ipa_scale=1.0,
+                 ipa_num_tokens=0):
+        super().__init__()
+        _check_extras(lora_ranks, ipa_num_tokens)
+        self.disable_self_attn = disable_self_attn
+        self.attn1 = CrossAttention(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout,
+                                    context_dim=context_dim if self.disable_self_attn else None)
+        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
+        self.attn2 = CrossAttention(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
+                                    dropout=dropout)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.checkpoint = checkpoint
+        self.dim = dim
+
+    def _own_params(self):
+        return [self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias, self.norm3.weight,
+                self.norm3.bias]
+
+    def _pack(self, device):
+        return {f"n{i}{k[0]}": f32(getattr(getattr(self, f"norm{i}"), k), device)
+                for i in (1, 2, 3) for k in ("weight", "bias")}
+
+    def _run(self, x2d: torch.Tensor, batch: int, n: int, ctx2d: Optional[torch.Tensor], nk: int) -> torch.Tensor:
+        p = self.packed(x2d.device)
+        h = ops.layernorm(x2d, p["n1w"], p["n1b"], self.norm1.eps)
+        if self.disable_self_attn:
+            x2d = self.attn1._run(h, batch, n, ctx2d, nk, residual=x2d)
+        else:
+            x2d = self.attn1._run(h, batch, n, None, n, residual=x2d)
+        h = ops.layernorm(x2d, p["n2w"], p["n2b"], self.norm2.eps)
+        x2d = self.attn2._run(h, batch, n, ctx2d, nk, residual=x2d)
+        h = ops.layernorm(x2d, p["n3w"], p["n3b"], self.norm3.eps)
+        return self.ff._run(h, residual=x2d)
+
+    def forward(self, x, context=None):
+        require_cuda(x, "BasicTransformerBlock.forward")
+        b, n, c = x.shape
+        x2d = x.reshape(b * n, c).to(BF16).contiguous()
+        ctx2d, nk = None, n
+        if context is not None:
+            nk = context.shape[1]
+            ctx2d = context.reshape(b * nk, -1).to(BF16).contiguous()
+        return self._run(x2d, b, n, ctx2d, nk).view(b, n, c).to(x.dtype)
+
+
+class SpatialTransformer(PackedModule):
+    """attention.py:915-1057. GroupNorm(eps 1e-6) -> 1x1 proj_in -> transformer blocks on [b, hw, c] -> 1x1 proj_out
+    -> + x_in.  In NHWC the two rearranges are free and the 1x1 convs are plain GEMMs. `use_linear` is accepted and
+    ignored exactly like the reference (docstring at attention.py:930-945)."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0., context_dim=None, disable_self_attn=False,
+                 use_linear=False, use_checkpoint=True, lora_ranks: List[int] = None, lora_weights: List[float] = None,
+                 ipa_scale=1.0, ipa_num_tokens=0):
+        super().__init__()
+        _check_extras(lora_ranks, ipa_num_tokens)
+        if context_dim is not None and not isinstance(context_dim, (list, tuple)):
+            context_dim = [context_dim]
+        if context_dim is None:
+            context_dim = [None] * depth
+        self.in_channels = in_channels
+        inner_dim = n_heads * d_head
+        self.inner_dim = inner_dim
+        self.norm = Normalize(in_channels)
+        self.proj_in = nn.Conv2d(in_channels, inner_dim, kernel_size=1, stride=1, padding=0)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim[d],
+                                  disable_self_attn=disable_self_attn, checkpoint=use_checkpoint)
+            for d in range(depth)])
+        self.proj_out = nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0)
+        with torch.no_grad():  # zero_module, attention.py:1002
+            self.proj_out.weight.zero_()
+            self.proj_out.bias.zero_()
+
+    def _own_params(self):
+        return [self.norm.weight, self.norm.bias, self.proj_in.weight, self.proj_in.bias, self.proj_out.weight,
+                self.proj_out.bias]
+
+    def _pack(self, device):
+        return {"ng": f32(self.norm.weight, device), "nb": f32(self.norm.bias, device),
+                "wi": packw(self.proj_in.weight, device), "bi": f32(self.proj_in.bias, device),
+                "wo": packw(self.proj_out.weight, device), "bo": f32(self.proj_out.bias, device)}
+
+    def _run(self, x: torch.Tensor, ctx2d: Optional[torch.Tensor], nk: int) -> torch.Tensor:
+        """x: NHWC bf16 [b, h, w, c] -> same shape."""
+        p = self.packed(x.device)
+        b, hh, ww, c = x.shape
+        n = hh * ww
+        g = ops.groupnorm(x, p["ng"], p["nb"], self.norm.eps, silu=False)
+        h2d = ops.igemm(g.view(b * n, c), p["wi"], self.inner_dim, bias=p["bi"])
+        for blk in self.transformer_blocks:
+            h2d = blk._run(h2d, b, n, ctx2d, nk)
+        out = ops.igemm(h2d, p["wo"], c, bias=p["bo"], residual=x.view(b * n, c))
+        return out.view(b, hh, ww, c)
+
+    def forward(self, x, context=None):
+        require_cuda(x, "SpatialTransformer.forward")
+        ctx2d, nk = None, 0
+        if context is not None:
+            nk = context.shape[1]
+            ctx2d = context.reshape(-1, context.shape[-1]).to(BF16).contiguous()
+        y = self._run(ops.nchw_to_nhwc(x), ctx2d, nk)
+        return ops.nhwc_to_nchw_f32(y).to(x.dtype)

@@ -1,0 +1,469 @@
+"""Drop-in mirror of the reference's `ldm.modules.diffusionmodules.openaimodel` (HowToSD/cremage
+modules/ldm/modules/diffusionmodules/openaimodel.py) running on hand-written sm_100a kernels.
+
+`UNetModel` keeps the reference constructor (:447-481), attribute names (`time_embed`, `input_blocks`, `middle_block`,
+`output_blocks`, `out` -- ControlNet walks them, cldm/cldm.py:44-70), state-dict keys (pinned by
+test/ldm/ldm_instantiation_test.py:23-26) and `forward(x, timesteps, context, y)` (:780).  Swapping the YAML `target:`
+string is the whole integration (ldm/util.py:81-96).
+
+Internally activations are NHWC bf16, every contraction is the tcgen05 implicit GEMM, the skip concat
+(`th.cat([h, hs.pop()], 1)`, :808) is never materialised (GroupNorm and the GEMM read two sources), the 22 per-block
+timestep projections (:222-228) run as ONE GEMM, and the per-image timestep bias / residual adds live in GEMM epilogues.
+There is no CPU fallback: tensors on a non-CUDA device raise.
+"""
+from __future__ import annotations
+
+import os
+from abc import abstractmethod
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .... import ops
+from ....engine import BF16, GraphedCall, PackedModule, f32, packw, require_cuda
+from ..attention import SpatialTransformer
+from .util import conv_nd, linear, normalization, timestep_freqs, zero_module
+
+
+def _ceil8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+class TimestepBlock(nn.Module):
+    """openaimodel.py:60-69."""
+
+    @abstractmethod
+    def forward(self, x, emb):
+        """Apply the module to `x` given `emb` timestep embeddings."""
+
+
+class Upsample(PackedModule):
+    """openaimodel.py:95-123: nearest 2x then conv3x3."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        if dims != 2 or padding != 1:
+            raise ValueError("cremage_b200: Upsample supports dims=2, padding=1")
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.dims = dims
+        if use_conv:
+            self.conv = conv_nd(dims, self.channels, self.out_channels, 3, padding=padding)
+
+    def _pack(self, device):
+        if not self.use_conv:
+            return {}
+        return {"w": packw(self.conv.weight, device), "b": f32(self.conv.bias, device)}
+
+    def _run(self, x: torch.Tensor) -> torch.Tensor:
+        p = self.packed(x.device)
+        up = ops.upsample2x(x)
+        if not self.use_conv:
+            return up
+        n, h, w, _ = up.shape
+        return ops.igemm(up, p["w"], self.out_channels, taps=ops.TAPS_3X3, bias=p["b"]).view(n, h, w, self.out_channels)
+
+    def forward(self, x):
+        require_cuda(x, "Upsample.forward")
+        assert x.shape[1] == self.channels
+        return ops.nhwc_to_nchw_f32(self._run(ops.nchw_to_nhwc(x))).to(x.dtype)
+
+
+class Downsample(PackedModule):
+    """openaimodel.py:138-164: conv3x3 stride 2 pad 1 (use_conv) on parity planes."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        if dims != 2 or padding != 1 or not use_conv:
+            raise ValueError("cremage_b200: Downsample supports the learned stride-2 conv (dims=2, padding=1) only")
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.dims = dims
+        self.op = conv_nd(dims, self.channels, self.out_channels, 3, stride=2, padding=padding)
+
+    def _pack(self, device):
+        return {"w": packw(self.op.weight, device), "b": f32(self.op.bias, device)}
+
+    def _run(self, x: torch.Tensor) -> torch.Tensor:
+        p = self.packed(x.device)
+        n, h, w, c = x.shape
+        if h % 2 or w % 2:
+            raise ValueError("cremage_b200: Downsample needs even spatial extents")
+        xs = ops.parity_split(x)
+        out = ops.igemm(xs.view(4 * n, h // 2, w // 2, c), p["w"], self.out_channels, out_grid=(n, h // 2, w // 2),
+                        taps=ops.taps_3x3_stride2(n), bias=p["b"])
+        return out.view(n, h // 2, w // 2, self.out_channels)
+
+    def forward(self, x):
+        require_cuda(x, "Downsample.forward")
+        assert x.shape[1] == self.channels
+        return ops.nhwc_to_nchw_f32(self._run(ops.nchw_to_nhwc(x))).to(x.dtype)
+
+
+class ResBlock(TimestepBlock, PackedModule):
+    """openaimodel.py:167-279: conv3x3(SiLU(GN32(x))) + emb -> conv3x3(SiLU(GN32(.))) + skip(x)."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False, use_scale_shift_norm=False,
+                 dims=2, use_checkpoint=False, up=False, down=False):
+        PackedModule.__init__(self)
+        if use_scale_shift_norm or up or down or use_conv:
+            raise NotImplementedError("cremage_b200: ResBlock variants use_scale_shift_norm / up / down / use_conv are "
+                                      "not used by the SD1.5 / SDXL configs and are not implemented")
+        self.channels = channels
+        self.emb_channels = emb_channels
+        self.dropout = dropout
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.use_checkpoint = use_checkpoint
+        self.use_scale_shift_norm = use_scale_shift_norm
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(),
+                                       conv_nd(dims, channels, self.out_channels, 3, padding=1))
+        self.updown = False
+        self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(conv_nd(dims, self.out_channels, self.out_channels, 3, padding=1)))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = conv_nd(dims, channels, self.out_channels, 1)
+        self._emb_offset = None  # column of this block inside the UNet-wide fused timestep projection
+
+    def _pack(self, device):
+        return self._pack_split(device, None)
+
+    def _pack_split(self, device, split):
+        # conv1 reads the normalised concat, which GroupNorm writes as ONE tensor -> single-source K layout;
+        # only the 1x1 skip conv reads the two raw sources
+        p = {"g1": f32(self.in_layers[0].weight, device), "b1": f32(self.in_layers[0].bias, device),
+             "w1": packw(self.in_layers[2].weight, device), "c1": f32(self.in_layers[2].bias, device),
+             "g2": f32(self.out_layers[0].weight, device), "b2": f32(self.out_layers[0].bias, device),
+             "w2": packw(self.out_layers[3].weight, device), "c2": f32(self.out_layers[3].bias, device),
+             "we": packw(self.emb_layers[1].weight, device), "be": f32(self.emb_layers[1].bias, device),
+             "split": split}
+        if not isinstance(self.skip_connection, nn.Identity):
+            p["ws"] = packw(self.skip_connection.weight, device, split)
+            p["cs"] = f32(self.skip_connection.bias, device)
+        return p
+
+    def packed_for(self, device, split):
+        """Weights packed for a (c0, c1) two-source input (the K layout pads each source to whole 64-channel chunks)."""
+        p = self.packed(device)
+        if p["split"] != split:
+            with torch.no_grad():
+                self._cb_packed = self._pack_split(device, split)
+            p = self._cb_packed
+        return p
+
+    def _run(self, x: torch.Tensor, skip: Optional[torch.Tensor], emb_bias: torch.Tensor) -> torch.Tensor:
+        """x (+ skip, concatenated on channels): NHWC bf16; emb_bias: fp32 [n, out_channels] (may be a strided view)."""
+        split = None if skip is None else (x.shape[-1], skip.shape[-1])
+        p = self.packed_for(x.device, split)
+        n, hh, ww, _ = x.shape
+        co = self.out_channels
+        g = ops.groupnorm(x, p["g1"], p["b1"], self.in_layers[0].eps, silu=True, x1=skip)
+        h = ops.igemm(g, p["w1"], co, taps=ops.TAPS_3X3, bias=p["c1"], rowbias=emb_bias).view(n, hh, ww, co)
+        g2 = ops.groupnorm(h, p["g2"], p["b2"], self.out_layers[0].eps, silu=True)
+        if "ws" in p:
+            xs = ops.igemm(x, p["ws"], co, a1=skip, bias=p["cs"])
+        else:
+            if skip is not None:
+                raise ValueError("identity skip connection with a concatenated input")
+            xs = x.view(-1, co)
+        out = ops.igemm(g2, p["w2"], co, taps=ops.TAPS_3X3, bias=p["c2"], residual=xs)
+        return out.view(n, hh, ww, co)
+
+    def _emb_out(self, emb: torch.Tensor) -> torch.Tensor:
+        p = self.packed(emb.device)
+        semb = ops.silu_add(emb.to(BF16).contiguous())
+        return ops.igemm(semb, p["we"], self.out_channels, bias=p["be"], out_f32=True)
+
+    def forward(self, x, emb):
+        require_cuda(x, "ResBlock.forward")
+        y = self._run(ops.nchw_to_nhwc(x), None, self._emb_out(emb))
+        return ops.nhwc_to_nchw_f32(y).to(x.dtype)
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    """openaimodel.py:74-92: routes (x, emb) / (x, context) / (x) by layer type."""
+
+    def _run(self, h, skip, emb_all, ctx2d, nk):
+        for layer in self:
+            if isinstance(layer, ResBlock):
+                if callable(emb_all):
+                    eb = emb_all(layer)
+                else:
+                    off = layer._emb_offset
+                    eb = emb_all[:, off:off + layer.out_channels]
+                h = layer._run(h, skip, eb)
+                skip = None
+            elif isinstance(layer, SpatialTransformer):
+                h = layer._run(h, ctx2d, nk)
+            else:
+                h = layer._run(h)
+        if skip is not None:
+            raise ValueError("skip connection was not consumed (block does not start with a ResBlock)")
+        return h
+
+    def forward(self, x, emb, context=None):
+        require_cuda(x, "TimestepEmbedSequential.forward")
+        if len(self) == 1 and isinstance(self[0], nn.Conv2d):
+            raise NotImplementedError("call UNetModel.forward; the input conv has no standalone CUDA wrapper")
+        ctx2d, nk = None, 0
+        if context is not None:
+            nk = context.shape[1]
+            ctx2d = context.reshape(-1, context.shape[-1]).to(BF16).contiguous()
+        y = self._run(ops.nchw_to_nhwc(x), None, lambda layer: layer._emb_out(emb), ctx2d, nk)
+        return ops.nhwc_to_nchw_f32(y).to(x.dtype)
+
+
+class UNetModel(PackedModule):
+    """openaimodel.py:417-816 -- the full UNet with attention and timestep embedding."""
+
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                 use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
+                 use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True,
+                 disable_self_attentions=None, num_attention_blocks=None, disable_middle_self_attn=False,
+                 use_linear_in_transformer=False, lora_ranks: List[int] = None, lora_weights: List[float] = None,
+                 ipa_scale=1.0, ipa_num_tokens=0):
+        super().__init__()
+        if use_spatial_transformer:
+            assert context_dim is not None, "context_dim is required with use_spatial_transformer"
+        if context_dim is not None:
+            assert use_spatial_transformer, "context_dim requires use_spatial_transformer"
+            if not isinstance(context_dim, int):
+                context_dim = list(context_dim)
+        if not use_spatial_transformer:
+            raise NotImplementedError("cremage_b200: the legacy AttentionBlock UNet (use_spatial_transformer=False) is "
+                                      "not on the SD path and is not implemented")
+        if dims != 2 or use_scale_shift_norm or resblock_updown or n_embed is not None or not conv_resample:
+            raise NotImplementedError("cremage_b200: dims!=2 / use_scale_shift_norm / resblock_updown / n_embed / "
+                                      "conv_resample=False are not implemented")
+        if num_classes is not None:
+            raise NotImplementedError("cremage_b200: class-conditional ldm UNet (num_classes) is not implemented")
+        if lora_ranks:
+            raise NotImplementedError("cremage_b200: merge LoRA weights before loading (lora_ranks must be empty)")
+        if ipa_num_tokens:
+            raise NotImplementedError("cremage_b200: IP-Adapter tokens are not implemented")
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        if num_heads == -1:
+            assert num_head_channels != -1, "Either num_heads or num_head_channels has to be set"
+        if num_head_channels == -1:
+            assert num_heads != -1, "Either num_heads or num_head_channels has to be set"
+
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        if isinstance(num_res_blocks, int):
+            self.num_res_blocks = len(channel_mult) * [num_res_blocks]
+        else:
+            if len(num_res_blocks) != len(channel_mult):
+                raise ValueError("provide num_res_blocks either as an int (globally constant) or "
+                                 "as a list/tuple (per-level) with the same length as channel_mult")
+            self.num_res_blocks = num_res_blocks
+        if disable_self_attentions is not None:
+            assert len(disable_self_attentions) == len(channel_mult)
+        if num_attention_blocks is not None:
+            assert len(num_attention_blocks) == len(self.num_res_blocks)
+        self.attention_resolutions = attention_resolutions
+        self.dropout = dropout
+        self.channel_mult = channel_mult
+        self.conv_resample = conv_resample
+        self.num_classes = num_classes
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float16 if use_fp16 else torch.float32
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads_upsample
+        self.predict_codebook_ids = False
+        self.context_dim = context_dim
+
+        def make_st(ch, heads, dim_head, disabled_sa=False):
+            return SpatialTransformer(ch, heads, dim_head, depth=transformer_depth, context_dim=context_dim,
+                                      disable_self_attn=disabled_sa, use_linear=use_linear_in_transformer,
+                                      use_checkpoint=use_checkpoint)
+
+        def head_cfg(ch, heads):
+            if num_head_channels == -1:
+                dim_head = ch // heads
+            else:
+                heads = ch // num_head_channels
+                dim_head = num_head_channels
+            if legacy:
+                dim_head = ch // heads  # use_spatial_transformer is always True here
+            return heads, dim_head
+
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(linear(model_channels, time_embed_dim), nn.SiLU(),
+                                        linear(time_embed_dim, time_embed_dim))
+        self.input_blocks = nn.ModuleList(
+            [TimestepEmbedSequential(conv_nd(dims, in_channels, model_channels, 3, padding=1))])
+        self._feature_size = model_channels
+        input_block_chans = [model_channels]
+        ch = model_channels
+        ds = 1
+        for level, mult in enumerate(channel_mult):
+            for nr in range(self.num_res_blocks[level]):
+                layers = [ResBlock(ch, time_embed_dim, dropout, out_channels=mult * model_channels, dims=dims,
+                                   use_checkpoint=use_checkpoint)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    heads, dim_head = head_cfg(ch, num_heads)
+                    disabled_sa = disable_self_attentions[level] if disable_self_attentions is not None else False
+                    if num_attention_blocks is None or nr < num_attention_blocks[level]:
+                        layers.append(make_st(ch, heads, dim_head, disabled_sa))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                self._feature_size += ch
+                input_block_chans.append(ch)
+            if level != len(channel_mult) - 1:
+                out_ch = ch
+                self.input_blocks.append(
+                    TimestepEmbedSequential(Downsample(ch, conv_resample, dims=dims, out_channels=out_ch)))
+                ch = out_ch
+                input_block_chans.append(ch)
+                ds *= 2
+                self._feature_size += ch
+
+        heads, dim_head = head_cfg(ch, num_heads)
+        self.middle_block = TimestepEmbedSequential(
+            ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint),
+            make_st(ch, heads, dim_head, disable_middle_self_attn),
+            ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint))
+        self._feature_size += ch
+
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(self.num_res_blocks[level] + 1):
+                ich = input_block_chans.pop()
+                layers = [ResBlock(ch + ich, time_embed_dim, dropout, out_channels=model_channels * mult, dims=dims,
+                                   use_checkpoint=use_checkpoint)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    heads, dim_head = head_cfg(ch, num_heads_upsample)
+                    disabled_sa = disable_self_attentions[level] if disable_self_attentions is not None else False
+                    if num_attention_blocks is None or i < num_attention_blocks[level]:
+                        layers.append(make_st(ch, heads, dim_head, disabled_sa))
+                if level and i == self.num_res_blocks[level]:
+                    out_ch = ch
+                    layers.append(Upsample(ch, conv_resample, dims=dims, out_channels=out_ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+                self._feature_size += ch
+
+        self.out = nn.Sequential(normalization(ch), nn.SiLU(),
+                                 zero_module(conv_nd(dims, model_channels, out_channels, 3, padding=1)))
+
+        # fused timestep projection: every ResBlock gets a column range of one [sum(out_channels), 4*mc] GEMM
+        off = 0
+        self._res_blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+        for rb in self._res_blocks:
+            rb._emb_offset = off
+            off += rb.out_channels
+        self._emb_total = off
+        # CUDA-graph replay of the whole forward (one capture per input signature); CREMAGE_B200_GRAPH=0 disables
+        self.use_cuda_graph = os.environ.get("CREMAGE_B200_GRAPH", "1") != "0"
+        self._graphed = None
+
+    # -- packing -------------------------------------------------------------------------------------------------
+    def _own_params(self):
+        ps = list(self.time_embed.parameters()) + list(self.input_blocks[0].parameters()) + list(self.out.parameters())
+        for rb in self._res_blocks:
+            ps += list(rb.emb_layers.parameters())
+        return ps
+
+    def _pack(self, device):
+        cin, cin_pad = self.in_channels, _ceil8(self.in_channels)
+        w_in = self.input_blocks[0][0].weight.detach().to(device=device, dtype=torch.float32)  # [mc, cin, 3, 3]
+        embw = torch.cat([rb.emb_layers[1].weight.detach().to(device=device, dtype=torch.float32)
+                          for rb in self._res_blocks], 0)
+        embb = torch.cat([rb.emb_layers[1].bias.detach().to(device=device, dtype=torch.float32)
+                          for rb in self._res_blocks], 0)
+        return {
+            "freqs": timestep_freqs(self.model_channels).to(device),
+            "te0w": packw(self.time_embed[0].weight, device), "te0b": f32(self.time_embed[0].bias, device),
+            "te2w": packw(self.time_embed[2].weight, device), "te2b": f32(self.time_embed[2].bias, device),
+            "embw": ops.pack_weight(embw), "embb": embb.contiguous(),
+            "inw": w_in.permute(2, 3, 1, 0).contiguous(), "inb": f32(self.input_blocks[0][0].bias, device),
+            "cin": cin, "cin_pad": cin_pad,
+            "og": f32(self.out[0].weight, device), "ob": f32(self.out[0].bias, device),
+            "ow": packw(self.out[2].weight, device), "oc": f32(self.out[2].bias, device),
+        }
+
+    # -- forward -------------------------------------------------------------------------------------------------
+    def _forward_impl(self, x: torch.Tensor, t: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        dev = x.device
+        p = self.packed(dev)
+        n, c, hh, ww = x.shape
+        mc, ted = self.model_channels, self.model_channels * 4
+        # timestep embedding -> time_embed MLP (SiLU fused) -> all per-block projections in one GEMM
+        temb = ops.timestep_embedding(t, mc, p["freqs"])
+        e = ops.igemm(temb, p["te0w"], ted, bias=p["te0b"], act=ops.ACT_SILU)
+        semb = ops.igemm(e, p["te2w"], ted, bias=p["te2b"], act=ops.ACT_SILU)  # silu(emb): every consumer applies SiLU first
+        emb_all = ops.igemm(semb, p["embw"], self._emb_total, bias=p["embb"], out_f32=True)
+        nk = context.shape[1]
+        ctx2d = context.reshape(n * nk, context.shape[-1]).to(BF16).contiguous()
+
+        h = ops.nchw_to_nhwc(x, c_pad=p["cin_pad"])
+        h = ops.conv3x3_small_cin(h, p["cin"], p["inw"], p["inb"], mc)
+        hs = [h]
+        for module in list(self.input_blocks)[1:]:
+            h = module._run(h, None, emb_all, ctx2d, nk)
+            hs.append(h)
+        h = self.middle_block._run(h, None, emb_all, ctx2d, nk)
+        for module in self.output_blocks:
+            h = module._run(h, hs.pop(), emb_all, ctx2d, nk)
+        g = ops.groupnorm(h, p["og"], p["ob"], self.out[0].eps, silu=True)
+        o = ops.igemm(g, p["ow"], self.out_channels, taps=ops.TAPS_3X3, bias=p["oc"], out_f32=True)
+        return ops.nhwc_to_nchw_f32(o.view(n, hh, ww, self.out_channels))
+
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        """Apply the model to an input batch (openaimodel.py:780-816).
+        x: [N, C, H, W]; timesteps: [N] (float, possibly fractional, or int64); context: [N, S, context_dim]."""
+        assert (y is not None) == (self.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        require_cuda(x, "UNetModel.forward")
+        if timesteps is None or context is None:
+            raise ValueError("UNetModel.forward needs timesteps and context")
+        if x.shape[0] != timesteps.shape[0] or x.shape[0] != context.shape[0]:
+            raise ValueError("batch sizes of x, timesteps and context differ")
+        if x.shape[2] % (2 ** (len(self.channel_mult) - 1)) or x.shape[3] % (2 ** (len(self.channel_mult) - 1)):
+            raise ValueError("latent height/width must be divisible by the total downsampling factor")
+        t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
+        ctx = context.to(device=x.device)
+        xin = x.contiguous()
+        if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
+            if self._graphed is None:
+                self._graphed = GraphedCall(self._forward_impl)
+            self.packed(x.device)  # refresh packs (and drop stale graphs) if parameters changed
+            out = self._graphed(xin, t, ctx)
+        else:
+            out = self._forward_impl(xin, t, ctx)
+        return out.to(x.dtype)
+
+    def packed(self, device):
+        before = self._cb_packed
+        p = super().packed(device)
+        if p is not before and self._graphed is not None:
+            self._graphed.reset()  # parameters changed: captured graphs hold stale weight buffers
+        return p
+
+    def invalidate_packed(self):
+        super().invalidate_packed()
+        if self._graphed is not None:
+            self._graphed.reset()
+
+    def convert_to_fp16(self):
+        """openaimodel.py:758-764. Storage dtype only; the kernels always compute bf16 x bf16 -> fp32."""
+        for blocks in (self.input_blocks, self.middle_block, self.output_blocks):
+            blocks.half()
+
+    def convert_to_fp32(self):
+        for blocks in (self.input_blocks, self.middle_block, self.output_blocks):
+            blocks.float()

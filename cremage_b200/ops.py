@@ -34,6 +34,52 @@ def _need_cuda(*ts):
             raise RuntimeError("cremage_b200 has no CPU path: tensors must live on a CUDA device")
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# optional per-launch timing (bench.py's roofline section): CUDA events on the launching stream around every call
+# ------------------------------------------------------------------------------------------------------------------
+class LaunchProfile:
+    """Collects (name, algorithmic flops, algorithmic bytes, start event, end event) for every C-ABI call."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _PROF
+        self._prev, _PROF = _PROF, self
+        return self
+
+    def __exit__(self, *exc):
+        global _PROF
+        _PROF = self._prev
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+_PROF: Optional[LaunchProfile] = None
+
+
+def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0) -> None:
+    if _PROF is None:
+        check(fn(), name)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(), name)
+    e1.record()
+    _PROF.records.append((name, flops, nbytes, e0, e1))
+
+
 def ceil64(c: int) -> int:
     return (c + 63) // 64 * 64
 
@@ -181,9 +227,9 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     d.cout = cout
     d.mode, d.act = mode, act
     d.bias = _p(bias)
-    d.rowbias, d.rowbias_ld = _p(rowbias), (rowbias.shape[-1] if rowbias is not None else 0)
+    d.rowbias, d.rowbias_ld = _p(rowbias), (rowbias.stride(0) if rowbias is not None else 0)
     if rowbias is not None:
-        assert rowbias.dtype == torch.float32
+        assert rowbias.dtype == torch.float32 and rowbias.stride(-1) == 1
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     d.residual, d.res_ld = _p(residual), (residual.shape[-1] if residual is not None else 0)
@@ -194,7 +240,9 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     if heads is not None:
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
     d.bn, d.stages = bn, stages
-    check(_lib.load().cb_igemm(C.byref(d), _stream()), "cb_igemm")
+    # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
+    _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
+            flops=2.0 * rows * len(dw) * (c0 + c1) * ncols)
     return out
 
 
@@ -207,16 +255,37 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
     _need_cuda(q, k, v)
     if out is None:
         out = torch.empty((batch * nq, heads * d), dtype=BF16, device=q.device)
-    check(_lib.load().cb_attention(_p(q), _p(k), _p(v), _p(out), batch, heads, nq, nk, d, dpad, scale, _stream()),
-          "cb_attention")
+    _launch("cb_attention", lambda: _lib.load().cb_attention(_p(q), _p(k), _p(v), _p(out), batch, heads, nq, nk, d, dpad, scale, _stream()),
+            flops=4.0 * batch * heads * nq * nk * d)
+    return out
+
+
+def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(scale * s) over the last dim of a 2-D fp32 or bf16 tensor -> bf16 `out` (in place for bf16 if None)."""
+    _need_cuda(s, out)
+    assert s.dim() == 2 and s.stride(1) == 1 and s.dtype in (BF16, torch.float32)
+    if out is None:
+        out = s if s.dtype == BF16 else torch.empty(s.shape, dtype=BF16, device=s.device)
+    assert out.dtype == BF16 and out.shape == s.shape and out.stride(1) == 1
+    _launch("cb_softmax_rows", lambda: _lib.load().cb_softmax_rows(_p(s), int(s.dtype == torch.float32), s.stride(0), _p(out), out.stride(0),
+                                      s.shape[0], s.shape[1], scale, _stream()))
     return out
 
 
 def softmax_rows_(s: torch.Tensor, scale: float) -> torch.Tensor:
-    _need_cuda(s)
-    assert s.dtype == BF16 and s.dim() == 2 and s.stride(1) == 1
-    check(_lib.load().cb_softmax_rows(_p(s), s.shape[0], s.shape[1], s.stride(0), scale, _stream()), "cb_softmax_rows")
-    return s
+    return softmax_rows(s, scale, None)
+
+
+def pointwise_nchw_to_nhwc(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], c_pad: int,
+                           scale: float = 1.0) -> torch.Tensor:
+    """1x1 channel mix of an NCHW fp32 tensor fused with the NHWC bf16 conversion (w fp32 [cout, c])."""
+    _need_cuda(x, w, b)
+    x = x.contiguous().float()
+    n, c, h, wd = x.shape
+    out = torch.empty((n, h, wd, c_pad), dtype=BF16, device=x.device)
+    _launch("cb_pointwise_nchw_to_nhwc", lambda: _lib.load().cb_pointwise_nchw_to_nhwc(_p(x), n, c, h * wd, _p(w), _p(b), w.shape[0], c_pad, scale, _p(out),
+                                                _stream()))
+    return out
 
 
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
@@ -229,9 +298,13 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     c0 = x0.shape[-1]
     c1 = 0 if x1 is None else x1.shape[-1]
     out = torch.empty((*x0.shape[:-1], c0 + c1), dtype=BF16, device=x0.device)
-    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x0.device)
-    check(_lib.load().cb_groupnorm_nhwc(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(gamma), _p(beta), int(silu),
-                                        _p(out), _p(stats), _stream()), "cb_groupnorm_nhwc")
+    ws = int(_lib.load().cb_groupnorm_workspace_bytes(c0 + c1, n, hw, groups))
+    if ws <= 0:
+        raise ValueError(f"groupnorm: unsupported shape n={n} hw={hw} c={c0 + c1} groups={groups}")
+    stats = torch.empty((ws // 4,), dtype=torch.float32, device=x0.device)
+    _launch("cb_groupnorm_nhwc", lambda: _lib.load().cb_groupnorm_nhwc(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(gamma), _p(beta), int(silu),
+                                        _p(out), _p(stats), _stream()),
+            nbytes=4.0 * n * hw * (c0 + c1))  # algorithmic: one bf16 read + one bf16 write per element
     return out
 
 
@@ -241,7 +314,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     c = x.shape[-1]
     rows = x.numel() // c
     out = torch.empty_like(x)
-    check(_lib.load().cb_layernorm(_p(x), rows, c, eps, _p(gamma), _p(beta), _p(out), _stream()), "cb_layernorm")
+    _launch("cb_layernorm", lambda: _lib.load().cb_layernorm(_p(x), rows, c, eps, _p(gamma), _p(beta), _p(out), _stream()),
+            nbytes=4.0 * rows * c)
     return out
 
 
@@ -257,8 +331,7 @@ def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None, scale: float = 1.
     n, c, h, w = x.shape
     c_pad = c if c_pad is None else c_pad
     out = torch.empty((n, h, w, c_pad), dtype=BF16, device=x.device)
-    check(_lib.load().cb_nchw_to_nhwc(_p(x), _SRC_DTYPE[x.dtype], n, c, h * w, c_pad, scale, _p(out), _stream()),
-          "cb_nchw_to_nhwc")
+    _launch("cb_nchw_to_nhwc", lambda: _lib.load().cb_nchw_to_nhwc(_p(x), _SRC_DTYPE[x.dtype], n, c, h * w, c_pad, scale, _p(out), _stream()))
     return out
 
 
@@ -269,8 +342,7 @@ def nhwc_to_nchw_f32(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
     n, h, w, c_ld = x.shape
     c = c_ld if c is None else c
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
-    check(_lib.load().cb_nhwc_to_nchw_f32(_p(x), int(x.dtype == torch.float32), n, c, h * w, c_ld, _p(out), _stream()),
-          "cb_nhwc_to_nchw_f32")
+    _launch("cb_nhwc_to_nchw_f32", lambda: _lib.load().cb_nhwc_to_nchw_f32(_p(x), int(x.dtype == torch.float32), n, c, h * w, c_ld, _p(out), _stream()))
     return out
 
 
@@ -278,7 +350,7 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
-    check(_lib.load().cb_upsample2x_nhwc(_p(x), n, h, w, c, _p(out), _stream()), "cb_upsample2x_nhwc")
+    _launch("cb_upsample2x_nhwc", lambda: _lib.load().cb_upsample2x_nhwc(_p(x), n, h, w, c, _p(out), _stream()))
     return out
 
 
@@ -286,7 +358,7 @@ def parity_split(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     n, h, w, c = x.shape
     out = torch.empty((4, n, h // 2, w // 2, c), dtype=BF16, device=x.device)
-    check(_lib.load().cb_parity_split_nhwc(_p(x), n, h, w, c, _p(out), _stream()), "cb_parity_split_nhwc")
+    _launch("cb_parity_split_nhwc", lambda: _lib.load().cb_parity_split_nhwc(_p(x), n, h, w, c, _p(out), _stream()))
     return out
 
 
@@ -294,8 +366,7 @@ def timestep_embedding(t: torch.Tensor, dim: int, freqs: torch.Tensor) -> torch.
     _need_cuda(t, freqs)
     assert t.dtype == torch.float32 and freqs.dtype == torch.float32 and freqs.numel() == dim // 2
     out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
-    check(_lib.load().cb_timestep_embedding(_p(t), t.shape[0], dim, _p(freqs), _p(out), _stream()),
-          "cb_timestep_embedding")
+    _launch("cb_timestep_embedding", lambda: _lib.load().cb_timestep_embedding(_p(t), t.shape[0], dim, _p(freqs), _p(out), _stream()))
     return out
 
 
@@ -304,15 +375,14 @@ def conv3x3_small_cin(x: torch.Tensor, cin: int, wgt: torch.Tensor, bias: Option
     _need_cuda(x, wgt, bias)
     n, h, w, cin_ld = x.shape
     out = torch.empty((n, h, w, cout), dtype=BF16, device=x.device)
-    check(_lib.load().cb_conv3x3_small_cin(_p(x), n, h, w, cin, cin_ld, _p(wgt), _p(bias), cout, _p(out), _stream()),
-          "cb_conv3x3_small_cin")
+    _launch("cb_conv3x3_small_cin", lambda: _lib.load().cb_conv3x3_small_cin(_p(x), n, h, w, cin, cin_ld, _p(wgt), _p(bias), cout, _p(out), _stream()))
     return out
 
 
 def silu_add(x: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(x, add)
     out = torch.empty_like(x)
-    check(_lib.load().cb_silu_add(_p(x), _p(add), x.numel(), _p(out), _stream()), "cb_silu_add")
+    _launch("cb_silu_add", lambda: _lib.load().cb_silu_add(_p(x), _p(add), x.numel(), _p(out), _stream()))
     return out
 
 
@@ -321,7 +391,7 @@ def image_to_u8(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     n, h, w, c_ld = x.shape
     out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device)
-    check(_lib.load().cb_image_to_u8(_p(x), n, h * w, c_ld, _p(out), _stream()), "cb_image_to_u8")
+    _launch("cb_image_to_u8", lambda: _lib.load().cb_image_to_u8(_p(x), n, h * w, c_ld, _p(out), _stream()))
     return out
 
 
@@ -333,36 +403,75 @@ def cfg_scale_input(x: torch.Tensor, c_in: float) -> torch.Tensor:
     assert x.dtype == torch.float32 and x.is_contiguous()
     b = x.shape[0]
     out = torch.empty((2 * b, *x.shape[1:]), dtype=torch.float32, device=x.device)
-    check(_lib.load().cb_cfg_scale_input(_p(x), x.numel() // b, b, c_in, _p(out), _stream()), "cb_cfg_scale_input")
+    _launch("cb_cfg_scale_input", lambda: _lib.load().cb_cfg_scale_input(_p(x), x.numel() // b, b, c_in, _p(out), _stream()))
     return out
 
 
-def step_euler_ancestral(x, eps2, noise, cfg_scale, sigma, sigma_down, sigma_up, want_denoised=False):
-    _need_cuda(x, eps2, noise)
-    b = x.shape[0]
+def axpby(x: torch.Tensor, a: float, y: Optional[torch.Tensor] = None, b: float = 0.0) -> torch.Tensor:
+    """a*x + b*y over fp32 tensors."""
+    _need_cuda(x, y)
+    assert x.dtype == torch.float32 and x.is_contiguous() and (y is None or (y.dtype == torch.float32 and y.is_contiguous()))
+    out = torch.empty_like(x)
+    _launch("cb_axpby_f32", lambda: _lib.load().cb_axpby_f32(_p(x), a, _p(y), b, x.numel(), _p(out), _stream()))
+    return out
+
+
+def cfg_mix(uncond: torch.Tensor, cond: torch.Tensor, scale: float) -> torch.Tensor:
+    _need_cuda(uncond, cond)
+    assert uncond.dtype == torch.float32 and cond.dtype == torch.float32 and uncond.is_contiguous() and cond.is_contiguous()
+    out = torch.empty_like(uncond)
+    _launch("cb_cfg_mix_f32", lambda: _lib.load().cb_cfg_mix_f32(_p(uncond), _p(cond), scale, uncond.numel(), _p(out), _stream()))
+    return out
+
+
+def _halves(eps2: torch.Tensor, b: int):
+    assert eps2.dtype == torch.float32 and eps2.is_contiguous() and eps2.shape[0] == 2 * b
+    return eps2[:b], eps2[b:]
+
+
+def step_euler_ancestral(x, eps2, noise, cfg_scale, sigma, sigma_down, sigma_up, want_denoised=False, denoised=None):
+    """Fused CFG + Euler-ancestral update. Pass `denoised` instead of `eps2` when the model call is opaque."""
+    _need_cuda(x, eps2, noise, denoised)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if denoised is not None:
+        eu, ec, isd = denoised.contiguous(), None, 1
+    else:
+        eu, ec = _halves(eps2, x.shape[0])
+        isd = 0
     x_out = torch.empty_like(x)
     den = torch.empty_like(x) if want_denoised else None
-    check(_lib.load().cb_step_euler_ancestral(_p(x), _p(eps2), _p(noise), x.numel() // b, b, cfg_scale, sigma,
-                                              sigma_down, sigma_up, _p(x_out), _p(den), _stream()),
-          "cb_step_euler_ancestral")
+    _launch("cb_step_euler_ancestral", lambda: _lib.load().cb_step_euler_ancestral(_p(x), _p(eu), _p(ec), isd, _p(noise), x.numel(), cfg_scale, sigma,
+                                              sigma_down, sigma_up, _p(x_out), _p(den), _stream()))
     return x_out, den
 
 
-def step_dpmpp_2m(x, eps2, old_denoised, cfg_scale, sigma, ratio, em1, c_new, c_old):
-    _need_cuda(x, eps2, old_denoised)
-    b = x.shape[0]
+def step_dpmpp_2m(x, eps2, old_denoised, cfg_scale, sigma, ratio, em1, c_new, c_old, denoised=None, want_denoised=True):
+    _need_cuda(x, eps2, old_denoised, denoised)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if denoised is not None:
+        eu, ec, isd = denoised.contiguous(), None, 1
+    else:
+        eu, ec = _halves(eps2, x.shape[0])
+        isd = 0
     x_out = torch.empty_like(x)
-    den = torch.empty_like(x)
-    check(_lib.load().cb_step_dpmpp_2m(_p(x), _p(eps2), _p(old_denoised), x.numel() // b, b, cfg_scale, sigma, ratio,
-                                       em1, c_new, c_old, _p(x_out), _p(den), _stream()), "cb_step_dpmpp_2m")
+    den = torch.empty_like(x) if want_denoised else None
+    _launch("cb_step_dpmpp_2m", lambda: _lib.load().cb_step_dpmpp_2m(_p(x), _p(eu), _p(ec), isd, _p(old_denoised), x.numel(), cfg_scale, sigma, ratio,
+                                       em1, c_new, c_old, _p(x_out), _p(den), _stream()))
     return x_out, den
 
 
-def step_ddim(x, eps2, noise, cfg_scale, sqrt_at, sqrt_one_minus_at, sqrt_aprev, dir_coef, sigma_t, want_x0=True):
-    _need_cuda(x, eps2, noise)
-    b = x.shape[0]
+def step_ddim(x, eps2, noise, cfg_scale, sqrt_at, sqrt_one_minus_at, sqrt_aprev, dir_coef, sigma_t, want_x0=True,
+              eps=None):
+    """Fused CFG + DDIM update; `eps` (no guidance) may be given instead of the doubled `eps2`."""
+    _need_cuda(x, eps2, noise, eps)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if eps is not None:
+        eu = ec = eps.contiguous()
+        cfg_scale = 0.0
+    else:
+        eu, ec = _halves(eps2, x.shape[0])
     x_out = torch.empty_like(x)
     x0 = torch.empty_like(x) if want_x0 else None
-    check(_lib.load().cb_step_ddim(_p(x), _p(eps2), _p(noise), x.numel() // b, b, cfg_scale, sqrt_at, sqrt_one_minus_at,
-                                   sqrt_aprev, dir_coef, sigma_t, _p(x_out), _p(x0), _stream()), "cb_step_ddim")
+    _launch("cb_step_ddim", lambda: _lib.load().cb_step_ddim(_p(x), _p(eu), _p(ec), _p(noise), x.numel(), cfg_scale, sqrt_at, sqrt_one_minus_at,
+                                   sqrt_aprev, dir_coef, sigma_t, _p(x_out), _p(x0), _stream()))
     return x_out, x0

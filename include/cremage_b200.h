@@ -91,16 +91,19 @@ int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
 int cb_attention(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads, int64_t nq,
                  int64_t nk, int d, int dpad, float scale, cudaStream_t stream);
 
-/* row softmax over fp32-scaled bf16 scores, in place: s[r][:] = softmax(scale * s[r][:]) (VAE AttnBlock,
- * ldm/modules/diffusionmodules/model.py:196-198) */
-int cb_softmax_rows(void* s, int64_t rows, int64_t cols, int64_t ld, float scale, cudaStream_t stream);
+/* row softmax: dst[r][:] = softmax(scale * src[r][:]); src fp32 (src_f32 = 1) or bf16, dst bf16 (may alias a bf16
+ * src); VAE AttnBlock, ldm/modules/diffusionmodules/model.py:196-198 */
+int cb_softmax_rows(const void* src, int src_f32, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
+                    int64_t cols, float scale, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) over NHWC bf16, fp32 statistics; replaces GroupNorm32+SiLU (ldm/modules/diffusionmodules/
  * util.py:214-216, openaimodel.py:205-207,229-231), Normalize (attention.py:189, model.py:45) + nonlinearity
  * (model.py:40-42).  Two sources = normalise the channel concat without materialising it.
- *   stats: fp32 [n][groups][2] workspace (sum, sum of squares), zeroed by the call.
+ *   stats: workspace of cb_groupnorm_workspace_bytes(c0 + c1, n, hw, groups) bytes; its first n*groups*2 floats
+ *   receive (sum, sum of squares).  Reductions use no floating-point atomics: results are run-to-run identical.
  * ------------------------------------------------------------------------------------------------------------- */
+int64_t cb_groupnorm_workspace_bytes(int64_t c, int64_t n, int64_t hw, int groups);
 int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int64_t c1, int64_t n, int64_t hw, int groups,
                       float eps, const float* gamma, const float* beta, int silu, void* out, float* stats,
                       cudaStream_t stream);
@@ -115,6 +118,11 @@ int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, const float*
 /* NCHW (fp32, or fp16/bf16 when src_dtype = 1/2) -> NHWC bf16 with channel padding to c_pad (zeros), times scale */
 int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_t c, int64_t hw, int64_t c_pad, float scale,
                     void* dst, cudaStream_t stream);
+/* 1x1 channel mix fused with the layout change: dst[n][p][co] = sum_ci w[co][ci] * src[n][ci][p] * scale + b[co]
+ * (AutoencoderKL.post_quant_conv + the 1/scale_factor of decode_first_stage, ldm/models/autoencoder.py:303,336,
+ * ldm/models/diffusion/ddpm.py:794-798); src NCHW fp32, w fp32 [cout][c], dst NHWC bf16 [n][hw][c_pad] */
+int cb_pointwise_nchw_to_nhwc(const float* src, int64_t n, int64_t c, int64_t hw, const float* w, const float* b,
+                              int64_t cout, int64_t c_pad, float scale, void* dst, cudaStream_t stream);
 /* NHWC (bf16, or fp32 when src_f32) [n][hw][c_ld] -> NCHW fp32 [n][c][hw], first c channels */
 int cb_nhwc_to_nchw_f32(const void* src, int src_f32, int64_t n, int64_t c, int64_t hw, int64_t c_ld, float* dst,
                         cudaStream_t stream);
@@ -133,25 +141,33 @@ int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64_t w, int c
 int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * sampler latent updates, fp32 NCHW latents, one launch per step.  `eps` is the CFG-doubled UNet output
- * [2b][c][h][w] (uncond first: ldm/models/diffusion/ldm_wrapper_for_k_diffusion.py:67-99, ddim.py:538-561).
+ * sampler latent updates, fp32 latents (any layout, `count` elements), one launch per step.
+ * eps_u / eps_c are the unconditional / conditional halves of the CFG-doubled UNet output (uncond first:
+ * ldm/models/diffusion/ldm_wrapper_for_k_diffusion.py:67-99, ddim.py:538-561).  Without guidance pass the same
+ * pointer twice and cfg_scale 0.  With is_denoised = 1, eps_u already holds the denoised prediction (generic
+ * `model(x, sigma)` callers) and eps_c / cfg_scale / the CompVis step are skipped.
  * ------------------------------------------------------------------------------------------------------------- */
-/* x_in = x * c_in for both CFG halves: out [2b] <- x [b]   (k_diffusion/external.py:111-114) */
+/* x_in = x * c_in duplicated for both CFG halves: out [2][count] <- x [count]   (k_diffusion/external.py:111-114) */
 int cb_cfg_scale_input(const float* x, int64_t per_batch, int64_t b, float c_in, float* out, cudaStream_t stream);
-/* Euler-ancestral (k_diffusion/sampling.py:147-163): denoised = x - sigma*(eu + s*(ec-eu));
- *   x' = x + (x-denoised)/sigma*(sigma_down - sigma) + noise*sigma_up ; writes x_out (and denoised if non-null) */
-int cb_step_euler_ancestral(const float* x, const float* eps2, const float* noise, int64_t per_batch, int64_t b,
-                            float cfg_scale, float sigma, float sigma_down, float sigma_up, float* x_out,
+/* out = a*x + b*y (y may be NULL): CompVisDenoiser's input*c_in and input + eps*c_out (external.py:111-114) */
+int cb_axpby_f32(const float* x, float a, const float* y, float b, int64_t count, float* out, cudaStream_t stream);
+/* out = uncond + scale * (cond - uncond)   (ldm_wrapper_for_k_diffusion.py:99) */
+int cb_cfg_mix_f32(const float* uncond, const float* cond, float scale, int64_t count, float* out, cudaStream_t stream);
+/* Euler-ancestral (k_diffusion/sampling.py:147-163): denoised = x - sigma*(eu + s*(ec-eu)) [per half, then mixed];
+ *   x' = x + (x-denoised)/sigma*(sigma_down - sigma) + noise*sigma_up ; noise may be NULL (last step) */
+int cb_step_euler_ancestral(const float* x, const float* eps_u, const float* eps_c, int is_denoised, const float* noise,
+                            int64_t count, float cfg_scale, float sigma, float sigma_down, float sigma_up, float* x_out,
                             float* denoised_out, cudaStream_t stream);
-/* DPM++ 2M (k_diffusion/sampling.py:593-615): x' = ratio*x - em1*(c_new*denoised + c_old*old_denoised) */
-int cb_step_dpmpp_2m(const float* x, const float* eps2, const float* old_denoised, int64_t per_batch, int64_t b,
-                     float cfg_scale, float sigma, float ratio, float em1, float c_new, float c_old, float* x_out,
-                     float* denoised_out, cudaStream_t stream);
+/* DPM++ 2M (k_diffusion/sampling.py:593-615): x' = ratio*x - em1*(c_new*denoised - c_old*old_denoised);
+ *   old_denoised NULL = first / last step form */
+int cb_step_dpmpp_2m(const float* x, const float* eps_u, const float* eps_c, int is_denoised, const float* old_denoised,
+                     int64_t count, float cfg_scale, float sigma, float ratio, float em1, float c_new, float c_old,
+                     float* x_out, float* denoised_out, cudaStream_t stream);
 /* DDIM (ldm/models/diffusion/ddim.py:590-611): e = eu + s*(ec-eu); pred_x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);
- *   x' = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) e + sigma*noise */
-int cb_step_ddim(const float* x, const float* eps2, const float* noise, int64_t per_batch, int64_t b, float cfg_scale,
-                 float sqrt_at, float sqrt_one_minus_at, float sqrt_aprev, float dir_coef, float sigma_t, float* x_out,
-                 float* pred_x0_out, cudaStream_t stream);
+ *   x' = sqrt(a_prev) pred_x0 + dir_coef * e + sigma_t*noise, dir_coef = sqrt(1-a_prev-sigma_t^2) */
+int cb_step_ddim(const float* x, const float* eps_u, const float* eps_c, const float* noise, int64_t count,
+                 float cfg_scale, float sqrt_at, float sqrt_one_minus_at, float sqrt_aprev, float dir_coef, float sigma_t,
+                 float* x_out, float* pred_x0_out, cudaStream_t stream);
 /* image post-process (sd/image_generator.py:1017-1018,1151-1152): NHWC fp32 [n][hw][c_ld] -> uint8 HWC [n][hw][3],
  * clamp((x+1)/2,0,1)*255 truncated */
 int cb_image_to_u8(const void* src, int64_t n, int64_t hw, int64_t c_ld, uint8_t* dst, cudaStream_t stream);
