@@ -49,6 +49,11 @@ SD15_VAE = dict(embed_dim=4, lossconfig=None,
                               ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0))
 
 
+def _dtype_name():
+    from cremage_b200 import _lib
+    return _lib.DTYPE  # fp16 (the reference's GPU precision: model.half() + autocast) or bf16; fp32 accumulate
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -299,11 +304,11 @@ def run_ours(args):
         "metric": "SD1.5 512x512 images/sec (UNet + sampler + VAE decode)", "value": round(value, 4),
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": _dtype_name(), "data": "synthetic",
         "config": {"workload": f"SD1.5 txt2img 512x512, batch {b}/GPU, {steps}-step {sampler}, CFG {CFG_SCALE}, "
                                f"random-init weights, + AutoencoderKL decode to uint8 ({args.workload})",
                    "global_batch": b * world, "parallelism": f"dp{world} (batch sharded, NCCL all_gather of uint8 images)",
-                   "l2": "no flush: weights (1.8 GB bf16) + activations per step exceed the 126 MB L2",
+                   "l2": "no flush: weights (1.8 GB) + activations per step exceed the 126 MB L2",
                    "algorithmic_gflop_per_image": round(gf_per_image, 1)},
         "e2e": {"value": round(e2e_value, 4), "unit": "images/s",
                 "h2d_bytes_per_step": int(h_xT.numel() * 4 + h_cond.numel() * 4 + h_uncond.numel() * 4),

@@ -8,9 +8,15 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 from . import build as _build
 
 _LIB = None
+# fp16 (the reference's GPU precision, default) or bf16; one precision per process
+DTYPE = os.environ.get("CREMAGE_B200_DTYPE", "fp16").lower()
+if DTYPE not in _build.DTYPES:
+    raise ValueError(f"CREMAGE_B200_DTYPE must be one of {_build.DTYPES}, got {DTYPE!r}")
 
 
 class IGemmDesc(C.Structure):
@@ -44,6 +50,7 @@ _i64, _int, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 SIGNATURES = {
     "cb_last_error": [],
     "cb_version": [],
+    "cb_act_dtype": [],
     "cb_launch_count": [],
     "cb_igemm": [C.POINTER(IGemmDesc), _vp],
     "cb_attention": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp],
@@ -71,7 +78,7 @@ _RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64, "cb_grou
 
 
 def lib_path() -> Path:
-    return _build.LIB_PATH
+    return _build.lib_path(DTYPE)
 
 
 def load() -> C.CDLL:
@@ -79,7 +86,7 @@ def load() -> C.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
+    path = lib_path()
     if not path.exists():
         _build.build()
     lib = C.CDLL(str(path))
@@ -87,6 +94,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.cb_act_dtype() != {"fp16": 1, "bf16": 2}[DTYPE]:
+        raise RuntimeError(f"{path} was not built for {DTYPE}")
     _LIB = lib
     return lib
 

@@ -15,7 +15,15 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 CSRC = PKG_DIR / "csrc"
-LIB_PATH = PKG_DIR / "libcremage_b200.so"
+DTYPES = ("fp16", "bf16")
+
+
+def lib_path(dtype: str = "fp16") -> Path:
+    assert dtype in DTYPES, dtype
+    return PKG_DIR / f"libcremage_b200_{dtype}.so"
+
+
+LIB_PATH = lib_path("fp16")
 STAMP = PKG_DIR / ".libcremage_b200.stamp"
 
 SOURCES = ["runtime.cu", "igemm.cu", "attention.cu", "norm.cu", "elementwise.cu", "sampler.cu"]
@@ -46,25 +54,36 @@ def _source_hash() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into one shared library. Returns the library path."""
+def build(force: bool = False, verbose: bool = False):
+    """Compile every CUDA source for sm_100a into one shared library per activation dtype (fp16 and bf16 builds of
+    the same sources). Returns the list of library paths."""
     want = _source_hash()
-    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == want:
-        return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(REPO_ROOT / "include"), "-I", str(CSRC)]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [str(CSRC / s) for s in SOURCES] + ["-o", str(LIB_PATH)]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-        raise RuntimeError("nvcc failed building libcremage_b200.so")
-    if verbose:
-        sys.stderr.write(proc.stdout + proc.stderr)
+    paths = [lib_path(d) for d in DTYPES]
+    if not force and all(p.exists() for p in paths) and STAMP.exists() and STAMP.read_text().strip() == want:
+        return paths
+    procs = []
+    for d in DTYPES:
+        cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(REPO_ROOT / "include"), "-I", str(CSRC)]
+        if d == "fp16":
+            cmd += ["-DCB_FP16"]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        cmd += [str(CSRC / s) for s in SOURCES] + ["-o", str(lib_path(d))]
+        procs.append((d, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for d, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            sys.stderr.write(out)
+            failed = True
+        elif verbose:
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc failed building libcremage_b200")
     STAMP.write_text(want)
-    return LIB_PATH
+    return paths
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(p)
+    for p in build(force="--force" in sys.argv, verbose="-v" in sys.argv):
+        print(p)

@@ -19,7 +19,7 @@ struct AttnParams {
   int nq, nk, d, dpad, np, heads, stages;
   float scale_log2;
   uint32_t idesc_qk, idesc_pv, tmem_cols;
-  __nv_bfloat16* out;
+  act_t* out;
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -159,8 +159,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         float p0 = (c + e < nvalid) ? exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_new)) : 0.f;
         float p1 = (c + e + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_new)) : 0.f;
         // accumulate the row sum from the bf16-rounded values so numerator and denominator agree
-        const uint32_t u = pack_bf16x2(p0, p1);
-        const float2 back = unpack_bf16x2(u);
+        const uint32_t u = pack_act2(p0, p1);
+        const float2 back = unpack_act2(u);
         rs += back.x + back.y;
         pk[e >> 1] = u;
       }
@@ -201,7 +201,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const int q = qblk * ATT_BM + r;
   const int b = bh / p.heads, head = bh - b * p.heads;
   const float inv_l = 1.f / l_run;
-  __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.nq + q) * (static_cast<long long>(p.heads) * p.d) +
+  act_t* orow = p.out + (static_cast<long long>(b) * p.nq + q) * (static_cast<long long>(p.heads) * p.d) +
                         static_cast<long long>(head) * p.d;
 #pragma unroll 1
   for (int c = 0; c < p.dpad; c += 32) {
@@ -215,8 +215,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g + e]) * inv_l;
-          *reinterpret_cast<uint4*>(orow + c + g) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          *reinterpret_cast<uint4*>(orow + c + g) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
+                                                               pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
         }
       }
     }
@@ -246,25 +246,25 @@ extern "C" int cb_attention(const void* q, const void* k, const void* v, void* o
   {
     uint64_t dims[3] = {(uint64_t)dpad, (uint64_t)nq, (uint64_t)bh};
     uint64_t str[3] = {1, (uint64_t)dpad, (uint64_t)dpad * nq};
-    int rc = make_tmap_bf16(&mq, q, 3, dims, str, box);
+    int rc = make_tmap_act(&mq, q, 3, dims, str, box);
     if (rc) return rc;
   }
   {
     uint64_t dims[3] = {(uint64_t)dpad, (uint64_t)nk, (uint64_t)bh};
     uint64_t str[3] = {1, (uint64_t)dpad, (uint64_t)dpad * nk};
-    int rc = make_tmap_bf16(&mk, k, 3, dims, str, box);
+    int rc = make_tmap_act(&mk, k, 3, dims, str, box);
     if (rc) return rc;
-    rc = make_tmap_bf16(&mv, v, 3, dims, str, box);
+    rc = make_tmap_act(&mv, v, 3, dims, str, box);
     if (rc) return rc;
   }
   AttnParams p{};
   p.nq = (int)nq; p.nk = (int)nk; p.d = d; p.dpad = dpad; p.np = dpad / 64; p.heads = (int)heads;
   p.stages = dpad <= 128 ? 2 : 1;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-  p.idesc_pv = make_idesc_bf16(128, dpad, 0, 1);   // B = V is MN-major
+  p.idesc_qk = make_idesc_f16(128, 128, 0, 0);
+  p.idesc_pv = make_idesc_f16(128, dpad, 0, 1);   // B = V is MN-major
   p.tmem_cols = (128 + dpad) <= 256 ? 256u : 512u;
-  p.out = (__nv_bfloat16*)out;
+  p.out = (act_t*)out;
   const size_t smem = (size_t)(1 + 2 * p.stages) * p.np * PANEL_BYTES + 2 * PANEL_BYTES + 64;
   CB_REQUIRE(smem <= 227 * 1024, "cb_attention: needs %zu bytes of shared memory", smem);
   static thread_local bool configured = false;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
@@ -11,6 +12,25 @@
 #define CB_DEVINL __device__ __forceinline__
 
 namespace cb {
+
+// ----------------------------------------------------------------------------------------------
+// 16-bit activation / weight type: fp16 (-DCB_FP16, the reference's own GPU precision: model.half() + autocast,
+// sd/image_generator.py:489,748) or bf16 (default build flag absent).  Both feed tcgen05 kind::f16 at the same rate;
+// accumulation and all statistics are fp32 either way.
+// ----------------------------------------------------------------------------------------------
+#ifdef CB_FP16
+using act_t = __half;
+using act_t2 = __half2;
+#define CB_MMA_FMT 0u
+#define CB_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define CB_ACT_DTYPE_ID 1
+#else
+using act_t = __nv_bfloat16;
+using act_t2 = __nv_bfloat162;
+#define CB_MMA_FMT 1u
+#define CB_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define CB_ACT_DTYPE_ID 2
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // error plumbing (host)
@@ -40,9 +60,9 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                   \
   } while (0)
 
-// Encode a tiled bf16 tensor map (rank 2..5), SWIZZLE_128B, zero OOB fill.
+// Encode a tiled act_t (fp16 / bf16) tensor map (rank 2..5), SWIZZLE_128B, zero OOB fill.
 // dims / strides are in ELEMENTS (strides[0] is implied = 1); box in elements.
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+int make_tmap_act(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_elems, const uint32_t* box);
 
 // ----------------------------------------------------------------------------------------------
@@ -181,11 +201,11 @@ CB_DEVINL void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
 // ----------------------------------------------------------------------------------------------
 // UMMA descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp InstrDescriptor / SmemDescriptor)
 // ----------------------------------------------------------------------------------------------
-// Instruction descriptor, kind::f16, A/B = bf16, D = fp32.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+// Instruction descriptor, kind::f16, A/B = act_t (fp16 or bf16), D = fp32.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                         // c_format = F32
-         | (1u << 7)                       // a_format = BF16
-         | (1u << 10)                      // b_format = BF16
+         | (CB_MMA_FMT << 7)               // a_format (0 = F16, 1 = BF16)
+         | (CB_MMA_FMT << 10)              // b_format
          | (uint32_t(a_mn_major) << 15)    // a_major (0 = K)
          | (uint32_t(b_mn_major) << 16)    // b_major (0 = K)
          | (uint32_t(N >> 3) << 17)        // n_dim
@@ -206,14 +226,30 @@ __host__ __device__ constexpr uint64_t make_sdesc_sw128(uint32_t smem_addr, uint
 // ----------------------------------------------------------------------------------------------
 // numerics helpers
 // ----------------------------------------------------------------------------------------------
-CB_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+#ifdef CB_FP16
+CB_DEVINL float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }  // finite saturation, NaN passes
+CB_DEVINL uint32_t pack_act2(float lo, float hi) {
+  act_t2 v = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
   return *reinterpret_cast<uint32_t*>(&v);
 }
-CB_DEVINL float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+CB_DEVINL float2 unpack_act2(uint32_t u) {
+  act_t2 v = *reinterpret_cast<act_t2*>(&u);
+  return __half22float2(v);
+}
+CB_DEVINL act_t to_act(float x) { return __float2half_rn(sat_f16(x)); }
+CB_DEVINL float from_act(act_t x) { return __half2float(x); }
+#else
+CB_DEVINL uint32_t pack_act2(float lo, float hi) {
+  act_t2 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+CB_DEVINL float2 unpack_act2(uint32_t u) {
+  act_t2 v = *reinterpret_cast<act_t2*>(&u);
   return __bfloat1622float2(v);
 }
+CB_DEVINL act_t to_act(float x) { return __float2bfloat16(x); }
+CB_DEVINL float from_act(act_t x) { return __bfloat162float(x); }
+#endif
 CB_DEVINL float silu_f(float x) { return x / (1.f + __expf(-x)); }
 CB_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 

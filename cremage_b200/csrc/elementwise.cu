@@ -9,43 +9,43 @@ namespace cb {
 // NCHW (fp32 / fp16 / bf16) -> NHWC bf16, zero padding channels [c, c_pad). One thread per (n, pixel).
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, long long n, int c, long long hw, int c_pad, float scale,
-                                    __nv_bfloat16* __restrict__ dst) {
+                                    act_t* __restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * hw) return;
   const long long b = i / hw, p = i - b * hw;
   const T* s = src + b * c * hw + p;
-  __nv_bfloat16* d = dst + i * c_pad;
+  act_t* d = dst + i * c_pad;
   for (int ch = 0; ch < c_pad; ++ch) {
     float v = ch < c ? float(s[(long long)ch * hw]) * scale : 0.f;
-    d[ch] = __float2bfloat16(v);
+    d[ch] = to_act(v);
   }
 }
 
 // 1x1 channel mix (tiny c, cout <= 16) fused with NCHW fp32 -> NHWC bf16. One thread per (n, pixel).
 __global__ void pointwise_nchw_to_nhwc_kernel(const float* __restrict__ src, long long n, int c, long long hw,
                                               const float* __restrict__ w, const float* __restrict__ b, int cout,
-                                              int c_pad, float scale, __nv_bfloat16* __restrict__ dst) {
+                                              int c_pad, float scale, act_t* __restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * hw) return;
   const long long bi = i / hw, p = i - bi * hw;
   const float* s = src + bi * c * hw + p;
   float xin[16];
   for (int ci = 0; ci < c; ++ci) xin[ci] = s[(long long)ci * hw] * scale;
-  __nv_bfloat16* d = dst + i * c_pad;
+  act_t* d = dst + i * c_pad;
   for (int co = 0; co < c_pad; ++co) {
     float acc = 0.f;
     if (co < cout) {
       acc = b ? b[co] : 0.f;
       for (int ci = 0; ci < c; ++ci) acc = fmaf(w[co * c + ci], xin[ci], acc);
     }
-    d[co] = __float2bfloat16(acc);
+    d[co] = to_act(acc);
   }
 }
 
 // generic tiled transpose for wide channel counts: [n][c][hw] -> [n][hw][c_pad]
 template <typename T>
 __global__ void nchw_to_nhwc_tiled_kernel(const T* __restrict__ src, int c, long long hw, int c_pad, float scale,
-                                          __nv_bfloat16* __restrict__ dst) {
+                                          act_t* __restrict__ dst) {
   __shared__ float tile[32][33];
   const long long b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -59,7 +59,7 @@ __global__ void nchw_to_nhwc_tiled_kernel(const T* __restrict__ src, int c, long
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const long long p = p0 + j;
     const int ch = c0 + threadIdx.x;
-    if (p < hw && ch < c_pad) dst[(b * hw + p) * c_pad + ch] = __float2bfloat16(tile[threadIdx.x][j]);
+    if (p < hw && ch < c_pad) dst[(b * hw + p) * c_pad + ch] = to_act(tile[threadIdx.x][j]);
   }
 }
 
@@ -118,23 +118,23 @@ __global__ void parity_split_kernel(const uint4* __restrict__ src, long long n, 
 // sinusoidal timestep embedding, out[n][dim] = [cos(t*f) | sin(t*f)]; the frequency table f (fp32 [dim/2]) is built
 // on the host with the reference's own expression so it is bit-identical to the reference's.
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, long long n, int dim,
-                                          const float* __restrict__ freqs, __nv_bfloat16* __restrict__ out) {
+                                          const float* __restrict__ freqs, act_t* __restrict__ out) {
   const int half = dim / 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half) return;
   const long long b = i / half;
   const int k = int(i - b * half);
   const float arg = t[b] * freqs[k];
-  out[b * dim + k] = __float2bfloat16(cosf(arg));
-  out[b * dim + half + k] = __float2bfloat16(sinf(arg));
-  if ((dim & 1) && k == 0) out[b * dim + dim - 1] = __float2bfloat16(0.f);
+  out[b * dim + k] = to_act(cosf(arg));
+  out[b * dim + half + k] = to_act(sinf(arg));
+  if ((dim & 1) && k == 0) out[b * dim + dim - 1] = to_act(0.f);
 }
 
 // direct 3x3 conv (pad 1, stride 1) for tiny cin; wgt fp32 [3][3][cin][cout]; thread = (pixel, 8 output channels)
 template <int CIN>
-__global__ void conv3x3_small_cin_kernel(const __nv_bfloat16* __restrict__ src, long long n, int h, int w, int cin_ld,
+__global__ void conv3x3_small_cin_kernel(const act_t* __restrict__ src, long long n, int h, int w, int cin_ld,
                                          const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
-                                         __nv_bfloat16* __restrict__ out) {
+                                         act_t* __restrict__ out) {
   const int cg = cout >> 3;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * h * w * cg) return;
@@ -155,10 +155,10 @@ __global__ void conv3x3_small_cin_kernel(const __nv_bfloat16* __restrict__ src, 
     for (int kx = 0; kx < 3; ++kx) {
       const int xx = x + kx - 1;
       if (xx < 0 || xx >= w) continue;
-      const __nv_bfloat16* s = src + ((b * h + yy) * w + xx) * cin_ld;
+      const act_t* s = src + ((b * h + yy) * w + xx) * cin_ld;
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
-        const float a = __bfloat162float(s[ci]);
+        const float a = from_act(s[ci]);
         const float* wp = wgt + ((ky * 3 + kx) * CIN + ci) * cout + g * 8;
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
@@ -169,18 +169,18 @@ __global__ void conv3x3_small_cin_kernel(const __nv_bfloat16* __restrict__ src, 
       }
     }
   }
-  __nv_bfloat16* o = out + ((b * h + y) * w + x) * (long long)cout + g * 8;
-  *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                            pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  act_t* o = out + ((b * h + y) * w + x) * (long long)cout + g * 8;
+  *reinterpret_cast<uint4*>(o) = make_uint4(pack_act2(acc[0], acc[1]), pack_act2(acc[2], acc[3]),
+                                            pack_act2(acc[4], acc[5]), pack_act2(acc[6], acc[7]));
 }
 
-__global__ void silu_add_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ add,
-                                long long count, __nv_bfloat16* __restrict__ out) {
+__global__ void silu_add_kernel(const act_t* __restrict__ x, const act_t* __restrict__ add,
+                                long long count, act_t* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  float v = __bfloat162float(x[i]);
-  if (add) v += __bfloat162float(add[i]);
-  out[i] = __float2bfloat16(silu_f(v));
+  float v = from_act(x[i]);
+  if (add) v += from_act(add[i]);
+  out[i] = to_act(silu_f(v));
 }
 
 __global__ void image_to_u8_kernel(const float* __restrict__ src, long long npix, long long c_ld,
@@ -203,7 +203,7 @@ extern "C" int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_
                                float scale, void* dst, cudaStream_t stream) {
   CB_REQUIRE(src && dst && n > 0 && c > 0 && hw > 0 && c_pad >= c, "cb_nchw_to_nhwc: bad arguments");
   CB_REQUIRE(src_dtype >= 0 && src_dtype <= 2, "cb_nchw_to_nhwc: src_dtype must be 0 (f32), 1 (f16) or 2 (bf16)");
-  auto D = (__nv_bfloat16*)dst;
+  auto D = (act_t*)dst;
   if (c_pad <= 16) {
     const long long total = n * hw;
     const unsigned grid = (unsigned)((total + 255) / 256);
@@ -227,7 +227,7 @@ extern "C" int cb_pointwise_nchw_to_nhwc(const float* src, int64_t n, int64_t c,
   CB_REQUIRE(src && w && dst && n > 0 && hw > 0, "cb_pointwise_nchw_to_nhwc: bad arguments");
   CB_REQUIRE(c > 0 && c <= 16 && cout > 0 && cout <= c_pad && c_pad <= 16, "cb_pointwise_nchw_to_nhwc: c, cout, c_pad must be <= 16");
   const long long total = n * hw;
-  pointwise_nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, n, (int)c, hw, w, b, (int)cout, (int)c_pad, scale, (__nv_bfloat16*)dst);
+  pointwise_nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, n, (int)c, hw, w, b, (int)cout, (int)c_pad, scale, (act_t*)dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -238,7 +238,7 @@ extern "C" int cb_nhwc_to_nchw_f32(const void* src, int src_f32, int64_t n, int6
   CB_REQUIRE(src && dst && n > 0 && c > 0 && hw > 0 && c_ld >= c, "cb_nhwc_to_nchw_f32: bad arguments");
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
   if (src_f32) nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const float*)src, (int)c, hw, c_ld, dst);
-  else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (int)c, hw, c_ld, dst);
+  else nhwc_to_nchw_kernel<act_t><<<grid, block, 0, stream>>>((const act_t*)src, (int)c, hw, c_ld, dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -277,7 +277,7 @@ extern "C" int cb_timestep_embedding(const float* t, int64_t n, int dim, const f
                                      cudaStream_t stream) {
   CB_REQUIRE(t && freqs && out && n > 0 && dim >= 2, "cb_timestep_embedding: bad arguments");
   const long long total = n * (dim / 2);
-  timestep_embedding_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(t, n, dim, freqs, (__nv_bfloat16*)out);
+  timestep_embedding_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(t, n, dim, freqs, (act_t*)out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -290,8 +290,8 @@ extern "C" int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64
   CB_REQUIRE(cin_ld >= cin, "cb_conv3x3_small_cin: cin_ld < cin");
   const long long total = n * h * w * (cout / 8);
   const unsigned grid = (unsigned)((total + 255) / 256);
-  auto S = (const __nv_bfloat16*)src;
-  auto O = (__nv_bfloat16*)out;
+  auto S = (const act_t*)src;
+  auto O = (act_t*)out;
   switch (cin) {
     case 3: conv3x3_small_cin_kernel<3><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
     case 4: conv3x3_small_cin_kernel<4><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
@@ -306,7 +306,7 @@ extern "C" int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64
 
 extern "C" int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream) {
   CB_REQUIRE(x && out && count > 0, "cb_silu_add: bad arguments");
-  silu_add_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)add, count, (__nv_bfloat16*)out);
+  silu_add_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>((const act_t*)x, (const act_t*)add, count, (act_t*)out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

@@ -38,7 +38,7 @@ struct IGemmKParams {
   const float* bias;
   const float* rowbias;
   long long rowbias_ld;
-  const __nv_bfloat16* residual;
+  const act_t* residual;
   long long res_ld;
   void* out;
   long long out_ld;
@@ -165,7 +165,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         tmem_ld_wait();
         if (row_ok) {
           const int ocol0 = nt * half + c;  // output column
-          __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.out_ld + ocol0;
+          act_t* optr = reinterpret_cast<act_t*>(p.out) + row * p.out_ld + ocol0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (ocol0 + j < p.cout) {  // cout here = number of OUTPUT columns (inner dim), multiple of 8
@@ -177,7 +177,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
                 float x1 = __uint_as_float(xv[j + e + 1]) + __ldg(p.bias + tc0 + 1);
                 float g0 = __uint_as_float(gv[j + e]) + __ldg(p.bias + tc0 + half);
                 float g1 = __uint_as_float(gv[j + e + 1]) + __ldg(p.bias + tc0 + half + 1);
-                packed[e >> 1] = pack_bf16x2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+                packed[e >> 1] = pack_act2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
               }
               *reinterpret_cast<uint4*>(optr + j) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
             }
@@ -218,7 +218,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float2 t = unpack_bf16x2(ru[e]);
+                float2 t = unpack_act2(ru[e]);
                 f[2 * e] += t.x;
                 f[2 * e + 1] += t.y;
               }
@@ -236,18 +236,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               const int jj = cc - head * p.hd;
               const long long b = row / p.htokens;
               const long long tok = row - b * p.htokens;
-              __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out) + which * p.hwhich_stride +
+              act_t* optr = reinterpret_cast<act_t*>(p.out) + which * p.hwhich_stride +
                                     ((b * p.hheads + head) * p.htokens + tok) * p.hdpad + jj;
-              *reinterpret_cast<uint4*>(optr) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                           pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              *reinterpret_cast<uint4*>(optr) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
+                                                           pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
             } else if (p.out_f32) {
               float* optr = reinterpret_cast<float*>(p.out) + row * p.out_ld + col;
               *reinterpret_cast<float4*>(optr) = make_float4(f[0], f[1], f[2], f[3]);
               *reinterpret_cast<float4*>(optr + 4) = make_float4(f[4], f[5], f[6], f[7]);
             } else {
-              __nv_bfloat16* optr = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.out_ld + col;
-              *reinterpret_cast<uint4*>(optr) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                           pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+              act_t* optr = reinterpret_cast<act_t*>(p.out) + row * p.out_ld + col;
+              *reinterpret_cast<uint4*>(optr) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
+                                                           pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
             }
           } else {
             // ragged tail (cout not a multiple of 8, e.g. the 4- and 3-channel output convs): scalar path
@@ -256,10 +256,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               if (p.bias) x += __ldg(p.bias + col + e);
               if (p.rowbias) x += __ldg(p.rowbias + static_cast<long long>(n) * p.rowbias_ld + col + e);
               x = apply_act(x, p.act);
-              if (p.residual) x += __bfloat162float(p.residual[row * p.res_ld + col + e]);
+              if (p.residual) x += from_act(p.residual[row * p.res_ld + col + e]);
               x *= p.out_scale;
               if (p.out_f32) reinterpret_cast<float*>(p.out)[row * p.out_ld + col + e] = x;
-              else reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.out_ld + col + e] = __float2bfloat16(x);
+              else reinterpret_cast<act_t*>(p.out)[row * p.out_ld + col + e] = to_act(x);
             }
           }
         }
@@ -312,13 +312,13 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     uint64_t dims[4] = {(uint64_t)d->c0, (uint64_t)d->a_w, (uint64_t)d->a_h, (uint64_t)d->a_n};
     uint64_t str[4] = {1, (uint64_t)a0_ld, (uint64_t)a0_ld * d->a_w, (uint64_t)a0_ld * d->a_w * d->a_h};
     uint32_t box[4] = {BK, (uint32_t)d->tw, (uint32_t)d->th, (uint32_t)d->tn};
-    int rc = make_tmap_bf16(&mapA0, d->a0, 4, dims, str, box);
+    int rc = make_tmap_act(&mapA0, d->a0, 4, dims, str, box);
     if (rc) return rc;
     if (chunks1 > 0) {
       CB_REQUIRE(d->a1, "cb_igemm: c1 > 0 but a1 is null");
       uint64_t dims1[4] = {(uint64_t)d->c1, (uint64_t)d->a_w, (uint64_t)d->a_h, (uint64_t)d->a_n};
       uint64_t str1[4] = {1, (uint64_t)a1_ld, (uint64_t)a1_ld * d->a_w, (uint64_t)a1_ld * d->a_w * d->a_h};
-      rc = make_tmap_bf16(&mapA1, d->a1, 4, dims1, str1, box);
+      rc = make_tmap_act(&mapA1, d->a1, 4, dims1, str1, box);
       if (rc) return rc;
     } else {
       mapA1 = mapA0;
@@ -327,7 +327,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     uint64_t bstr[2] = {1, (uint64_t)ktot};
     uint32_t bbox[2] = {BK, (uint32_t)d->bn};
     CB_REQUIRE(d->wgt_rows > 0, "cb_igemm: wgt_rows must be > 0");
-    rc = make_tmap_bf16(&mapB, d->wgt, 2, bdims, bstr, bbox);
+    rc = make_tmap_act(&mapB, d->wgt, 2, bdims, bstr, bbox);
     if (rc) return rc;
   }
 
@@ -340,11 +340,11 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.taps = d->taps; p.chunks0 = chunks0; p.chunks1 = chunks1; p.num_k = num_k;
   for (int i = 0; i < 9; ++i) { p.tap_dw[i] = d->tap_dw[i]; p.tap_dh[i] = d->tap_dh[i]; p.tap_dn[i] = d->tap_dn[i]; }
   p.cout = (int)d->cout; p.bn = d->bn;
-  p.idesc = make_idesc_bf16(BM, d->bn, 0, 0);
+  p.idesc = make_idesc_f16(BM, d->bn, 0, 0);
   p.tmem_cols = (uint32_t)pow2_cols(d->bn);
   p.mode = d->mode; p.act = d->act; p.out_f32 = d->out_f32;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); p.res_ld = d->res_ld;
+  p.residual = reinterpret_cast<const act_t*>(d->residual); p.res_ld = d->res_ld;
   p.out = d->out; p.out_ld = d->out_ld;
   p.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
   p.hd = d->heads_d; p.hdpad = d->heads_dpad; p.hheads = d->heads_h; p.htokens = d->heads_tokens;

@@ -7,20 +7,20 @@ namespace cb {
 
 struct alignas(16) Vec8 { uint32_t u[4]; };
 
-CB_DEVINL Vec8 ld_vec8(const __nv_bfloat16* p) {
+CB_DEVINL Vec8 ld_vec8(const act_t* p) {
   Vec8 v;
   const uint4 t = *reinterpret_cast<const uint4*>(p);
   v.u[0] = t.x; v.u[1] = t.y; v.u[2] = t.z; v.u[3] = t.w;
   return v;
 }
-CB_DEVINL void st_vec8(__nv_bfloat16* p, const float (&f)[8]) {
+CB_DEVINL void st_vec8(act_t* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) =
-      make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
 }
 CB_DEVINL void unpack8(const Vec8& v, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = unpack_bf16x2(v.u[i]);
+    float2 t = unpack_act2(v.u[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -33,7 +33,7 @@ CB_DEVINL void unpack8(const Vec8& v, float (&f)[8]) {
 // in a fixed order and writes one partial per (image, split, group); the last CTA of an image to finish (ticket
 // counter) folds the partials in split order into stats[n][group][2].
 // ------------------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1,
+__global__ void gn_stats_kernel(const act_t* __restrict__ x0, int c0, const act_t* __restrict__ x1,
                                 int c1, long long hw, int groups, int P, long long pix_per_cta,
                                 float* __restrict__ stats, float* __restrict__ partials,
                                 unsigned int* __restrict__ counters) {
@@ -48,7 +48,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;  // blockDim % 32 == 0
 
   const int c = cv << 3;
-  const __nv_bfloat16* src;
+  const act_t* src;
   long long ld;
   if (c < c0) { src = x0 + (long long)n * hw * c0 + c; ld = c0; }
   else        { src = x1 + (long long)n * hw * c1 + (c - c0); ld = c1; }
@@ -129,10 +129,10 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
 }
 
 // GroupNorm pass 2: y = silu?((x - mean) * rstd * gamma + beta) -> bf16 [n][hw][C]
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1,
+__global__ void gn_apply_kernel(const act_t* __restrict__ x0, int c0, const act_t* __restrict__ x1,
                                 int c1, long long hw, int groups, int P, long long pix_per_cta, float eps,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                const float* __restrict__ stats, __nv_bfloat16* __restrict__ out) {
+                                const float* __restrict__ stats, act_t* __restrict__ out) {
   const int C = c0 + c1;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
@@ -154,11 +154,11 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
     a[i] = rstd * gamma[c + i];
     b[i] = beta[c + i] - mean * a[i];
   }
-  const __nv_bfloat16* src;
+  const act_t* src;
   long long ld;
   if (c < c0) { src = x0 + (long long)n * hw * c0 + c; ld = c0; }
   else        { src = x1 + (long long)n * hw * c1 + (c - c0); ld = c1; }
-  __nv_bfloat16* dst = out + (long long)n * hw * C + c;
+  act_t* dst = out + (long long)n * hw * C + c;
 
   const long long p_begin = (long long)blockIdx.x * pix_per_cta;
   long long p_end = p_begin + pix_per_cta;
@@ -196,14 +196,14 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
 // LayerNorm: one warp per row, the row lives in registers (two-pass mean / variance, exact in fp32).
 // ------------------------------------------------------------------------------------------------------------
 template <int MAXV>
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C, float eps,
+__global__ void layernorm_kernel(const act_t* __restrict__ x, long long rows, int C, float eps,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 __nv_bfloat16* __restrict__ out) {
+                                 act_t* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
   const int CV = C >> 3;
-  const __nv_bfloat16* src = x + row * C;
+  const act_t* src = x + row * C;
   float f[MAXV][8];
   float sum = 0.f;
 #pragma unroll
@@ -228,7 +228,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
   sq = warp_sum(sq);
   const float rstd = rsqrtf(sq / float(C) + eps);
-  __nv_bfloat16* dst = out + row * C;
+  act_t* dst = out + row * C;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int v = lane + i * 32;
@@ -252,7 +252,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
 // one CTA per row, the row is staged in shared memory.
 // ------------------------------------------------------------------------------------------------------------
 template <bool SRC_F32>
-__global__ void softmax_rows_kernel(const void* __restrict__ src, long long src_ld, __nv_bfloat16* __restrict__ dst,
+__global__ void softmax_rows_kernel(const void* __restrict__ src, long long src_ld, act_t* __restrict__ dst,
                                     long long dst_ld, long long cols, float scale) {
   extern __shared__ float s_row[];
   __shared__ float red[32];
@@ -267,7 +267,7 @@ __global__ void softmax_rows_kernel(const void* __restrict__ src, long long src_
       for (int e = 0; e < 4; ++e) { s_row[v * 4 + e] = f[e]; m = fmaxf(m, f[e]); }
     }
   } else {
-    const __nv_bfloat16* row = reinterpret_cast<const __nv_bfloat16*>(src) + (long long)blockIdx.x * src_ld;
+    const act_t* row = reinterpret_cast<const act_t*>(src) + (long long)blockIdx.x * src_ld;
     for (long long v = tid; v < (cols >> 3); v += blockDim.x) {
       float f[8];
       unpack8(ld_vec8(row + v * 8), f);
@@ -293,7 +293,7 @@ __global__ void softmax_rows_kernel(const void* __restrict__ src, long long src_
   sum = 0.f;
   for (int i = 0; i < nw; ++i) sum += red[i];
   const float inv = 1.f / sum;
-  __nv_bfloat16* orow = dst + (long long)blockIdx.x * dst_ld;
+  act_t* orow = dst + (long long)blockIdx.x * dst_ld;
   for (long long v = tid; v < (cols >> 3); v += blockDim.x) {
     float f[8];
 #pragma unroll
@@ -359,12 +359,12 @@ extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int
     configured = true;
   }
   dim3 grid((unsigned)g.splits, (unsigned)n);
-  gn_stats_kernel<<<grid, g.threads, g.smem, stream>>>((const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1,
+  gn_stats_kernel<<<grid, g.threads, g.smem, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1,
                                                        (int)c1, hw, groups, g.P, g.pix_per_cta, stats, partials, counters);
   CB_CHECK_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<grid, g.threads, 0, stream>>>((const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1, (int)c1, hw,
+  gn_apply_kernel<<<grid, g.threads, 0, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw,
                                                   groups, g.P, g.pix_per_cta, eps, gamma, beta, silu, stats,
-                                                  (__nv_bfloat16*)out);
+                                                  (act_t*)out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(2);
   return CB_OK;
@@ -378,8 +378,8 @@ extern "C" int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, c
   const int warps = 8;
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
   const int maxv = int((c / 8 + 31) / 32);
-  auto X = (const __nv_bfloat16*)x;
-  auto O = (__nv_bfloat16*)out;
+  auto X = (const act_t*)x;
+  auto O = (act_t*)out;
   if (maxv <= 2)       layernorm_kernel<2><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
   else if (maxv <= 4)  layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
   else if (maxv <= 8)  layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
@@ -401,8 +401,8 @@ extern "C" int cb_softmax_rows(const void* src, int src_f32, int64_t src_ld, voi
     CB_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  if (src_f32) softmax_rows_kernel<true><<<(unsigned)rows, 256, smem, stream>>>(src, src_ld, (__nv_bfloat16*)dst, dst_ld, cols, scale);
-  else softmax_rows_kernel<false><<<(unsigned)rows, 256, smem, stream>>>(src, src_ld, (__nv_bfloat16*)dst, dst_ld, cols, scale);
+  if (src_f32) softmax_rows_kernel<true><<<(unsigned)rows, 256, smem, stream>>>(src, src_ld, (act_t*)dst, dst_ld, cols, scale);
+  else softmax_rows_kernel<false><<<(unsigned)rows, 256, smem, stream>>>(src, src_ld, (act_t*)dst, dst_ld, cols, scale);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

@@ -43,7 +43,7 @@ static EncodeTiledFn resolve_encode() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+int make_tmap_act(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                    const uint32_t* box) {
   EncodeTiledFn fn = resolve_encode();
   if (!fn) {
@@ -51,11 +51,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     return CB_ERR_NODRIVER;
   }
   if (rank < 2 || rank > 5) {
-    set_error("make_tmap_bf16: rank %d unsupported", rank);
+    set_error("make_tmap_act: rank %d unsupported", rank);
     return CB_ERR_INVALID;
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) {
-    set_error("make_tmap_bf16: base pointer %p is not 16-byte aligned", base);
+    set_error("make_tmap_act: base pointer %p is not 16-byte aligned", base);
     return CB_ERR_INVALID;
   }
   cuuint64_t gdim[5];
@@ -67,18 +67,18 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     gbox[i] = box[i];
     estr[i] = 1;
     if (box[i] == 0 || box[i] > 256) {
-      set_error("make_tmap_bf16: box[%d] = %u out of range", i, box[i]);
+      set_error("make_tmap_act: box[%d] = %u out of range", i, box[i]);
       return CB_ERR_INVALID;
     }
     if (i > 0) {
       gstr[i - 1] = strides_elems[i] * 2;  // bytes
       if (gstr[i - 1] % 16 != 0) {
-        set_error("make_tmap_bf16: stride[%d] = %llu bytes is not a multiple of 16", i, (unsigned long long)gstr[i - 1]);
+        set_error("make_tmap_act: stride[%d] = %llu bytes is not a multiple of 16", i, (unsigned long long)gstr[i - 1]);
         return CB_ERR_INVALID;
       }
     }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, gbox,
+  CUresult r = fn(out, CB_TMAP_DTYPE, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, gbox,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -93,4 +93,5 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 extern "C" const char* cb_last_error(void) { return cb::g_err; }
 extern "C" int cb_version(void) { return 100; }
+extern "C" int cb_act_dtype(void) { return CB_ACT_DTYPE_ID; }
 extern "C" int64_t cb_launch_count(void) { return (int64_t)cb::g_launches.load(); }

@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from . import ops
 
-BF16 = torch.bfloat16
+ACT = ops.ACT
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:
@@ -78,7 +78,7 @@ def zero_workspace(tag: str, shape: Tuple[int, ...], device: torch.device) -> to
     if buf is None:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("workspace allocation during CUDA-graph capture; run one eager call first")
-        buf = torch.zeros(shape, dtype=BF16, device=device)
+        buf = torch.zeros(shape, dtype=ACT, device=device)
         _WORKSPACES[key] = buf
     return buf
 

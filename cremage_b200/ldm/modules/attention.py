@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...engine import BF16, PackedModule, f32, head_pad, packw, require_cuda, zero_workspace
+from ...engine import ACT, PackedModule, f32, head_pad, packw, require_cuda, zero_workspace
 
 GEGLU_BN = 128  # N tile of the fused GEGLU projection (x / gate rows interleaved per 64 output columns)
 
@@ -75,7 +75,7 @@ class FeedForward(PackedModule):
     def forward(self, x):
         require_cuda(x, "FeedForward.forward")
         shp = x.shape
-        y = self._run(x.reshape(-1, shp[-1]).to(BF16).contiguous())
+        y = self._run(x.reshape(-1, shp[-1]).to(ACT).contiguous())
         return y.view(*shp[:-1], self.dim_out).to(x.dtype)
 
 
@@ -138,11 +138,11 @@ class CrossAttention(PackedModule):
         if mask is not None:
             raise NotImplementedError("cremage_b200: attention masks are not used on the SD path")
         b, n, _ = x.shape
-        x2d = x.reshape(b * n, -1).to(BF16).contiguous()
+        x2d = x.reshape(b * n, -1).to(ACT).contiguous()
         ctx2d, nk = None, n
         if context is not None:
             nk = context.shape[1]
-            ctx2d = context.reshape(b * nk, -1).to(BF16).contiguous()
+            ctx2d = context.reshape(b * nk, -1).to(ACT).contiguous()
         elif not self.is_self and self.context_dim != self.query_dim:
             raise ValueError("context is required for this CrossAttention")
         return self._run(x2d, b, n, ctx2d, nk).view(b, n, self.query_dim).to(x.dtype)
@@ -195,11 +195,11 @@ class BasicTransformerBlock(PackedModule):
     def forward(self, x, context=None):
         require_cuda(x, "BasicTransformerBlock.forward")
         b, n, c = x.shape
-        x2d = x.reshape(b * n, c).to(BF16).contiguous()
+        x2d = x.reshape(b * n, c).to(ACT).contiguous()
         ctx2d, nk = None, n
         if context is not None:
             nk = context.shape[1]
-            ctx2d = context.reshape(b * nk, -1).to(BF16).contiguous()
+            ctx2d = context.reshape(b * nk, -1).to(ACT).contiguous()
         return self._run(x2d, b, n, ctx2d, nk).view(b, n, c).to(x.dtype)
 
 
@@ -257,6 +257,6 @@ class SpatialTransformer(PackedModule):
         ctx2d, nk = None, 0
         if context is not None:
             nk = context.shape[1]
-            ctx2d = context.reshape(-1, context.shape[-1]).to(BF16).contiguous()
+            ctx2d = context.reshape(-1, context.shape[-1]).to(ACT).contiguous()
         y = self._run(ops.nchw_to_nhwc(x), ctx2d, nk)
         return ops.nhwc_to_nchw_f32(y).to(x.dtype)

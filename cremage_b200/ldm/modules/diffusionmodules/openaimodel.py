@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .... import ops
-from ....engine import BF16, GraphedCall, PackedModule, f32, packw, require_cuda
+from ....engine import ACT, GraphedCall, PackedModule, f32, packw, require_cuda
 from ..attention import SpatialTransformer
 from .util import conv_nd, linear, normalization, timestep_freqs, zero_module
 
@@ -178,7 +178,7 @@ class ResBlock(TimestepBlock, PackedModule):
 
     def _emb_out(self, emb: torch.Tensor) -> torch.Tensor:
         p = self.packed(emb.device)
-        semb = ops.silu_add(emb.to(BF16).contiguous())
+        semb = ops.silu_add(emb.to(ACT).contiguous())
         return ops.igemm(semb, p["we"], self.out_channels, bias=p["be"], out_f32=True)
 
     def forward(self, x, emb):
@@ -215,7 +215,7 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
         ctx2d, nk = None, 0
         if context is not None:
             nk = context.shape[1]
-            ctx2d = context.reshape(-1, context.shape[-1]).to(BF16).contiguous()
+            ctx2d = context.reshape(-1, context.shape[-1]).to(ACT).contiguous()
         y = self._run(ops.nchw_to_nhwc(x), None, lambda layer: layer._emb_out(emb), ctx2d, nk)
         return ops.nhwc_to_nchw_f32(y).to(x.dtype)
 
@@ -408,7 +408,7 @@ class UNetModel(PackedModule):
         semb = ops.igemm(e, p["te2w"], ted, bias=p["te2b"], act=ops.ACT_SILU)  # silu(emb): every consumer applies SiLU first
         emb_all = ops.igemm(semb, p["embw"], self._emb_total, bias=p["embb"], out_f32=True)
         nk = context.shape[1]
-        ctx2d = context.reshape(n * nk, context.shape[-1]).to(BF16).contiguous()
+        ctx2d = context.reshape(n * nk, context.shape[-1]).to(ACT).contiguous()
 
         h = ops.nchw_to_nhwc(x, c_pad=p["cin_pad"])
         h = ops.conv3x3_small_cin(h, p["cin"], p["inw"], p["inb"], mc)

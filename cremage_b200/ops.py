@@ -17,7 +17,8 @@ from ._lib import IGemmDesc, check
 EPI_LINEAR, EPI_GEGLU, EPI_HEADS = 0, 1, 2
 ACT_NONE, ACT_SILU = 0, 1
 
-BF16 = torch.bfloat16
+# 16-bit activation / weight dtype of the loaded library build (fp16 unless CREMAGE_B200_DTYPE=bf16)
+ACT = torch.float16 if _lib.DTYPE == "fp16" else torch.bfloat16
 
 
 def _stream() -> int:
@@ -102,7 +103,7 @@ def pack_weight(w: torch.Tensor, splits: Optional[Tuple[int, int]] = None) -> to
         blk = torch.zeros(o, kh * kw, ceil64(n), dtype=torch.float32, device=w.device)
         blk[:, :, :n] = wt[:, :, lo:lo + n]
         parts.append(blk)
-    return torch.cat(parts, dim=2).reshape(o, -1).to(BF16).contiguous()
+    return torch.cat(parts, dim=2).reshape(o, -1).to(ACT).contiguous()
 
 
 def pack_geglu(w: torch.Tensor, b: torch.Tensor, bn: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -192,14 +193,14 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     heads: (d, dpad, n_heads, tokens_per_batch, which_stride) for EPI_HEADS (then `out` must be given).
     """
     _need_cuda(a0, a1, wgt, bias, rowbias, residual, out)
-    assert a0.dtype == BF16 and wgt.dtype == BF16 and a0.is_contiguous() and wgt.is_contiguous()
+    assert a0.dtype == ACT and wgt.dtype == ACT and a0.is_contiguous() and wgt.is_contiguous()
     if a0.dim() == 2:
         a_n, a_h, a_w, c0 = 1, 1, a0.shape[0], a0.shape[1]
     else:
         a_n, a_h, a_w, c0 = a0.shape
     c1 = 0
     if a1 is not None:
-        assert a1.dtype == BF16 and a1.is_contiguous() and tuple(a1.shape[:-1]) == tuple(a0.shape[:-1])
+        assert a1.dtype == ACT and a1.is_contiguous() and tuple(a1.shape[:-1]) == tuple(a0.shape[:-1])
         c1 = a1.shape[-1]
     n, h, w = out_grid if out_grid is not None else (a_n, a_h, a_w)
     rows = n * h * w
@@ -210,7 +211,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
     if out is None:
         ld = out_ld if out_ld is not None else cout
-        out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else BF16, device=a0.device)
+        out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
     ld = out_ld if out_ld is not None else (out.shape[-1] if mode != EPI_HEADS else 0)
 
     d = IGemmDesc()
@@ -234,7 +235,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     d.residual, d.res_ld = _p(residual), (residual.shape[-1] if residual is not None else 0)
     if residual is not None:
-        assert residual.dtype == BF16 and residual.is_contiguous()
+        assert residual.dtype == ACT and residual.is_contiguous()
     d.out, d.out_ld, d.out_f32 = _p(out), ld, int(out.dtype == torch.float32)
     d.out_scale = out_scale
     if heads is not None:
@@ -254,7 +255,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
     """q,k,v: bf16 [batch*heads, tokens, dpad] -> out bf16 [batch*nq, heads*d]."""
     _need_cuda(q, k, v)
     if out is None:
-        out = torch.empty((batch * nq, heads * d), dtype=BF16, device=q.device)
+        out = torch.empty((batch * nq, heads * d), dtype=ACT, device=q.device)
     _launch("cb_attention", lambda: _lib.load().cb_attention(_p(q), _p(k), _p(v), _p(out), batch, heads, nq, nk, d, dpad, scale, _stream()),
             flops=4.0 * batch * heads * nq * nk * d)
     return out
@@ -263,10 +264,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
 def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(scale * s) over the last dim of a 2-D fp32 or bf16 tensor -> bf16 `out` (in place for bf16 if None)."""
     _need_cuda(s, out)
-    assert s.dim() == 2 and s.stride(1) == 1 and s.dtype in (BF16, torch.float32)
+    assert s.dim() == 2 and s.stride(1) == 1 and s.dtype in (ACT, torch.float32)
     if out is None:
-        out = s if s.dtype == BF16 else torch.empty(s.shape, dtype=BF16, device=s.device)
-    assert out.dtype == BF16 and out.shape == s.shape and out.stride(1) == 1
+        out = s if s.dtype == ACT else torch.empty(s.shape, dtype=ACT, device=s.device)
+    assert out.dtype == ACT and out.shape == s.shape and out.stride(1) == 1
     _launch("cb_softmax_rows", lambda: _lib.load().cb_softmax_rows(_p(s), int(s.dtype == torch.float32), s.stride(0), _p(out), out.stride(0),
                                       s.shape[0], s.shape[1], scale, _stream()))
     return out
@@ -282,7 +283,7 @@ def pointwise_nchw_to_nhwc(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.T
     _need_cuda(x, w, b)
     x = x.contiguous().float()
     n, c, h, wd = x.shape
-    out = torch.empty((n, h, wd, c_pad), dtype=BF16, device=x.device)
+    out = torch.empty((n, h, wd, c_pad), dtype=ACT, device=x.device)
     _launch("cb_pointwise_nchw_to_nhwc", lambda: _lib.load().cb_pointwise_nchw_to_nhwc(_p(x), n, c, h * wd, _p(w), _p(b), w.shape[0], c_pad, scale, _p(out),
                                                 _stream()))
     return out
@@ -292,12 +293,12 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
               x1: Optional[torch.Tensor] = None, groups: int = 32) -> torch.Tensor:
     """GroupNorm(+SiLU) over NHWC bf16 [N,H,W,C0] (+ [N,H,W,C1] concatenated on channels) -> [N,H,W,C0+C1]."""
     _need_cuda(x0, x1, gamma, beta)
-    assert x0.dtype == BF16 and x0.is_contiguous() and gamma.dtype == torch.float32
+    assert x0.dtype == ACT and x0.is_contiguous() and gamma.dtype == torch.float32
     n = x0.shape[0]
     hw = x0.numel() // (n * x0.shape[-1])
     c0 = x0.shape[-1]
     c1 = 0 if x1 is None else x1.shape[-1]
-    out = torch.empty((*x0.shape[:-1], c0 + c1), dtype=BF16, device=x0.device)
+    out = torch.empty((*x0.shape[:-1], c0 + c1), dtype=ACT, device=x0.device)
     ws = int(_lib.load().cb_groupnorm_workspace_bytes(c0 + c1, n, hw, groups))
     if ws <= 0:
         raise ValueError(f"groupnorm: unsupported shape n={n} hw={hw} c={c0 + c1} groups={groups}")
@@ -310,7 +311,7 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     _need_cuda(x, gamma, beta)
-    assert x.dtype == BF16 and x.is_contiguous()
+    assert x.dtype == ACT and x.is_contiguous()
     c = x.shape[-1]
     rows = x.numel() // c
     out = torch.empty_like(x)
@@ -330,7 +331,7 @@ def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None, scale: float = 1.
     x = x.contiguous()
     n, c, h, w = x.shape
     c_pad = c if c_pad is None else c_pad
-    out = torch.empty((n, h, w, c_pad), dtype=BF16, device=x.device)
+    out = torch.empty((n, h, w, c_pad), dtype=ACT, device=x.device)
     _launch("cb_nchw_to_nhwc", lambda: _lib.load().cb_nchw_to_nhwc(_p(x), _SRC_DTYPE[x.dtype], n, c, h * w, c_pad, scale, _p(out), _stream()))
     return out
 
@@ -349,7 +350,7 @@ def nhwc_to_nchw_f32(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
 def upsample2x(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     n, h, w, c = x.shape
-    out = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=ACT, device=x.device)
     _launch("cb_upsample2x_nhwc", lambda: _lib.load().cb_upsample2x_nhwc(_p(x), n, h, w, c, _p(out), _stream()))
     return out
 
@@ -357,7 +358,7 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
 def parity_split(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     n, h, w, c = x.shape
-    out = torch.empty((4, n, h // 2, w // 2, c), dtype=BF16, device=x.device)
+    out = torch.empty((4, n, h // 2, w // 2, c), dtype=ACT, device=x.device)
     _launch("cb_parity_split_nhwc", lambda: _lib.load().cb_parity_split_nhwc(_p(x), n, h, w, c, _p(out), _stream()))
     return out
 
@@ -365,7 +366,7 @@ def parity_split(x: torch.Tensor) -> torch.Tensor:
 def timestep_embedding(t: torch.Tensor, dim: int, freqs: torch.Tensor) -> torch.Tensor:
     _need_cuda(t, freqs)
     assert t.dtype == torch.float32 and freqs.dtype == torch.float32 and freqs.numel() == dim // 2
-    out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
+    out = torch.empty((t.shape[0], dim), dtype=ACT, device=t.device)
     _launch("cb_timestep_embedding", lambda: _lib.load().cb_timestep_embedding(_p(t), t.shape[0], dim, _p(freqs), _p(out), _stream()))
     return out
 
@@ -374,7 +375,7 @@ def conv3x3_small_cin(x: torch.Tensor, cin: int, wgt: torch.Tensor, bias: Option
     """x: NHWC bf16 [N,H,W,cin_ld]; wgt fp32 [3,3,cin,cout]."""
     _need_cuda(x, wgt, bias)
     n, h, w, cin_ld = x.shape
-    out = torch.empty((n, h, w, cout), dtype=BF16, device=x.device)
+    out = torch.empty((n, h, w, cout), dtype=ACT, device=x.device)
     _launch("cb_conv3x3_small_cin", lambda: _lib.load().cb_conv3x3_small_cin(_p(x), n, h, w, cin, cin_ld, _p(wgt), _p(bias), cout, _p(out), _stream()))
     return out
 

@@ -31,6 +31,9 @@ typedef struct CUstream_st* cudaStream_t;
  * ------------------------------------------------------------------------------------------------------------- */
 const char* cb_last_error(void);
 int cb_version(void);
+/* 16-bit storage type this build of the library computes in: 1 = fp16, 2 = bf16 ("bf16" in the comments below
+ * means this type).  fp16 is the reference's own GPU precision (model.half() + autocast) and the default. */
+int cb_act_dtype(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 int64_t cb_launch_count(void);
 

@@ -2,6 +2,8 @@
 import pytest
 import torch
 
+from cremage_b200.ops import ACT  # fp16 (default) or bf16 build of the library
+
 pytestmark = pytest.mark.gpu
 
 
@@ -10,7 +12,7 @@ def _mk(bh, n, d, dpad, seed):
     x = torch.randn(bh, n, d, generator=g)
     xp = torch.zeros(bh, n, dpad)
     xp[..., :d] = x
-    return xp.to(torch.bfloat16)
+    return xp.to(ACT)
 
 
 @pytest.mark.parametrize("batch,heads,nq,nk,d,dpad", [

@@ -3,6 +3,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from cremage_b200.ops import ACT  # fp16 (default) or bf16 build of the library
+
 pytestmark = pytest.mark.gpu
 
 
@@ -27,26 +29,26 @@ def _close(got, want, rtol=2e-2, atol=2e-2):
 @pytest.mark.parametrize("m,k,n", [(128, 64, 32), (1000, 320, 320), (154, 768, 640), (4096, 1280, 1280), (256, 96, 72)])
 def test_plain_gemm_bias_residual(m, k, n):
     ops = _ops()
-    a = _rand(m, k, seed=1).to(torch.bfloat16)
+    a = _rand(m, k, seed=1).to(ACT)
     w = _rand(n, k, scale=k ** -0.5, seed=2)
     b = _rand(n, seed=3)
-    r = _rand(m, n, seed=4).to(torch.bfloat16)
+    r = _rand(m, n, seed=4).to(ACT)
     wp = ops.pack_weight(w).cuda()
     out = ops.igemm(a.cuda(), wp, n, bias=b.cuda(), residual=r.cuda())
     torch.cuda.synchronize()
-    want = a.float() @ w.to(torch.bfloat16).float().t() + b + r.float()
+    want = a.float() @ w.to(ACT).float().t() + b + r.float()
     _close(out, want)
 
 
 def test_gemm_f32_out_ragged_cout_and_silu():
     ops = _ops()
     m, k, n = 300, 128, 4
-    a = _rand(m, k, seed=1).to(torch.bfloat16)
+    a = _rand(m, k, seed=1).to(ACT)
     w = _rand(n, k, scale=k ** -0.5, seed=2)
     b = _rand(n, seed=3)
     out = ops.igemm(a.cuda(), ops.pack_weight(w).cuda(), n, bias=b.cuda(), out_f32=True, act=ops.ACT_SILU)
     torch.cuda.synchronize()
-    want = F.silu(a.float() @ w.to(torch.bfloat16).float().t() + b)
+    want = F.silu(a.float() @ w.to(ACT).float().t() + b)
     assert out.dtype == torch.float32 and out.shape == (m, n)
     _close(out, want, rtol=1e-3, atol=1e-3)
 
@@ -54,27 +56,27 @@ def test_gemm_f32_out_ragged_cout_and_silu():
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 128), (3, 8, 8, 128, 64), (1, 64, 64, 64, 160), (2, 32, 32, 192, 64), (1, 12, 20, 64, 32)])
 def test_conv3x3_stride1(n, h, w, cin, cout):
     ops = _ops()
-    x = _rand(n, cin, h, w, seed=5).to(torch.bfloat16)
+    x = _rand(n, cin, h, w, seed=5).to(ACT)
     wt = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=6)
     b = _rand(cout, seed=7)
     emb = _rand(n, cout, seed=8)
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
     out = ops.igemm(x_nhwc, ops.pack_weight(wt).cuda(), cout, taps=ops.TAPS_3X3, bias=b.cuda(), rowbias=emb.cuda())
     torch.cuda.synchronize()
-    want = F.conv2d(x.float(), wt.to(torch.bfloat16).float(), b, padding=1) + emb[:, :, None, None]
+    want = F.conv2d(x.float(), wt.to(ACT).float(), b, padding=1) + emb[:, :, None, None]
     _close(out.view(n, h, w, cout).permute(0, 3, 1, 2), want)
 
 
 def test_conv3x3_two_sources_is_concat():
     ops = _ops()
     n, h, w, c0, c1, cout = 2, 16, 16, 128, 64, 128
-    x0 = _rand(n, c0, h, w, seed=1).to(torch.bfloat16)
-    x1 = _rand(n, c1, h, w, seed=2).to(torch.bfloat16)
+    x0 = _rand(n, c0, h, w, seed=1).to(ACT)
+    x1 = _rand(n, c1, h, w, seed=2).to(ACT)
     wt = _rand(cout, c0 + c1, 3, 3, scale=(9 * (c0 + c1)) ** -0.5, seed=3)
     out = ops.igemm(x0.permute(0, 2, 3, 1).contiguous().cuda(), ops.pack_weight(wt, (c0, c1)).cuda(), cout,
                     a1=x1.permute(0, 2, 3, 1).contiguous().cuda(), taps=ops.TAPS_3X3)
     torch.cuda.synchronize()
-    want = F.conv2d(torch.cat([x0, x1], 1).float(), wt.to(torch.bfloat16).float(), None, padding=1)
+    want = F.conv2d(torch.cat([x0, x1], 1).float(), wt.to(ACT).float(), None, padding=1)
     _close(out.view(n, h, w, cout).permute(0, 3, 1, 2), want)
 
 
@@ -82,28 +84,28 @@ def test_conv3x3_two_sources_is_concat():
 def test_conv3x3_stride2_parity_planes(n, h, w, c):
     ops = _ops()
     cout = 64
-    x = _rand(n, c, h, w, seed=1).to(torch.bfloat16)
+    x = _rand(n, c, h, w, seed=1).to(ACT)
     wt = _rand(cout, c, 3, 3, scale=(9 * c) ** -0.5, seed=2)
     b = _rand(cout, seed=3)
     xs = ops.parity_split(x.permute(0, 2, 3, 1).contiguous().cuda())
     out = ops.igemm(xs.view(4 * n, h // 2, w // 2, c), ops.pack_weight(wt).cuda(), cout, out_grid=(n, h // 2, w // 2),
                     taps=ops.taps_3x3_stride2(n), bias=b.cuda())
     torch.cuda.synchronize()
-    want = F.conv2d(x.float(), wt.to(torch.bfloat16).float(), b, stride=2, padding=1)
+    want = F.conv2d(x.float(), wt.to(ACT).float(), b, stride=2, padding=1)
     _close(out.view(n, h // 2, w // 2, cout).permute(0, 3, 1, 2), want)
 
 
 def test_geglu_epilogue():
     ops = _ops()
     m, dim, inner = 512, 64, 256
-    a = _rand(m, dim, seed=1).to(torch.bfloat16)
+    a = _rand(m, dim, seed=1).to(ACT)
     w = _rand(2 * inner, dim, scale=dim ** -0.5, seed=2)
     b = _rand(2 * inner, seed=3)
     bn = 128
     wq, bq = ops.pack_geglu(w, b, bn)
     out = ops.igemm(a.cuda(), ops.pack_weight(wq).cuda(), inner, bias=bq.cuda(), mode=ops.EPI_GEGLU, bn=bn)
     torch.cuda.synchronize()
-    y = a.float() @ w.to(torch.bfloat16).float().t() + b
+    y = a.float() @ w.to(ACT).float().t() + b
     xh, gate = y.chunk(2, dim=-1)
     _close(out, xh * F.gelu(gate))
 
@@ -112,13 +114,13 @@ def test_heads_epilogue_scatter():
     ops = _ops()
     batch, tokens, dim, heads, d, dpad = 2, 96, 64, 2, 40, 64
     inner = heads * d
-    a = _rand(batch * tokens, dim, seed=1).to(torch.bfloat16)
+    a = _rand(batch * tokens, dim, seed=1).to(ACT)
     w = _rand(3 * inner, dim, scale=dim ** -0.5, seed=2)
-    qkv = torch.zeros(3, batch * heads, tokens, dpad, dtype=torch.bfloat16, device="cuda")
+    qkv = torch.zeros(3, batch * heads, tokens, dpad, dtype=ACT, device="cuda")
     ops.igemm(a.cuda(), ops.pack_weight(w).cuda(), 3 * inner, mode=ops.EPI_HEADS, out=qkv,
               heads=(d, dpad, heads, tokens, batch * heads * tokens * dpad))
     torch.cuda.synchronize()
-    y = (a.float() @ w.to(torch.bfloat16).float().t()).view(batch, tokens, 3, heads, d).permute(2, 0, 3, 1, 4)
+    y = (a.float() @ w.to(ACT).float().t()).view(batch, tokens, 3, heads, d).permute(2, 0, 3, 1, 4)
     got = qkv.view(3, batch, heads, tokens, dpad).float().cpu()
     _close(got[..., :d], y)
     assert got[..., d:].abs().max().item() == 0.0

@@ -5,6 +5,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from cremage_b200.ops import ACT  # fp16 (default) or bf16 build of the library
+
 pytestmark = pytest.mark.gpu
 
 
@@ -20,7 +22,7 @@ def _rand(*shape, seed=0, scale=1.0, shift=0.0):
 def test_groupnorm_silu(n, h, w, c0, c1, silu, eps):
     from cremage_b200 import ops
     c = c0 + c1
-    x = _rand(n, c, h, w, seed=1, scale=1.5, shift=0.3).to(torch.bfloat16)
+    x = _rand(n, c, h, w, seed=1, scale=1.5, shift=0.3).to(ACT)
     gamma = _rand(c, seed=2, scale=0.2, shift=1.0)
     beta = _rand(c, seed=3, scale=0.2)
     xn = x.permute(0, 2, 3, 1).contiguous().cuda()
@@ -38,7 +40,7 @@ def test_groupnorm_silu(n, h, w, c0, c1, silu, eps):
 @pytest.mark.parametrize("rows,c", [(1000, 320), (64, 640), (257, 1280), (33, 64), (5, 2048)])
 def test_layernorm(rows, c):
     from cremage_b200 import ops
-    x = _rand(rows, c, seed=1, scale=2.0, shift=-0.5).to(torch.bfloat16)
+    x = _rand(rows, c, seed=1, scale=2.0, shift=-0.5).to(ACT)
     gamma = _rand(c, seed=2, scale=0.2, shift=1.0)
     beta = _rand(c, seed=3, scale=0.2)
     out = ops.layernorm(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5)
@@ -49,7 +51,7 @@ def test_layernorm(rows, c):
 
 def test_softmax_rows_inplace():
     from cremage_b200 import ops
-    s = _rand(300, 4096, seed=1, scale=3.0).to(torch.bfloat16)
+    s = _rand(300, 4096, seed=1, scale=3.0).to(ACT)
     got = ops.softmax_rows_(s.clone().cuda(), 0.5)
     torch.cuda.synchronize()
     want = torch.softmax(s.float() * 0.5, dim=-1)
@@ -62,10 +64,10 @@ def test_layout_roundtrip_and_upsample_and_parity():
     nhwc = ops.nchw_to_nhwc(x.cuda(), c_pad=8, scale=0.5)
     want = torch.zeros(2, 16, 16, 8)
     want[..., :4] = (x * 0.5).permute(0, 2, 3, 1)
-    assert torch.equal(nhwc.float().cpu(), want.to(torch.bfloat16).float())
+    assert torch.equal(nhwc.float().cpu(), want.to(ACT).float())
     back = ops.nhwc_to_nchw_f32(nhwc, 4)
-    assert torch.equal(back.cpu(), want[..., :4].to(torch.bfloat16).float().permute(0, 3, 1, 2))
-    y = _rand(2, 64, 6, 10, seed=2).to(torch.bfloat16)
+    assert torch.equal(back.cpu(), want[..., :4].to(ACT).float().permute(0, 3, 1, 2))
+    y = _rand(2, 64, 6, 10, seed=2).to(ACT)
     wide = ops.nchw_to_nhwc(y.cuda())
     assert torch.equal(wide.cpu(), y.permute(0, 2, 3, 1))
     up = ops.upsample2x(wide)
@@ -86,7 +88,7 @@ def test_timestep_embedding_and_small_conv():
     args = t[:, None] * freqs[None]
     want = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     assert (got.float().cpu() - want).abs().max().item() < 1e-2
-    x = _rand(2, 4, 16, 16, seed=1).to(torch.bfloat16)
+    x = _rand(2, 4, 16, 16, seed=1).to(ACT)
     w = _rand(320, 4, 3, 3, seed=2, scale=1 / 6)
     b = _rand(320, seed=3)
     xn = ops.nchw_to_nhwc(x.cuda(), c_pad=8)

@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Per-shape timing of the hot kernels on the SD1.5 shapes (UNet batch 16 = 8 images with CFG), CUDA events.
+
+    python tools/prof_kernels.py [--only attn|igemm|norm] [--iters 10] [--batch 16]
+
+Prints one line per shape: ms, achieved TFLOP/s or GB/s, fraction of the measured peak. Also the target of the ncu
+captures kept under profiles/ (run with --iters 1 under ncu).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cremage_b200 import ops  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops"], d["hbm_gbs"]
+    return 1590.0, 6650.0
+
+
+def timeit(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def act(*shape):
+    return (torch.randn(*shape, device="cuda") * 0.5).to(ops.ACT)
+
+
+def bench_attn(B, iters, warm):
+    tf_peak, _ = peaks()
+    print("== attention (cb_attention) ==")
+    for name, heads, nq, nk, d in [("self 64x64 d40", 8, 4096, 4096, 40), ("self 32x32 d80", 8, 1024, 1024, 80),
+                                   ("self 16x16 d160", 8, 256, 256, 160), ("self 8x8 d160", 8, 64, 64, 160),
+                                   ("cross 64x64 d40", 8, 4096, 77, 40), ("cross 32x32 d80", 8, 1024, 77, 80),
+                                   ("cross 16x16 d160", 8, 256, 77, 160)]:
+        dpad = (d + 63) // 64 * 64
+        q, k, v = act(B * heads, nq, dpad), act(B * heads, nk, dpad), act(B * heads, nk, dpad)
+        ms = timeit(lambda: ops.attention(q, k, v, B, heads, nq, nk, d, dpad, d ** -0.5), iters, warm)
+        fl = 4.0 * B * heads * nq * nk * d
+        print(f"{name:22s} bh={B * heads:4d} nq={nq:5d} nk={nk:5d} d={d:3d}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  "
+              f"{fl / ms / 1e9 / tf_peak:6.1%} of burst peak")
+
+
+def bench_igemm(B, iters, warm):
+    tf_peak, _ = peaks()
+    print("== implicit GEMM (cb_igemm) ==")
+    shapes = [
+        # (name, n, h, w, cin, cout, taps)
+        ("conv3x3 320->320 @64", B, 64, 64, 320, 320, 9), ("conv3x3 640->640 @32", B, 32, 32, 640, 640, 9),
+        ("conv3x3 1280->1280 @16", B, 16, 16, 1280, 1280, 9), ("conv3x3 1280->1280 @8", B, 8, 8, 1280, 1280, 9),
+        ("conv3x3 2560->1280 @8", B, 8, 8, 2560, 1280, 9), ("conv3x3 2560->1280 @16", B, 16, 16, 2560, 1280, 9),
+        ("conv3x3 1920->640 @32", B, 32, 32, 1920, 640, 9), ("conv3x3 960->320 @64", B, 64, 64, 960, 320, 9),
+        ("conv3x3 640->320 @64", B, 64, 64, 640, 320, 9), ("conv3x3 640->640 @64", B, 64, 64, 640, 640, 9),
+        ("linear 320->320 @4096", 1, 1, B * 4096, 320, 320, 1), ("linear 640->640 @1024", 1, 1, B * 1024, 640, 640, 1),
+        ("linear 1280->1280 @256", 1, 1, B * 256, 1280, 1280, 1), ("linear 320->960 qkv", 1, 1, B * 4096, 320, 960, 1),
+        ("linear 1280->320 ff2", 1, 1, B * 4096, 1280, 320, 1), ("linear 5120->1280 ff2", 1, 1, B * 256, 5120, 1280, 1),
+        ("conv3x3 512->512 @64 vae", B // 2, 64, 64, 512, 512, 9), ("conv3x3 512->512 @128 vae", B // 2, 128, 128, 512, 512, 9),
+        ("conv3x3 256->256 @256 vae", B // 2, 256, 256, 256, 256, 9), ("conv3x3 128->128 @512 vae", B // 2, 512, 512, 128, 128, 9),
+    ]
+    for name, n, h, w, cin, cout, taps in shapes:
+        x = act(n, h, w, cin)
+        wt = ops.pack_weight(torch.randn(cout, cin, 3 if taps == 9 else 1, 3 if taps == 9 else 1, device="cuda") * (taps * cin) ** -0.5)
+        bias = torch.zeros(cout, device="cuda")
+        tp = ops.TAPS_3X3 if taps == 9 else ops.TAPS_1X1
+        out = torch.empty(n * h * w, cout, dtype=ops.ACT, device="cuda")
+        ms = timeit(lambda: ops.igemm(x, wt, cout, taps=tp, bias=bias, out=out), iters, warm)
+        fl = 2.0 * n * h * w * taps * cin * cout
+        print(f"{name:28s} M={n * h * w:7d} K={taps * cin:6d} N={cout:5d}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  "
+              f"{fl / ms / 1e9 / tf_peak:6.1%} of burst peak")
+    # GEGLU
+    for name, m, dim in [("geglu 320->2560 @4096", B * 4096, 320), ("geglu 640->5120 @1024", B * 1024, 640),
+                         ("geglu 1280->10240 @256", B * 256, 1280)]:
+        x = act(m, dim)
+        w = torch.randn(8 * dim, dim, device="cuda") * dim ** -0.5
+        b = torch.zeros(8 * dim, device="cuda")
+        wq, bq = ops.pack_geglu(w, b, 128)
+        wq = ops.pack_weight(wq)
+        ms = timeit(lambda: ops.igemm(x, wq, 4 * dim, bias=bq, mode=ops.EPI_GEGLU, bn=128), iters, warm)
+        fl = 2.0 * m * dim * 8 * dim
+        print(f"{name:28s} M={m:7d} K={dim:6d} N={8 * dim:5d}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  "
+              f"{fl / ms / 1e9 / tf_peak:6.1%} of burst peak")
+
+
+def bench_norm(B, iters, warm):
+    _, bw_peak = peaks()
+    print("== GroupNorm+SiLU / LayerNorm ==")
+    for name, n, h, w, c in [("gn 320 @64", B, 64, 64, 320), ("gn 640 @32", B, 32, 32, 640), ("gn 1280 @16", B, 16, 16, 1280),
+                             ("gn 2560 @8", B, 8, 8, 2560), ("gn 960 @64", B, 64, 64, 960),
+                             ("gn 128 @512 vae", B // 2, 512, 512, 128), ("gn 256 @256 vae", B // 2, 256, 256, 256),
+                             ("gn 512 @128 vae", B // 2, 128, 128, 512)]:
+        x = act(n, h, w, c)
+        g, b = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+        ms = timeit(lambda: ops.groupnorm(x, g, b, 1e-5, True), iters, warm)
+        by = 4.0 * n * h * w * c
+        print(f"{name:22s} elems={n * h * w * c / 1e6:8.1f} M: {ms * 1e3:9.1f} us  {by / ms / 1e6:8.1f} GB/s  {by / ms / 1e6 / bw_peak:6.1%} of HBM peak")
+    for name, rows, c in [("ln 320 @4096", B * 4096, 320), ("ln 640 @1024", B * 1024, 640), ("ln 1280 @256", B * 256, 1280)]:
+        x = act(rows, c)
+        g, b = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+        ms = timeit(lambda: ops.layernorm(x, g, b), iters, warm)
+        by = 4.0 * rows * c
+        print(f"{name:22s} elems={rows * c / 1e6:8.1f} M: {ms * 1e3:9.1f} us  {by / ms / 1e6:8.1f} GB/s  {by / ms / 1e6 / bw_peak:6.1%} of HBM peak")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="all")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16)
+    a = ap.parse_args()
+    if a.only in ("all", "attn"):
+        bench_attn(a.batch, a.iters, a.warm)
+    if a.only in ("all", "igemm"):
+        bench_igemm(a.batch, a.iters, a.warm)
+    if a.only in ("all", "norm"):
+        bench_norm(a.batch, a.iters, a.warm)
