@@ -1,59 +1,97 @@
 // Fused flash-style attention for sm_100a:  O = softmax(scale * Q K^T) V, never materialising the score matrix.
-//   S = Q K^T      tcgen05.mma  (A = Q tile [128 x dpad], B = K tile [128 x dpad], both K-major)  -> TMEM cols [0,128)
-//   online softmax 128 threads, one query row each, tcgen05.ld of S, exp2 with running max / sum in fp32
-//   O += P V       tcgen05.mma  (A = P [128 x 128] bf16 written to swizzled smem, B = V tile, MN-major) -> TMEM cols [128, 128+dpad)
+//
+//   S = Q K^T      tcgen05.mma  (A = Q tile [128 x dpad], B = K tile [128 x dpad], both K-major)  -> TMEM
+//   online softmax one thread per query row: tcgen05.ld of S, exp2 (packed 16-bit MUFU in the fp16 build), lazy
+//                  running-max rescale of the TMEM accumulator, P -> swizzled smem
+//   O += P V       tcgen05.mma  (A = P [128 x 128], B = V tile, MN-major)                          -> TMEM
+//
+// Warp-specialised, one CTA = up to two 128-row query tiles of one (batch, head) sharing every K/V tile:
+//   warp 0        TMA producer (Q once, K/V ring)
+//   warp 1        TMEM allocator + single-thread MMA issuer
+//   warps 2..5    softmax warpgroup 0 (query tile 0)      warps 6..9    softmax warpgroup 1 (query tile 1)
+// The two warpgroups run half a phase apart: while one does exp/convert on its S tile the tensor core computes the
+// other's P*V and next Q*K^T, so MUFU / FMA issue and the tensor pipe stay busy together.
+// The softmax row sum costs nothing when dpad > d: column d of V holds 1.0 (contract of cb_attention), so the
+// tensor core accumulates sum_j P_ij into O[:, d].
 // Q/K/V arrive through 3-D TMA boxes from the per-head padded layout [bh][tokens][dpad] written by the QKV
-// projection epilogue (CB_EPI_HEADS).  One CTA = 128 query rows of one (batch, head); for dpad = 64 two CTAs are
-// co-resident per SM so one CTA's softmax overlaps the other's MMAs.
+// projection epilogue (CB_EPI_HEADS).
 // Replaces the attention cores at ldm/modules/attention.py:418-423 (Doggettx), :646-657 (Original), :811 (xformers).
 #include "common.cuh"
 #include "cremage_b200.h"
 
 namespace cb {
 
-constexpr int ATT_BM = 128;   // query rows per CTA
-constexpr int ATT_BN = 128;   // kv rows per iteration
-constexpr int PANEL_BYTES = 128 * 128;  // [128 rows][64 bf16]
+constexpr int ATT_BM = 128;             // query rows per warpgroup tile
+constexpr int ATT_BN = 128;             // kv rows per iteration
+constexpr int PANEL_BYTES = 128 * 128;  // [128 rows][64 x 16-bit]
+constexpr int ATT_THREADS = 320;
+constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
-  int nq, nk, d, dpad, np, heads, stages;
+  int nq, nk, d, dpad, np, heads, stages, nwg, use_ones;
   float scale_log2;
   uint32_t idesc_qk, idesc_pv, tmem_cols;
   act_t* out;
 };
 
-__global__ void __launch_bounds__(128, 1)
+// p = 2^(s * scale - m) for two scores -> packed 16-bit pair
+CB_DEVINL uint32_t exp2_pack(float s0, float s1, float scale, float m) {
+  const float a0 = fmaf(s0, scale, -m), a1 = fmaf(s1, scale, -m);
+#ifdef CB_FP16
+  const __half2 h = __floats2half2_rn(a0, a1);
+  uint32_t r;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&h)));
+  return r;
+#else
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  return pack_act2(e0, e1);
+#endif
+}
+
+template <bool USE_ONES>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();  // swizzled tiles need a 1024-byte aligned base
   const uint32_t tile_bytes = uint32_t(p.np) * PANEL_BYTES;
-  const uint32_t sQ = base;
-  const uint32_t sK = sQ + tile_bytes;                       // [stages]
-  const uint32_t sV = sK + uint32_t(p.stages) * tile_bytes;  // [stages]
-  const uint32_t sP = sV + uint32_t(p.stages) * tile_bytes;  // 2 panels
-  const uint32_t bars = sP + 2u * PANEL_BYTES;
-  const uint32_t q_bar = bars, s_bar = bars + 8;
-  auto k_bar = [&](int s) { return bars + 16u + 8u * uint32_t(s); };
-  auto v_bar = [&](int s) { return bars + 32u + 8u * uint32_t(s); };
-  const uint32_t tmem_slot = bars + 48u;
+  const uint32_t sQ = base;                                    // [nwg]
+  const uint32_t sK = sQ + uint32_t(p.nwg) * tile_bytes;       // [stages]
+  const uint32_t sV = sK + uint32_t(p.stages) * tile_bytes;    // [stages]
+  const uint32_t sP = sV + uint32_t(p.stages) * tile_bytes;    // [nwg][2 panels]
+  const uint32_t bars = sP + uint32_t(p.nwg) * 2u * PANEL_BYTES;
+  const uint32_t q_full = bars;
+  auto k_full = [&](int s) { return bars + 8u + 8u * uint32_t(s); };
+  auto k_empty = [&](int s) { return bars + 24u + 8u * uint32_t(s); };
+  auto v_full = [&](int s) { return bars + 40u + 8u * uint32_t(s); };
+  auto v_empty = [&](int s) { return bars + 56u + 8u * uint32_t(s); };
+  auto s_full = [&](int w) { return bars + 72u + 8u * uint32_t(w); };
+  auto p_full = [&](int w) { return bars + 88u + 8u * uint32_t(w); };
+  const uint32_t tmem_slot = bars + 104u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int qblk = blockIdx.x, bh = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.y;
   const int nblk = (p.nk + ATT_BN - 1) / ATT_BN;
+  const int q_first = blockIdx.x * p.nwg * ATT_BM;                              // first query row of this CTA
+  const int nact = (p.nwg == 2 && q_first + ATT_BM < p.nq) ? 2 : 1;            // active query tiles
 
   if (tid == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
-    mbar_init(q_bar, 1);
-    mbar_init(s_bar, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(k_bar(s), 1); mbar_init(v_bar(s), 1); }
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), ATT_BM);
+    }
     fence_mbar_init();
   }
-  if (warp == 0) {
+  if (warp == 1) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
@@ -61,169 +99,206 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base;          // 128 columns
-  const uint32_t tO = tmem_base + 128u;   // dpad columns
+  auto tS = [&](int w) { return tmem_base + uint32_t(w) * 128u; };
+  auto tO = [&](int w) { return tmem_base + uint32_t(p.nwg) * 128u + uint32_t(w) * uint32_t(p.dpad); };
 
-  auto load_tile = [&](const CUtensorMap* m, uint32_t dst, uint32_t bar, int row0) {
-    mbar_expect_tx(bar, tile_bytes);
-    for (int pn = 0; pn < p.np; ++pn) tma_load_3d(dst + uint32_t(pn) * PANEL_BYTES, m, bar, pn * 64, row0, bh);
-  };
-  auto issue_qk = [&](int kstage) {
-    const uint32_t kb = sK + uint32_t(kstage) * tile_bytes;
-    const int ksteps = p.dpad / 16;
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint32_t off = uint32_t(ks >> 2) * PANEL_BYTES + uint32_t(ks & 3) * 32u;
-      umma_bf16(tS, make_sdesc_sw128(sQ + off, 16, 1024), make_sdesc_sw128(kb + off, 16, 1024), p.idesc_qk, ks != 0);
-    }
-  };
-  auto issue_pv = [&](int vstage, bool accumulate) {
-    const uint32_t vb = sV + uint32_t(vstage) * tile_bytes;
-    for (int ks = 0; ks < ATT_BN / 16; ++ks) {
-      const uint32_t aoff = uint32_t(ks >> 2) * PANEL_BYTES + uint32_t(ks & 3) * 32u;   // P: K-major
-      const uint32_t boff = uint32_t(ks) * 2048u;                                        // V: 16 kv rows = 2 atoms
-      umma_bf16(tO, make_sdesc_sw128(sP + aoff, 16, 1024), make_sdesc_sw128(vb + boff, PANEL_BYTES, 1024), p.idesc_pv,
-                (accumulate || ks != 0) ? 1u : 0u);
-    }
-  };
-
-  if (tid == 0) {
-    load_tile(&mapQ, sQ, q_bar, qblk * ATT_BM);
-    load_tile(&mapK, sK, k_bar(0), 0);
-    load_tile(&mapV, sV, v_bar(0), 0);
-    mbar_wait(q_bar, 0);
-    mbar_wait(k_bar(0), 0);
-    tc_fence_after();
-    issue_qk(0);
-    umma_commit(s_bar);
-  }
-
-  const int r = tid;                                   // query row within the tile == TMEM lane
-  const uint32_t lane_off = uint32_t(warp * 32) << 16;
-  float m_run = -INFINITY, l_run = 0.f;
-  const uint32_t p_row = sP + uint32_t(r) * 128u;
-  const uint32_t sw = uint32_t(r & 7);
-
-  for (int j = 0; j < nblk; ++j) {
-    mbar_wait(s_bar, uint32_t(j & 1));   // S_j ready, every earlier MMA (PV_{j-1}) retired
-    tc_fence_after();
-    if (tid == 0) {
-      if (p.stages == 1 && j > 0) load_tile(&mapV, sV, v_bar(0), j * ATT_BN);   // V buffer freed by PV_{j-1}
-      if (j + 1 < nblk) {
-        const int st = (j + 1) % p.stages;
-        load_tile(&mapK, sK + uint32_t(st) * tile_bytes, k_bar(st), (j + 1) * ATT_BN);
-        if (p.stages == 2) load_tile(&mapV, sV + uint32_t(st) * tile_bytes, v_bar(st), (j + 1) * ATT_BN);
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, uint32_t(nact) * tile_bytes);
+      for (int w = 0; w < nact; ++w)
+        for (int pn = 0; pn < p.np; ++pn)
+          tma_load_3d(sQ + uint32_t(w) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapQ, q_full, pn * 64,
+                      q_first + w * ATT_BM, bh);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j % p.stages;
+        const uint32_t ph = uint32_t((j / p.stages) & 1);
+        mbar_wait(k_empty(st), ph ^ 1u);
+        mbar_expect_tx(k_full(st), tile_bytes);
+        for (int pn = 0; pn < p.np; ++pn)
+          tma_load_3d(sK + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapK, k_full(st), pn * 64, j * ATT_BN, bh);
+        mbar_wait(v_empty(st), ph ^ 1u);
+        mbar_expect_tx(v_full(st), tile_bytes);
+        for (int pn = 0; pn < p.np; ++pn)
+          tma_load_3d(sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapV, v_full(st), pn * 64, j * ATT_BN, bh);
       }
     }
-    const int kv0 = j * ATT_BN;
-    const int nvalid = min(ATT_BN, p.nk - kv0);   // columns >= nvalid are padding (K rows zero filled)
-
-    // ---- pass 1: row maximum of the raw scores
-    float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < ATT_BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tS + lane_off + uint32_t(c), v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; ++e)
-        if (c + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
-    }
-    const float m_new = fmaxf(m_run, mx * p.scale_log2);
-    const float alpha = exp2f(m_run - m_new);   // 0 on the first block (m_run = -inf)
-    m_run = m_new;
-
-    // ---- rescale the running output if any row of this warp moved its maximum
-    if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll 1
-      for (int c = 0; c < p.dpad; c += 32) {
-        uint32_t o[32];
-        tmem_ld32(tO + lane_off + uint32_t(c), o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-        tmem_st32(tO + lane_off + uint32_t(c), o);
-      }
-      tmem_st_wait();
-    }
-
-    // ---- pass 2: P = exp2(S*scale - m), row sum, bf16 -> swizzled smem (K-major A operand of the PV MMA)
-    float rs = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < ATT_BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tS + lane_off + uint32_t(c), v);
-      tmem_ld_wait();
-      uint32_t pk[16];
-#pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        float p0 = (c + e < nvalid) ? exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_new)) : 0.f;
-        float p1 = (c + e + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_new)) : 0.f;
-        // accumulate the row sum from the bf16-rounded values so numerator and denominator agree
-        const uint32_t u = pack_act2(p0, p1);
-        const float2 back = unpack_act2(u);
-        rs += back.x + back.y;
-        pk[e >> 1] = u;
-      }
-      const uint32_t panel = uint32_t(c >> 6) * PANEL_BYTES;
-      const uint32_t chunk0 = uint32_t((c & 63) >> 3);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t addr = p_row + panel + (((chunk0 + uint32_t(g)) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * g]), "r"(pk[4 * g + 1]),
-                     "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
-                     : "memory");
-      }
-    }
-    l_run = l_run * alpha + rs;
-
-    fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async proxy
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      auto issue_qk = [&](int w, int kstage) {
+        const uint32_t qb = sQ + uint32_t(w) * tile_bytes, kb = sK + uint32_t(kstage) * tile_bytes;
+        const int ksteps = p.dpad / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = uint32_t(ks >> 2) * PANEL_BYTES + uint32_t(ks & 3) * 32u;
+          umma_bf16(tS(w), make_sdesc_sw128(qb + off, 16, 1024), make_sdesc_sw128(kb + off, 16, 1024), p.idesc_qk, ks != 0);
+        }
+      };
+      auto issue_pv = [&](int w, int vstage, bool accumulate) {
+        const uint32_t pb = sP + uint32_t(w) * 2u * PANEL_BYTES, vb = sV + uint32_t(vstage) * tile_bytes;
+        for (int ks = 0; ks < ATT_BN / 16; ++ks) {
+          const uint32_t aoff = uint32_t(ks >> 2) * PANEL_BYTES + uint32_t(ks & 3) * 32u;  // P: K-major
+          const uint32_t boff = uint32_t(ks) * 2048u;                                       // V: 16 kv rows = 2 atoms
+          umma_bf16(tO(w), make_sdesc_sw128(pb + aoff, 16, 1024), make_sdesc_sw128(vb + boff, PANEL_BYTES, 1024),
+                    p.idesc_pv, (accumulate || ks != 0) ? 1u : 0u);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full(0), 0);
       tc_fence_after();
-      const int vs = j % p.stages;
-      mbar_wait(v_bar(vs), uint32_t((j / p.stages) & 1));
-      tc_fence_after();
-      issue_pv(vs, j > 0);
-      if (j + 1 < nblk) {
-        const int ks = (j + 1) % p.stages;
-        mbar_wait(k_bar(ks), uint32_t(((j + 1) / p.stages) & 1));
+      for (int w = 0; w < nact; ++w) {
+        issue_qk(w, 0);
+        umma_commit(s_full(w));
+      }
+      umma_commit(k_empty(0));
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j % p.stages;
+        const uint32_t ph = uint32_t((j / p.stages) & 1);
+        const bool more = (j + 1 < nblk);
+        const int st1 = (j + 1) % p.stages;
+        const uint32_t ph1 = uint32_t(((j + 1) / p.stages) & 1);
+        for (int w = 0; w < nact; ++w) {
+          mbar_wait(p_full(w), uint32_t(j & 1));   // softmax w: S consumed, P written, O rescaled
+          if (w == 0) mbar_wait(v_full(st), ph);
+          tc_fence_after();
+          issue_pv(w, st, j > 0);
+          if (w == nact - 1) umma_commit(v_empty(st));
+          if (more) {
+            if (w == 0) { mbar_wait(k_full(st1), ph1); tc_fence_after(); }
+            issue_qk(w, st1);
+          }
+          umma_commit(s_full(w));                   // S_w(j+1) ready / final O_w ready
+          if (more && w == nact - 1) umma_commit(k_empty(st1));
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int w = (warp - 2) >> 2;
+    if (w < nact) {
+      const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+      const int r = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
+      const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+      const uint32_t p_row = sP + uint32_t(w) * 2u * PANEL_BYTES + uint32_t(r) * 128u;
+      const uint32_t sw = uint32_t(r & 7);
+      const uint32_t tSw = tS(w) + lane_off, tOw = tO(w) + lane_off;
+      float m_used = -INFINITY, l_run = 0.f;
+
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(s_full(w), uint32_t(j & 1));
         tc_fence_after();
-        issue_qk(ks);
-      }
-      umma_commit(s_bar);
-    }
-  }
-
-  // ---- epilogue: O / l -> out[b][q][head*d + :]
-  mbar_wait(s_bar, uint32_t(nblk & 1));
-  tc_fence_after();
-  const int q = qblk * ATT_BM + r;
-  const int b = bh / p.heads, head = bh - b * p.heads;
-  const float inv_l = 1.f / l_run;
-  act_t* orow = p.out + (static_cast<long long>(b) * p.nq + q) * (static_cast<long long>(p.heads) * p.d) +
-                        static_cast<long long>(head) * p.d;
+        uint32_t s[128];
+        tmem_ld32(tSw + 0u, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld32(tSw + 32u, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        tmem_ld32(tSw + 64u, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+        tmem_ld32(tSw + 96u, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+        tmem_ld_wait();
+        const int nvalid = p.nk - j * ATT_BN;
+        if (nvalid < ATT_BN) {   // ragged last block: K rows beyond nk were zero filled -> mask
+#pragma unroll
+          for (int e = 0; e < 128; ++e)
+            if (e >= nvalid) s[e] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 128; e += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[e]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[e + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[e + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[e + 3]));
+        }
+        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        if (j == 0) {
+          m_used = m_blk;
+        } else {
+          const bool need = (m_blk - m_used) > RESCALE_TAU;
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? exp2f(m_used - m_blk) : 1.f;
+            if (need) m_used = m_blk;
+            if (!USE_ONES) l_run *= alpha;
 #pragma unroll 1
-  for (int c = 0; c < p.dpad; c += 32) {
-    uint32_t o[32];
-    tmem_ld32(tO + lane_off + uint32_t(c), o);
-    tmem_ld_wait();
-    if (q < p.nq) {
+            for (int c = 0; c < p.dpad; c += 32) {
+              uint32_t o[32];
+              tmem_ld32(tOw + uint32_t(c), o);
+              tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 32; g += 8) {
-        if (c + g < p.d) {
-          float f[8];
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tOw + uint32_t(c), o);
+            }
+            tmem_st_wait();
+          }
+        }
+        float rs = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g + e]) * inv_l;
-          *reinterpret_cast<uint4*>(orow + c + g) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
-                                                               pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+        for (int c = 0; c < ATT_BN; c += 32) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            pk[e >> 1] = exp2_pack(__uint_as_float(s[c + e]), __uint_as_float(s[c + e + 1]), p.scale_log2, m_used);
+            if (!USE_ONES) {
+              const float2 b = unpack_act2(pk[e >> 1]);
+              rs += b.x + b.y;
+            }
+          }
+          const uint32_t panel = uint32_t(c >> 6) * PANEL_BYTES;
+          const uint32_t chunk0 = uint32_t((c & 63) >> 3);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t addr = p_row + panel + (((chunk0 + uint32_t(g)) ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * g]), "r"(pk[4 * g + 1]),
+                         "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
+                         : "memory");
+          }
+        }
+        if (!USE_ONES) l_run += rs;
+        fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async proxy
+        tc_fence_before();
+        mbar_arrive(p_full(w));
+      }
+
+      // ---- epilogue: O / l -> out[b][q][head*d + :]
+      mbar_wait(s_full(w), uint32_t(nblk & 1));
+      tc_fence_after();
+      const int q = q_first + w * ATT_BM + r;
+      const int b = bh / p.heads, head = bh - b * p.heads;
+      float inv_l;
+      if (USE_ONES) {
+        uint32_t o[32];
+        tmem_ld32(tOw + uint32_t(p.d & ~31), o);
+        tmem_ld_wait();
+        float l = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (e == (p.d & 31)) l = __uint_as_float(o[e]);
+        inv_l = 1.f / l;
+      } else {
+        inv_l = 1.f / l_run;
+      }
+      act_t* orow = p.out + (static_cast<long long>(b) * p.nq + q) * (static_cast<long long>(p.heads) * p.d) +
+                    static_cast<long long>(head) * p.d;
+#pragma unroll 1
+      for (int c = 0; c < p.d; c += 32) {
+        uint32_t o[32];
+        tmem_ld32(tOw + uint32_t(c), o);
+        tmem_ld_wait();
+        if (q < p.nq) {
+#pragma unroll
+          for (int g = 0; g < 32; g += 8) {
+            if (c + g < p.d) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g + e]) * inv_l;
+              *reinterpret_cast<uint4*>(orow + c + g) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
+                                                                   pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+            }
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -259,21 +334,26 @@ extern "C" int cb_attention(const void* q, const void* k, const void* v, void* o
   }
   AttnParams p{};
   p.nq = (int)nq; p.nk = (int)nk; p.d = d; p.dpad = dpad; p.np = dpad / 64; p.heads = (int)heads;
-  p.stages = dpad <= 128 ? 2 : 1;
+  p.nwg = dpad <= 128 ? 2 : 1;           // TMEM: nwg * (128 + dpad) columns <= 512
+  p.stages = dpad <= 64 ? 2 : 1;         // smem: (nwg + 2*stages) * np panels + nwg * 2 panels
+  p.use_ones = dpad > d;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.idesc_qk = make_idesc_f16(128, 128, 0, 0);
   p.idesc_pv = make_idesc_f16(128, dpad, 0, 1);   // B = V is MN-major
-  p.tmem_cols = (128 + dpad) <= 256 ? 256u : 512u;
+  p.tmem_cols = 512u;
   p.out = (act_t*)out;
-  const size_t smem = (size_t)(1 + 2 * p.stages) * p.np * PANEL_BYTES + 2 * PANEL_BYTES + 64;
+  const size_t smem = (size_t)(p.nwg + 2 * p.stages) * p.np * PANEL_BYTES + (size_t)p.nwg * 2 * PANEL_BYTES + 128;
   CB_REQUIRE(smem <= 227 * 1024, "cb_attention: needs %zu bytes of shared memory", smem);
   static thread_local bool configured = false;
   if (!configured) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  dim3 grid((unsigned)((nq + ATT_BM - 1) / ATT_BM), (unsigned)bh);
-  attention_kernel<<<grid, 128, smem, stream>>>(mq, mk, mv, p);
+  const int rows_per_cta = p.nwg * ATT_BM;
+  dim3 grid((unsigned)((nq + rows_per_cta - 1) / rows_per_cta), (unsigned)bh);
+  if (p.use_ones) attention_kernel<true><<<grid, ATT_THREADS, smem, stream>>>(mq, mk, mv, p);
+  else attention_kernel<false><<<grid, ATT_THREADS, smem, stream>>>(mq, mk, mv, p);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

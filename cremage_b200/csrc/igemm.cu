@@ -36,8 +36,10 @@ struct IGemmKParams {
   // epilogue
   int mode, act, out_f32;
   const float* bias;
+  int bias_len;          // entries of `bias`
   const float* rowbias;
   long long rowbias_ld;
+  int rowbias_vec;       // row-bias rows are 16-byte aligned -> float4 loads
   const act_t* residual;
   long long res_ld;
   void* out;
@@ -64,6 +66,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   auto empty_bar = [&](int s) { return bar_base + 8u * uint32_t(p.stages + s); };
   const uint32_t accum_bar = bar_base + 8u * uint32_t(2 * p.stages);
   const uint32_t tmem_slot = accum_bar + 8u;
+  const uint32_t bias_smem = (tmem_slot + 4u + 15u) & ~15u;  // float[bn]: this tile's bias slice
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -151,6 +154,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const bool row_ok = (n < p.n_img) && (h < p.H) && (w < p.W);
     const long long row = (static_cast<long long>(n) * p.H + h) * p.W + w;
 
+    // stage this tile's bias slice in shared memory while the main loop runs; the epilogue reads it as broadcasts
+    const float* sbias = reinterpret_cast<const float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
+    {
+      float* sb = const_cast<float*>(sbias);
+      for (int i = threadIdx.x - 64; i < p.bn; i += 128) {
+        const int bc = nt * p.bn + i;
+        sb[i] = (p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+    }
+
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const uint32_t trow = tmem_acc + (uint32_t(q * 32) << 16);
@@ -172,11 +186,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
               uint32_t packed[4];
 #pragma unroll
               for (int e = 0; e < 8; e += 2) {
-                const int tc0 = nt * p.bn + c + j + e;  // column in the permuted weight/bias order
-                float x0 = __uint_as_float(xv[j + e]) + __ldg(p.bias + tc0);
-                float x1 = __uint_as_float(xv[j + e + 1]) + __ldg(p.bias + tc0 + 1);
-                float g0 = __uint_as_float(gv[j + e]) + __ldg(p.bias + tc0 + half);
-                float g1 = __uint_as_float(gv[j + e + 1]) + __ldg(p.bias + tc0 + half + 1);
+                const int tc0 = c + j + e;  // tile-relative column in the permuted weight/bias order
+                float x0 = __uint_as_float(xv[j + e]) + sbias[tc0];
+                float x1 = __uint_as_float(xv[j + e + 1]) + sbias[tc0 + 1];
+                float g0 = __uint_as_float(gv[j + e]) + sbias[tc0 + half];
+                float g1 = __uint_as_float(gv[j + e + 1]) + sbias[tc0 + half + 1];
                 packed[e >> 1] = pack_act2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
               }
               *reinterpret_cast<uint4*>(optr + j) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -200,14 +214,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
           const bool full8 = (col + 8 <= p.cout);
           if (full8) {
-            if (p.bias) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += __ldg(p.bias + col + e);
+            {
+              const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + j);
+              const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + j + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
             if (p.rowbias) {
               const float* rb = p.rowbias + static_cast<long long>(n) * p.rowbias_ld + col;
+              if (p.rowbias_vec) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += __ldg(rb + e);
+                for (int e = 0; e < 8; ++e) f[e] += __ldg(rb + e);
+              }
             }
             if (p.act) {
 #pragma unroll
@@ -253,7 +276,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             // ragged tail (cout not a multiple of 8, e.g. the 4- and 3-channel output convs): scalar path
             for (int e = 0; e < 8 && col + e < p.cout; ++e) {
               float x = f[e];
-              if (p.bias) x += __ldg(p.bias + col + e);
+              x += sbias[c + j + e];
               if (p.rowbias) x += __ldg(p.rowbias + static_cast<long long>(n) * p.rowbias_ld + col + e);
               x = apply_act(x, p.act);
               if (p.residual) x += from_act(p.residual[row * p.res_ld + col + e]);
@@ -344,6 +367,8 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.tmem_cols = (uint32_t)pow2_cols(d->bn);
   p.mode = d->mode; p.act = d->act; p.out_f32 = d->out_f32;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
+  p.bias_len = int(d->mode == CB_EPI_GEGLU ? 2 * d->cout : d->cout);
+  p.rowbias_vec = (d->rowbias != nullptr) && ((reinterpret_cast<uintptr_t>(d->rowbias) & 15u) == 0) && (d->rowbias_ld % 4 == 0);
   p.residual = reinterpret_cast<const act_t*>(d->residual); p.res_ld = d->res_ld;
   p.out = d->out; p.out_ld = d->out_ld;
   p.out_scale = d->out_scale == 0.f ? 1.f : d->out_scale;
@@ -361,7 +386,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   if (stages > num_k && num_k >= 1) stages = num_k < 2 ? 2 : num_k;
   CB_REQUIRE(stages >= 2 && stages <= 12, "cb_igemm: stages out of range");
   p.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 1) + 16;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 1) + 32 + sizeof(float) * 256;
   CB_REQUIRE(smem <= 227 * 1024, "cb_igemm: tile needs %zu bytes of shared memory", smem);
 
   static thread_local size_t configured_smem = 0;

@@ -72,15 +72,28 @@ def packw(w: torch.Tensor, device, splits=None) -> torch.Tensor:
 _WORKSPACES: Dict[Tuple, torch.Tensor] = {}
 
 
-def zero_workspace(tag: str, shape: Tuple[int, ...], device: torch.device) -> torch.Tensor:
+def zero_workspace(tag: str, shape: Tuple[int, ...], device: torch.device, init=None) -> torch.Tensor:
+    """Persistent zero-filled buffer; `init(buf)` runs once at creation (e.g. the attention row-sum column)."""
     key = (tag, tuple(shape), str(device))
     buf = _WORKSPACES.get(key)
     if buf is None:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("workspace allocation during CUDA-graph capture; run one eager call first")
         buf = torch.zeros(shape, dtype=ACT, device=device)
+        if init is not None:
+            init(buf)
         _WORKSPACES[key] = buf
     return buf
+
+
+def qkv_workspace(tag: str, which: int, v_index: int, bh: int, tokens: int, d: int, dpad: int,
+                  device: torch.device) -> torch.Tensor:
+    """[which][bh][tokens][dpad] per-head padded projection target. Pad columns stay zero except column d of the V
+    plane, which holds 1.0 when dpad > d: cb_attention's tensor core then accumulates the softmax row sum for free."""
+    def init(buf):
+        if dpad > d:
+            buf[v_index, :, :, d] = 1.0
+    return zero_workspace(f"{tag}_d{d}", (which, bh, tokens, dpad), device, init)
 
 
 def clear_workspaces():

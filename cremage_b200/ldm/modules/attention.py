@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...engine import ACT, PackedModule, f32, head_pad, packw, require_cuda, zero_workspace
+from ...engine import ACT, PackedModule, f32, head_pad, packw, qkv_workspace, require_cuda, zero_workspace
 
 GEGLU_BN = 128  # N tile of the fused GEGLU projection (x / gate rows interleaved per 64 output columns)
 
@@ -119,13 +119,13 @@ class CrossAttention(PackedModule):
             if "wqkv" not in p:
                 raise ValueError("self-attention requested on a CrossAttention built with a different context_dim")
             nk = nq
-            qkv = zero_workspace("qkv", (3, batch * h, nq, dpad), dev)
+            qkv = qkv_workspace("qkv", 3, 2, batch * h, nq, d, dpad, dev)
             ops.igemm(x2d, p["wqkv"], 3 * self.inner_dim, mode=ops.EPI_HEADS, out=qkv,
                       heads=(d, dpad, h, nq, batch * h * nq * dpad))
             q, k, v = qkv[0], qkv[1], qkv[2]
         else:
-            qb = zero_workspace("q", (1, batch * h, nq, dpad), dev)
-            kv = zero_workspace("kv", (2, batch * h, nk, dpad), dev)
+            qb = zero_workspace(f"q_d{d}", (1, batch * h, nq, dpad), dev)
+            kv = qkv_workspace("kv", 2, 1, batch * h, nk, d, dpad, dev)
             ops.igemm(x2d, p["wq"], self.inner_dim, mode=ops.EPI_HEADS, out=qb, heads=(d, dpad, h, nq, 0))
             ops.igemm(ctx2d, p["wkv"], 2 * self.inner_dim, mode=ops.EPI_HEADS, out=kv,
                       heads=(d, dpad, h, nk, batch * h * nk * dpad))

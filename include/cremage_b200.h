@@ -89,7 +89,8 @@ int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
 /* ---------------------------------------------------------------------------------------------------------------
  * fused flash-style attention on tcgen05 (QK^T -> online softmax -> PV), replaces
  *   CrossAttention / CrossAttentionOriginal / MemoryEfficientCrossAttention cores  ldm/modules/attention.py:418-423,646-657,811
- * q,k,v: bf16 [bh][tokens][dpad] (dpad multiple of 64, pad columns zero); out: bf16 [b][nq][heads*d]
+ * q,k,v: 16-bit [bh][tokens][dpad] (dpad multiple of 64, pad columns zero, EXCEPT when dpad > d: column d of v must
+ * hold 1.0 -- the tensor core then accumulates the softmax row sum in O[:, d]); out: 16-bit [b][nq][heads*d]
  * ------------------------------------------------------------------------------------------------------------- */
 int cb_attention(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads, int64_t nq,
                  int64_t nk, int d, int dpad, float scale, cudaStream_t stream);

@@ -7,11 +7,13 @@ from cremage_b200.ops import ACT  # fp16 (default) or bf16 build of the library
 pytestmark = pytest.mark.gpu
 
 
-def _mk(bh, n, d, dpad, seed):
+def _mk(bh, n, d, dpad, seed, ones_col=False):
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = torch.randn(bh, n, d, generator=g)
     xp = torch.zeros(bh, n, dpad)
     xp[..., :d] = x
+    if ones_col and dpad > d:
+        xp[..., d] = 1.0  # cb_attention contract: V's first pad column carries the row-sum ones
     return xp.to(ACT)
 
 
@@ -22,14 +24,17 @@ def _mk(bh, n, d, dpad, seed):
     (2, 8, 1024, 77, 40, 64),      # cross attention, ragged kv
     (2, 8, 256, 256, 80, 128),     # 32x32 level
     (2, 8, 100, 333, 160, 192),    # deepest level head dim, ragged q and kv, single-stage K/V
-    (1, 4, 300, 300, 64, 64),      # SDXL head dim
+    (1, 4, 300, 300, 64, 64),      # SDXL head dim (no pad column: explicit row sum)
+    (2, 8, 4096, 4096, 40, 64),    # two query tiles per CTA, 32 kv blocks, lazy rescale
+    (1, 2, 129, 130, 40, 64),      # second query tile nearly empty
+    (1, 2, 640, 640, 128, 128),    # dpad 128: two warpgroups, single-stage K/V, explicit row sum
 ])
 def test_attention_matches_torch(batch, heads, nq, nk, d, dpad):
     from cremage_b200 import ops
     bh = batch * heads
     q = _mk(bh, nq, d, dpad, 1)
     k = _mk(bh, nk, d, dpad, 2)
-    v = _mk(bh, nk, d, dpad, 3)
+    v = _mk(bh, nk, d, dpad, 3, ones_col=True)
     scale = d ** -0.5
     out = ops.attention(q.cuda(), k.cuda(), v.cuda(), batch, heads, nq, nk, d, dpad, scale)
     torch.cuda.synchronize()
@@ -46,7 +51,7 @@ def test_attention_peaked_scores_rescale_path():
     batch, heads, n, d, dpad = 1, 2, 512, 40, 64
     q = _mk(heads, n, d, dpad, 4) * 4
     k = _mk(heads, n, d, dpad, 5) * 4
-    v = _mk(heads, n, d, dpad, 6)
+    v = _mk(heads, n, d, dpad, 6, ones_col=True)
     scale = d ** -0.5
     out = ops.attention(q.cuda(), k.cuda(), v.cuda(), batch, heads, n, n, d, dpad, scale)
     torch.cuda.synchronize()

@@ -54,6 +54,10 @@ def bench_attn(B, iters, warm):
                                    ("cross 16x16 d160", 8, 256, 77, 160)]:
         dpad = (d + 63) // 64 * 64
         q, k, v = act(B * heads, nq, dpad), act(B * heads, nk, dpad), act(B * heads, nk, dpad)
+        for t in (q, k, v):
+            t[..., d:] = 0
+        if dpad > d:
+            v[..., d] = 1.0
         ms = timeit(lambda: ops.attention(q, k, v, B, heads, nq, nk, d, dpad, d ** -0.5), iters, warm)
         fl = 4.0 * B * heads * nq * nk * d
         print(f"{name:22s} bh={B * heads:4d} nq={nq:5d} nk={nk:5d} d={d:3d}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  "
