@@ -70,8 +70,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   auto v_empty = [&](int s) { return bars + 56u + 8u * uint32_t(s); };
   auto s_full = [&](int w) { return bars + 72u + 8u * uint32_t(w); };
   auto p_full = [&](int w) { return bars + 88u + 8u * uint32_t(w); };
-  auto o_done = [&](int w) { return bars + 104u + 8u * uint32_t(w); };
-  const uint32_t tmem_slot = bars + 120u;
+  const uint32_t tmem_slot = bars + 104u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -88,7 +87,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
       mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
-      mbar_init(s_full(s), 1); mbar_init(p_full(s), ATT_BM); mbar_init(o_done(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), ATT_BM);
     }
     fence_mbar_init();
   }
@@ -160,17 +159,16 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         const uint32_t ph1 = uint32_t(((j + 1) / p.stages) & 1);
         for (int w = 0; w < nact; ++w) {
           mbar_wait(p_full(w), uint32_t(j & 1));   // softmax w: S consumed, P written, O rescaled
+          if (w == 0) mbar_wait(v_full(st), ph);
           tc_fence_after();
-          if (more) {                               // next scores first: the softmax warps wait on these
+          issue_pv(w, st, j > 0);
+          if (w == nact - 1) umma_commit(v_empty(st));
+          if (more) {
             if (w == 0) { mbar_wait(k_full(st1), ph1); tc_fence_after(); }
             issue_qk(w, st1);
-            umma_commit(s_full(w));                 // S_w(j+1) ready
-            if (w == nact - 1) umma_commit(k_empty(st1));
           }
-          if (w == 0) { mbar_wait(v_full(st), ph); tc_fence_after(); }
-          issue_pv(w, st, j > 0);
-          umma_commit(o_done(w));                   // O_w(j) accumulated, P_w free again
-          if (w == nact - 1) umma_commit(v_empty(st));
+          umma_commit(s_full(w));                   // S_w(j+1) ready / final O_w ready
+          if (more && w == nact - 1) umma_commit(k_empty(st1));
         }
       }
     }
@@ -213,8 +211,6 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         if (j == 0) {
           m_used = m_blk;
         } else {
-          mbar_wait(o_done(w), uint32_t((j - 1) & 1));   // P*V of the previous block retired: O stable, P buffer free
-          tc_fence_after();
           const bool need = (m_blk - m_used) > RESCALE_TAU;
           if (__any_sync(0xffffffffu, need)) {
             const float alpha = need ? exp2f(m_used - m_blk) : 1.f;
@@ -261,7 +257,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       }
 
       // ---- epilogue: O / l -> out[b][q][head*d + :]
-      mbar_wait(o_done(w), uint32_t((nblk - 1) & 1));
+      mbar_wait(s_full(w), uint32_t(nblk & 1));
       tc_fence_after();
       const int q = q_first + w * ATT_BM + r;
       const int b = bh / p.heads, head = bh - b * p.heads;
