@@ -229,8 +229,9 @@ __host__ __device__ constexpr uint64_t make_sdesc_sw128(uint32_t smem_addr, uint
 #ifdef CB_FP16
 CB_DEVINL float sat_f16(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }  // finite saturation, NaN passes
 CB_DEVINL uint32_t pack_act2(float lo, float hi) {
-  act_t2 v = __floats2half2_rn(sat_f16(lo), sat_f16(hi));
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;  // one F2FP.SATFINITE: converts, saturates to +-65504 and packs (first source -> upper half)
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 CB_DEVINL float2 unpack_act2(uint32_t u) {
   act_t2 v = *reinterpret_cast<act_t2*>(&u);

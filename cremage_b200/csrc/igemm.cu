@@ -3,15 +3,18 @@
 //
 //   D[row, co] = sum_{tap, c} A_src(c)[pixel(row) + shift(tap), c] * Wt[co, tap, c]      (fp32 accumulate in TMEM)
 //
-// * A is read straight from the NHWC bf16 activation tensor(s) with 4-D TMA boxes {64 ch, TW, TH, TN}
+// * A is read straight from the NHWC 16-bit activation tensor(s) with 4-D TMA boxes {64 ch, TW, TH, TN}
 //   (TW*TH*TN = 128 output pixels); a 3x3 tap is just a shifted box and the conv zero padding is TMA's
 //   out-of-bounds zero fill.  No im2col buffer exists.  Two A sources give the UNet skip-concat for free
 //   (reference: torch.cat([h, hs.pop()], 1) at ldm/modules/diffusionmodules/openaimodel.py:808).
-// * B (weights, repacked [Cout][tap][Cin] bf16, K-major) is read with 2-D TMA boxes {64, BN}.
-// * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) issued by one thread, accumulator in TMEM.
-// * Warp roles: warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue
-//   (tcgen05.ld -> bias / per-image bias / residual / SiLU / GEGLU / per-head scatter -> global).
-// * Non-persistent grid, 2 CTAs per SM co-resident so one CTA's epilogue overlaps the other's main loop.
+// * B (weights, repacked [Cout][tap][Cin] 16-bit, K-major) is read with 2-D TMA boxes {64, BN}: either streamed
+//   through the same smem ring as A, or -- when the whole K extent of one N tile fits (small-K linears / 1x1 convs) --
+//   loaded ONCE per CTA and kept resident while the CTA walks the M tiles of that N tile (B-stationary), which
+//   removes the weight re-reads that otherwise make K <= 640 shapes L2-bandwidth bound.
+// * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) issued by one thread; TWO fp32 accumulators in TMEM.
+// * Persistent: one CTA per SM loops over tiles.  Warp roles: warp0 = TMA producer (runs ahead across tile
+//   boundaries), warp1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue (tcgen05.ld -> bias / per-image bias /
+//   SiLU / residual / GEGLU / per-head scatter -> global) draining accumulator i while the MMAs fill i+1.
 #include "common.cuh"
 #include "cremage_b200.h"
 
@@ -21,18 +24,22 @@ constexpr int BM = 128;          // rows per tile (UMMA M)
 constexpr int BK = 64;           // K elements per pipeline stage (= one 128-byte swizzle row)
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int NUM_THREADS = 192;
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct IGemmKParams {
   // rows
   int n_img, H, W;       // output pixel grid
   int TW, TH, TN;        // tile decomposition, TW*TH*TN == 128
-  int tiles_w, tiles_h;  // tiles along w / h (tiles along n = gridDim.y / (tiles_w*tiles_h))
+  int tiles_w, tiles_h;  // tiles along w / h
+  int m_tiles, n_tiles;  // tile grid
+  int resident_b;        // 1: B of this CTA's N tile stays in smem, CTA walks M tiles of that N tile
+  int m_step;            // resident mode: stride between the M tiles of one CTA ( = gridDim.x / n_tiles )
   // K loop
   int taps, chunks0, chunks1, num_k;
   int tap_dw[9], tap_dh[9], tap_dn[9];
   // N
   int cout, bn, stages;
-  uint32_t idesc, tmem_cols;
+  uint32_t idesc, tmem_cols, acc_stride;
   // epilogue
   int mode, act, out_f32;
   const float* bias;
@@ -52,34 +59,205 @@ struct IGemmKParams {
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == CB_ACT_SILU ? silu_f(v) : v; }
 
+// tile scheduler shared by the three roles: local tile i of this CTA -> (mt, nt), false when exhausted
+struct TileSched {
+  const IGemmKParams& p;
+  __device__ explicit TileSched(const IGemmKParams& pp) : p(pp) {}
+  __device__ __forceinline__ bool get(int i, int& mt, int& nt) const {
+    if (p.resident_b) {
+      nt = int(blockIdx.x) % p.n_tiles;
+      mt = int(blockIdx.x) / p.n_tiles + i * p.m_step;
+      return mt < p.m_tiles;
+    }
+    const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
+    if (t >= (long long)p.m_tiles * p.n_tiles) return false;
+    nt = int(t % p.n_tiles);
+    mt = int(t / p.n_tiles);
+    return true;
+  }
+};
+
+// Epilogue specialisations (compile-time, so the inner loops carry no mode / flag branches):
+enum : int {
+  EPI_GENERIC = 0,   // every runtime flag honoured (fp32 out, ragged cout, activation, scale) -- small / rare launches
+  EPI_PLAIN = 1,     // + bias                          -> 16-bit
+  EPI_RES = 2,       // + bias + residual               -> 16-bit
+  EPI_ROWBIAS = 3,   // + bias + per-image bias         -> 16-bit   (ResBlock conv1 with the timestep projection)
+  EPI_GEGLU = 4,     // x * gelu(gate)                  -> 16-bit
+  EPI_HEADS = 5,     // + bias, per-head padded scatter -> 16-bit
+  EPI_COUNT = 6
+};
+
+// 32 accumulator columns [c, c+32) of one row -> global
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const IGemmKParams& p, const uint32_t (&v)[32], const float* __restrict__ sbias,
+                                               int nt, int c, int n, long long row) {
+  const int col0 = nt * p.bn + c;
+  if (col0 >= p.cout) return;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const int col = col0 + j;
+    if (col >= p.cout) break;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
+    if (EPI != EPI_GENERIC || col + 8 <= p.cout) {
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + j);
+        const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + j + 4);
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      }
+      if (EPI == EPI_ROWBIAS || (EPI == EPI_GENERIC && p.rowbias)) {
+        const float* rb = p.rowbias + static_cast<long long>(n) * p.rowbias_ld + col;
+        if (p.rowbias_vec) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += __ldg(rb + e);
+        }
+      }
+      if (EPI == EPI_GENERIC && p.act) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = apply_act(f[e], p.act);
+      }
+      if (EPI == EPI_RES || (EPI == EPI_GENERIC && p.residual)) {
+        const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + row * p.res_ld + col);
+        const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 t = unpack_act2(ru[e]);
+          f[2 * e] += t.x;
+          f[2 * e + 1] += t.y;
+        }
+      }
+      if (EPI == EPI_GENERIC && p.out_scale != 1.f) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] *= p.out_scale;
+      }
+      if (EPI == EPI_HEADS) {
+        // column -> (which, head, j); row -> (batch, token); 8-column groups never straddle a head (d % 8 == 0)
+        const int inner = p.hheads * p.hd;
+        const int which = col / inner;
+        const int cc = col - which * inner;
+        const int head = cc / p.hd;
+        const int jj = cc - head * p.hd;
+        const long long b = row / p.htokens;
+        const long long tok = row - b * p.htokens;
+        act_t* optr = reinterpret_cast<act_t*>(p.out) + which * p.hwhich_stride +
+                      ((b * p.hheads + head) * p.htokens + tok) * p.hdpad + jj;
+        *reinterpret_cast<uint4*>(optr) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
+                                                     pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+      } else if (EPI == EPI_GENERIC && p.out_f32) {
+        float* optr = reinterpret_cast<float*>(p.out) + row * p.out_ld + col;
+        *reinterpret_cast<float4*>(optr) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(optr + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      } else {
+        act_t* optr = reinterpret_cast<act_t*>(p.out) + row * p.out_ld + col;
+        *reinterpret_cast<uint4*>(optr) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
+                                                     pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+      }
+    } else {
+      // EPI_GENERIC ragged tail (cout not a multiple of 8, e.g. the 4- and 3-channel output convs): scalar path
+      for (int e = 0; e < 8 && col + e < p.cout; ++e) {
+        float x = f[e];
+        x += sbias[c + j + e];
+        if (p.rowbias) x += __ldg(p.rowbias + static_cast<long long>(n) * p.rowbias_ld + col + e);
+        x = apply_act(x, p.act);
+        if (p.residual) x += from_act(p.residual[row * p.res_ld + col + e]);
+        x *= p.out_scale;
+        if (p.out_f32) reinterpret_cast<float*>(p.out)[row * p.out_ld + col + e] = x;
+        else reinterpret_cast<act_t*>(p.out)[row * p.out_ld + col + e] = to_act(x);
+      }
+    }
+  }
+}
+
+// epilogue of one 128 x bn accumulator tile (thread = one row); `trow` = TMEM address of this thread's lane, column 0
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const IGemmKParams& p, uint32_t trow, const float* __restrict__ sbias,
+                                              int nt, int n, bool row_ok, long long row) {
+  if (EPI == EPI_GEGLU) {
+    // tile columns [0, bn/2) hold x, [bn/2, bn) hold the gate (weights were interleaved per tile on the host)
+    const int half = p.bn >> 1;
+    for (int c = 0; c < half; c += 32) {
+      uint32_t xv[32], gv[32];
+      tmem_ld32(trow + uint32_t(c), xv);
+      tmem_ld32(trow + uint32_t(half + c), gv);
+      tmem_ld_wait();
+      if (row_ok) {
+        const int ocol0 = nt * half + c;  // output column
+        act_t* optr = reinterpret_cast<act_t*>(p.out) + row * p.out_ld + ocol0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (ocol0 + j < p.cout) {  // cout here = number of OUTPUT columns (inner dim), multiple of 8
+            uint32_t packed[4];
+            const float4 bx0 = *reinterpret_cast<const float4*>(sbias + c + j);
+            const float4 bx1 = *reinterpret_cast<const float4*>(sbias + c + j + 4);
+            const float4 bg0 = *reinterpret_cast<const float4*>(sbias + half + c + j);
+            const float4 bg1 = *reinterpret_cast<const float4*>(sbias + half + c + j + 4);
+            const float bx[8] = {bx0.x, bx0.y, bx0.z, bx0.w, bx1.x, bx1.y, bx1.z, bx1.w};
+            const float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) {
+              const float x0 = __uint_as_float(xv[j + e]) + bx[e];
+              const float x1 = __uint_as_float(xv[j + e + 1]) + bx[e + 1];
+              const float g0 = __uint_as_float(gv[j + e]) + bg[e];
+              const float g1 = __uint_as_float(gv[j + e + 1]) + bg[e + 1];
+              packed[e >> 1] = pack_act2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
+            }
+            *reinterpret_cast<uint4*>(optr + j) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+        }
+      }
+    }
+    return;
+  }
+  // two register buffers: the TMEM load of chunk c+32 is in flight while chunk c is converted and stored
+  uint32_t va[32], vb[32];
+  tmem_ld32(trow, va);
+  for (int c = 0; c < p.bn; c += 64) {
+    tmem_ld_wait();
+    const bool more_b = (c + 32 < p.bn);
+    if (more_b) tmem_ld32(trow + uint32_t(c + 32), vb);
+    if (row_ok) epilogue_chunk<EPI>(p, va, sbias, nt, c, n, row);
+    if (more_b) {
+      tmem_ld_wait();
+      if (c + 64 < p.bn) tmem_ld32(trow + uint32_t(c + 64), va);
+      if (row_ok) epilogue_chunk<EPI>(p, vb, sbias, nt, c + 32, n, row);
+    }
+  }
+}
+
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
              const __grid_constant__ CUtensorMap mapB, const IGemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A 16K][B bn*128] (1024-aligned), then barriers
+  // carve (1024-aligned): [resident B: num_k x bn*128] [ring: stages x (A 16K [+ B bn*128])] [barriers] [bias x2]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_stage_bytes = uint32_t(p.bn) * 128u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  const uint32_t bar_base = smem_base + uint32_t(p.stages) * stage_bytes;
-  // barriers: full[s] at bar_base + 8*s ; empty[s] at bar_base + 8*(stages+s); accum at 8*(2*stages); tmem ptr after
+  const uint32_t b_chunk_bytes = uint32_t(p.bn) * 128u;
+  const uint32_t res_bytes = p.resident_b ? uint32_t(p.num_k) * b_chunk_bytes : 0u;
+  const uint32_t stage_bytes = A_STAGE_BYTES + (p.resident_b ? 0u : b_chunk_bytes);
+  const uint32_t ring_base = smem_base + res_bytes;
+  const uint32_t bar_base = ring_base + uint32_t(p.stages) * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * uint32_t(s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * uint32_t(p.stages + s); };
-  const uint32_t accum_bar = bar_base + 8u * uint32_t(2 * p.stages);
-  const uint32_t tmem_slot = accum_bar + 8u;
-  const uint32_t bias_smem = (tmem_slot + 4u + 15u) & ~15u;  // float[bn]: this tile's bias slice
+  const uint32_t misc = bar_base + 16u * uint32_t(p.stages);
+  auto acc_full = [&](int b) { return misc + 8u * uint32_t(b); };
+  auto acc_empty = [&](int b) { return misc + 16u + 8u * uint32_t(b); };
+  const uint32_t bres_bar = misc + 32u;
+  const uint32_t tmem_slot = misc + 40u;
+  const uint32_t bias_smem = (misc + 48u + 15u) & ~15u;  // float[2][256]: the tile's bias slice, double buffered
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int nt = blockIdx.x;  // N tile
-  const int mt = blockIdx.y;  // M tile
-  const int tw = mt % p.tiles_w;
-  const int th = (mt / p.tiles_w) % p.tiles_h;
-  const int tn = mt / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+  const TileSched sched(p);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -89,7 +267,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 128);
+    }
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -99,26 +281,40 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot_ptr;
+  const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (p.resident_b) {
+        int mt, nt;
+        if (sched.get(0, mt, nt)) {
+          mbar_expect_tx(bres_bar, res_bytes);
+          for (int kt = 0; kt < p.num_k; ++kt)
+            tma_load_2d(smem_base + uint32_t(kt) * b_chunk_bytes, &mapB, bres_bar, kt * BK, nt * p.bn);
+        }
+      }
       const int cpt = p.chunks0 + p.chunks1;
       int stage = 0;
       uint32_t phase = 0;
-      int tap = 0, ch = 0;
-      for (int kt = 0; kt < p.num_k; ++kt) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = smem_base + uint32_t(stage) * stage_bytes;
-        const uint32_t sb = sa + A_STAGE_BYTES;
-        mbar_expect_tx(full_bar(stage), stage_bytes);
-        const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], cn = n0 + p.tap_dn[tap];
-        if (ch < p.chunks0) tma_load_4d(sa, &mapA0, full_bar(stage), ch * BK, cw, chh, cn);
-        else                tma_load_4d(sa, &mapA1, full_bar(stage), (ch - p.chunks0) * BK, cw, chh, cn);
-        tma_load_2d(sb, &mapB, full_bar(stage), kt * BK, nt * p.bn);
-        if (++ch == cpt) { ch = 0; ++tap; }
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      int mt, nt;
+      for (int i = 0; sched.get(i, mt, nt); ++i) {
+        const int tw = mt % p.tiles_w;
+        const int th = (mt / p.tiles_w) % p.tiles_h;
+        const int tn = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+        int tap = 0, ch = 0;
+        for (int kt = 0; kt < p.num_k; ++kt) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = ring_base + uint32_t(stage) * stage_bytes;
+          mbar_expect_tx(full_bar(stage), stage_bytes);
+          const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], cn = n0 + p.tap_dn[tap];
+          if (ch < p.chunks0) tma_load_4d(sa, &mapA0, full_bar(stage), ch * BK, cw, chh, cn);
+          else                tma_load_4d(sa, &mapA1, full_bar(stage), (ch - p.chunks0) * BK, cw, chh, cn);
+          if (!p.resident_b) tma_load_2d(sa + A_STAGE_BYTES, &mapB, full_bar(stage), kt * BK, nt * p.bn);
+          if (++ch == cpt) { ch = 0; ++tap; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -126,22 +322,32 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kt = 0; kt < p.num_k; ++kt) {
-        mbar_wait(full_bar(stage), phase);
+      int mt, nt;
+      bool b_ready = !p.resident_b;
+      for (int i = 0; sched.get(i, mt, nt); ++i) {
+        const int buf = i & 1;
+        const uint32_t use = uint32_t(i >> 1);
+        mbar_wait(acc_empty(buf), (use & 1u) ^ 1u);   // epilogue drained this accumulator (first two uses pass)
         tc_fence_after();
-        const uint32_t sa = smem_base + uint32_t(stage) * stage_bytes;
-        const uint32_t sb = sa + A_STAGE_BYTES;
-        const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
-        const uint64_t bdesc = make_sdesc_sw128(sb, 16, 1024);
+        if (!b_ready) { mbar_wait(bres_bar, 0); b_ready = true; }
+        const uint32_t tacc = tmem_base + uint32_t(buf) * p.acc_stride;
+        for (int kt = 0; kt < p.num_k; ++kt) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = ring_base + uint32_t(stage) * stage_bytes;
+          const uint32_t sb = p.resident_b ? (smem_base + uint32_t(kt) * b_chunk_bytes) : (sa + A_STAGE_BYTES);
+          const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = make_sdesc_sw128(sb, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
-          umma_bf16(tmem_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), p.idesc, (kt | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
+            umma_bf16(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), p.idesc, (kt | k) != 0);
+          }
+          umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above have read it
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        umma_commit(acc_full(buf));  // accumulator complete
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -150,143 +356,32 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const int rn = r / (p.TW * p.TH);
     const int rh = (r / p.TW) % p.TH;
     const int rw = r % p.TW;
-    const int n = n0 + rn, h = h0 + rh, w = w0 + rw;
-    const bool row_ok = (n < p.n_img) && (h < p.H) && (w < p.W);
-    const long long row = (static_cast<long long>(n) * p.H + h) * p.W + w;
-
-    // stage this tile's bias slice in shared memory while the main loop runs; the epilogue reads it as broadcasts
-    const float* sbias = reinterpret_cast<const float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
-    {
-      float* sb = const_cast<float*>(sbias);
-      for (int i = threadIdx.x - 64; i < p.bn; i += 128) {
-        const int bc = nt * p.bn + i;
-        sb[i] = (p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
+    float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
+    int mt, nt;
+    for (int i = 0; sched.get(i, mt, nt); ++i) {
+      const int buf = i & 1;
+      const uint32_t use = uint32_t(i >> 1);
+      const int tw = mt % p.tiles_w;
+      const int th = (mt / p.tiles_w) % p.tiles_h;
+      const int tn = mt / (p.tiles_w * p.tiles_h);
+      const int n = tn * p.TN + rn, h = th * p.TH + rh, w = tw * p.TW + rw;
+      const bool row_ok = (n < p.n_img) && (h < p.H) && (w < p.W);
+      const long long row = (static_cast<long long>(n) * p.H + h) * p.W + w;
+      // stage this tile's bias slice (overlaps the MMAs of this tile); the named barrier also orders the reuse of
+      // the slot against the slowest warp's reads two tiles ago
+      float* sb = sbias_all + buf * 256;
+      for (int c = threadIdx.x - 64; c < p.bn; c += 128) {
+        const int bc = nt * p.bn + c;
+        sb[c] = (p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-    }
 
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_acc + (uint32_t(q * 32) << 16);
-
-    if (p.mode == CB_EPI_GEGLU) {
-      // tile columns [0, bn/2) hold x, [bn/2, bn) hold the gate (weights were interleaved per tile on the host)
-      const int half = p.bn >> 1;
-      for (int c = 0; c < half; c += 32) {
-        uint32_t xv[32], gv[32];
-        tmem_ld32(trow + uint32_t(c), xv);
-        tmem_ld32(trow + uint32_t(half + c), gv);
-        tmem_ld_wait();
-        if (row_ok) {
-          const int ocol0 = nt * half + c;  // output column
-          act_t* optr = reinterpret_cast<act_t*>(p.out) + row * p.out_ld + ocol0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (ocol0 + j < p.cout) {  // cout here = number of OUTPUT columns (inner dim), multiple of 8
-              uint32_t packed[4];
-#pragma unroll
-              for (int e = 0; e < 8; e += 2) {
-                const int tc0 = c + j + e;  // tile-relative column in the permuted weight/bias order
-                float x0 = __uint_as_float(xv[j + e]) + sbias[tc0];
-                float x1 = __uint_as_float(xv[j + e + 1]) + sbias[tc0 + 1];
-                float g0 = __uint_as_float(gv[j + e]) + sbias[tc0 + half];
-                float g1 = __uint_as_float(gv[j + e + 1]) + sbias[tc0 + half + 1];
-                packed[e >> 1] = pack_act2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
-              }
-              *reinterpret_cast<uint4*>(optr + j) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
-          }
-        }
-      }
-    } else {
-      for (int c = 0; c < p.bn; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(trow + uint32_t(c), v);
-        tmem_ld_wait();
-        const int col0 = nt * p.bn + c;
-        if (!row_ok || col0 >= p.cout) continue;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const int col = col0 + j;
-          if (col >= p.cout) break;
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
-          const bool full8 = (col + 8 <= p.cout);
-          if (full8) {
-            {
-              const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + j);
-              const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + j + 4);
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            }
-            if (p.rowbias) {
-              const float* rb = p.rowbias + static_cast<long long>(n) * p.rowbias_ld + col;
-              if (p.rowbias_vec) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += __ldg(rb + e);
-              }
-            }
-            if (p.act) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = apply_act(f[e], p.act);
-            }
-            if (p.residual) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + row * p.res_ld + col);
-              const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 t = unpack_act2(ru[e]);
-                f[2 * e] += t.x;
-                f[2 * e + 1] += t.y;
-              }
-            }
-            if (p.out_scale != 1.f) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] *= p.out_scale;
-            }
-            if (p.mode == CB_EPI_HEADS) {
-              // column -> (which, head, j); row -> (batch, token); 8-column groups never straddle a head (d % 8 == 0)
-              const int inner = p.hheads * p.hd;
-              const int which = col / inner;
-              const int cc = col - which * inner;
-              const int head = cc / p.hd;
-              const int jj = cc - head * p.hd;
-              const long long b = row / p.htokens;
-              const long long tok = row - b * p.htokens;
-              act_t* optr = reinterpret_cast<act_t*>(p.out) + which * p.hwhich_stride +
-                                    ((b * p.hheads + head) * p.htokens + tok) * p.hdpad + jj;
-              *reinterpret_cast<uint4*>(optr) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
-                                                           pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
-            } else if (p.out_f32) {
-              float* optr = reinterpret_cast<float*>(p.out) + row * p.out_ld + col;
-              *reinterpret_cast<float4*>(optr) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(optr + 4) = make_float4(f[4], f[5], f[6], f[7]);
-            } else {
-              act_t* optr = reinterpret_cast<act_t*>(p.out) + row * p.out_ld + col;
-              *reinterpret_cast<uint4*>(optr) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
-                                                           pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
-            }
-          } else {
-            // ragged tail (cout not a multiple of 8, e.g. the 4- and 3-channel output convs): scalar path
-            for (int e = 0; e < 8 && col + e < p.cout; ++e) {
-              float x = f[e];
-              x += sbias[c + j + e];
-              if (p.rowbias) x += __ldg(p.rowbias + static_cast<long long>(n) * p.rowbias_ld + col + e);
-              x = apply_act(x, p.act);
-              if (p.residual) x += from_act(p.residual[row * p.res_ld + col + e]);
-              x *= p.out_scale;
-              if (p.out_f32) reinterpret_cast<float*>(p.out)[row * p.out_ld + col + e] = x;
-              else reinterpret_cast<act_t*>(p.out)[row * p.out_ld + col + e] = to_act(x);
-            }
-          }
-        }
-      }
+      mbar_wait(acc_full(buf), use & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + uint32_t(buf) * p.acc_stride + (uint32_t(q * 32) << 16);
+      epilogue_tile<EPI>(p, trow, sb, nt, n, row_ok, row);
+      tc_fence_before();
+      mbar_arrive(acc_empty(buf));   // 128 arrivals: every epilogue thread has drained its TMEM lanes
     }
   }
 
@@ -294,7 +389,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, p.tmem_cols);
+    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -303,6 +398,8 @@ static int pow2_cols(int bn) {
   while (c < bn) c <<= 1;
   return c;
 }
+
+static int g_num_sms = 0;
 
 }  // namespace cb
 
@@ -318,7 +415,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   CB_REQUIRE(d->bn >= 32 && d->bn <= 256 && d->bn % 32 == 0, "cb_igemm: bn must be a multiple of 32 in [32,256] (got %d)", d->bn);
   CB_REQUIRE(d->tw > 0 && d->th > 0 && d->tn > 0 && d->tw * d->th * d->tn == BM, "cb_igemm: tile %dx%dx%d is not 128 rows", d->tw, d->th, d->tn);
   CB_REQUIRE(d->tw <= 256 && d->th <= 256 && d->tn <= 256, "cb_igemm: tile extent > 256");
-  if (d->mode == CB_EPI_GEGLU) CB_REQUIRE(d->bn % 64 == 0 && d->bias && !d->out_f32, "cb_igemm: GEGLU needs bn %% 64 == 0, a bias and bf16 output");
+  if (d->mode == CB_EPI_GEGLU) CB_REQUIRE(d->bn % 64 == 0 && d->bias && !d->out_f32, "cb_igemm: GEGLU needs bn %% 64 == 0, a bias and 16-bit output");
   if (d->mode == CB_EPI_HEADS) CB_REQUIRE(d->heads_d % 8 == 0 && d->heads_dpad >= d->heads_d && d->heads_h > 0 && d->heads_tokens > 0 && !d->out_f32, "cb_igemm: bad heads epilogue arguments");
 
   const int chunks0 = int((d->c0 + BK - 1) / BK);
@@ -354,17 +451,27 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     if (rc) return rc;
   }
 
+  if (g_num_sms == 0) {
+    int dev = 0, sms = 0;
+    CB_CHECK_CUDA(cudaGetDevice(&dev));
+    CB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    g_num_sms = sms > 0 ? sms : 148;
+  }
+
   IGemmKParams p{};
   p.n_img = (int)d->n; p.H = (int)d->h; p.W = (int)d->w;
   p.TW = d->tw; p.TH = d->th; p.TN = d->tn;
   p.tiles_w = int((d->w + d->tw - 1) / d->tw);
   p.tiles_h = int((d->h + d->th - 1) / d->th);
   const int tiles_n = int((d->n + d->tn - 1) / d->tn);
+  p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  p.n_tiles = int((d->mode == CB_EPI_GEGLU ? 2 * d->cout : d->cout) + d->bn - 1) / d->bn;
   p.taps = d->taps; p.chunks0 = chunks0; p.chunks1 = chunks1; p.num_k = num_k;
   for (int i = 0; i < 9; ++i) { p.tap_dw[i] = d->tap_dw[i]; p.tap_dh[i] = d->tap_dh[i]; p.tap_dn[i] = d->tap_dn[i]; }
   p.cout = (int)d->cout; p.bn = d->bn;
   p.idesc = make_idesc_f16(BM, d->bn, 0, 0);
-  p.tmem_cols = (uint32_t)pow2_cols(d->bn);
+  p.acc_stride = (uint32_t)pow2_cols(d->bn);
+  p.tmem_cols = 2u * p.acc_stride;   // two accumulators: <= 512 columns
   p.mode = d->mode; p.act = d->act; p.out_f32 = d->out_f32;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.bias_len = int(d->mode == CB_EPI_GEGLU ? 2 * d->cout : d->cout);
@@ -375,28 +482,60 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.hd = d->heads_d; p.hdpad = d->heads_dpad; p.hheads = d->heads_h; p.htokens = d->heads_tokens;
   p.hwhich_stride = d->heads_which_stride;
 
-  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)d->bn * 128u;
+  // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
+  //      that N tile gets several M tiles; otherwise stream A and B through the ring
+  const size_t fixed = 1024 + 16 * 12 + 64 + sizeof(float) * 512 + 64;
+  const size_t b_chunk = (size_t)d->bn * 128;
+  const size_t res_bytes = (size_t)num_k * b_chunk;
+  int resident = 0;
+  unsigned grid = 0;
+  if (d->stages <= 0 && p.n_tiles <= g_num_sms && res_bytes + 4 * (size_t)A_STAGE_BYTES + fixed <= (size_t)SMEM_LIMIT) {
+    const int ctas_per_nt = g_num_sms / p.n_tiles;
+    if (ctas_per_nt >= 1 && p.m_tiles >= 3 * ctas_per_nt) {
+      resident = 1;
+      grid = (unsigned)(ctas_per_nt * p.n_tiles);
+      p.m_step = ctas_per_nt;
+    }
+  }
+  p.resident_b = resident;
+  const size_t stage_bytes = A_STAGE_BYTES + (resident ? 0 : b_chunk);
   int stages = d->stages;
   if (stages <= 0) {
-    // aim for two co-resident CTAs per SM (<= ~110 KiB each) with at least 2 and at most 6 stages
-    stages = int((110u * 1024u) / stage_bytes);
-    if (stages < 2) stages = 2;
-    if (stages > 6) stages = 6;
+    stages = int(((size_t)SMEM_LIMIT - fixed - (resident ? res_bytes : 0)) / stage_bytes);
+    if (stages > 8) stages = 8;
   }
-  if (stages > num_k && num_k >= 1) stages = num_k < 2 ? 2 : num_k;
-  CB_REQUIRE(stages >= 2 && stages <= 12, "cb_igemm: stages out of range");
+  CB_REQUIRE(stages >= 2 && stages <= 12, "cb_igemm: %d pipeline stages do not fit / out of range", stages);
   p.stages = stages;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * stages + 1) + 32 + sizeof(float) * 256;
-  CB_REQUIRE(smem <= 227 * 1024, "cb_igemm: tile needs %zu bytes of shared memory", smem);
-
-  static thread_local size_t configured_smem = 0;
-  if (smem > configured_smem) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured_smem = 227 * 1024;
+  const size_t smem = 1024 + (resident ? res_bytes : 0) + (size_t)stages * stage_bytes + 16 * (size_t)stages + 64 +
+                      sizeof(float) * 512 + 64;
+  CB_REQUIRE(smem <= (size_t)SMEM_LIMIT, "cb_igemm: tile needs %zu bytes of shared memory", smem);
+  if (!resident) {
+    const long long total = (long long)p.m_tiles * p.n_tiles;
+    grid = (unsigned)(total < g_num_sms ? total : g_num_sms);
   }
-  const int n_tiles = int((d->mode == CB_EPI_GEGLU ? 2 * d->cout : d->cout) + d->bn - 1) / d->bn;
-  dim3 grid((unsigned)n_tiles, (unsigned)(p.tiles_w * p.tiles_h * tiles_n), 1);
-  igemm_kernel<<<grid, NUM_THREADS, smem, stream>>>(mapA0, mapA1, mapB, p);
+
+  // epilogue specialisation
+  int epi = EPI_GENERIC;
+  const bool simple16 = !d->out_f32 && d->act == CB_ACT_NONE && p.out_scale == 1.f && d->cout % 8 == 0;
+  if (d->mode == CB_EPI_GEGLU) epi = EPI_GEGLU;
+  else if (d->mode == CB_EPI_HEADS && simple16 && !d->rowbias && !d->residual) epi = EPI_HEADS;
+  else if (d->mode == CB_EPI_LINEAR && simple16) {
+    if (!d->rowbias && !d->residual) epi = EPI_PLAIN;
+    else if (!d->rowbias && d->residual) epi = EPI_RES;
+    else if (d->rowbias && !d->residual) epi = EPI_ROWBIAS;
+  }
+  CB_REQUIRE(d->mode != CB_EPI_HEADS || epi == EPI_HEADS, "cb_igemm: the heads epilogue takes bias only (no activation / residual / row bias / scale)");
+
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IGemmKParams);
+  static const KernelFn kernels[EPI_COUNT] = {igemm_kernel<EPI_GENERIC>, igemm_kernel<EPI_PLAIN>, igemm_kernel<EPI_RES>,
+                                              igemm_kernel<EPI_ROWBIAS>, igemm_kernel<EPI_GEGLU>, igemm_kernel<EPI_HEADS>};
+  static thread_local bool configured = false;
+  if (!configured) {
+    for (int i = 0; i < EPI_COUNT; ++i)
+      CB_CHECK_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    configured = true;
+  }
+  kernels[epi]<<<grid, NUM_THREADS, smem, stream>>>(mapA0, mapA1, mapB, p);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

@@ -144,19 +144,20 @@ def choose_tile(n: int, h: int, w: int) -> Tuple[int, int, int]:
     return tw, th, tn
 
 
+NUM_SMS = 148  # B200
+
+
 def choose_bn(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
-    """N tile: largest of (160, 128, 64, 32) with little padding waste that still yields >= 2 CTAs per SM."""
+    """N tile for the persistent kernel (one CTA per SM): minimise rounds x per-tile cost, where a tile costs about
+    bn MMA columns plus a fixed prologue/epilogue share; ties go to the wider tile (fewer A re-reads)."""
     best = None
-    for want_tiles in (296, 148, 1):
-        for bn in (160, 128, 64, 32):
-            if bn % multiple:
-                continue
-            nt = -(-cout_cols // bn)
-            waste = nt * bn / cout_cols
-            if waste <= 1.1 and nt * m_tiles >= want_tiles:
-                return bn
-            if best is None or waste < best[0]:
-                best = (waste, bn)
+    for bn in (160, 128, 64, 32):
+        if bn % multiple:
+            continue
+        tiles = m_tiles * (-(-cout_cols // bn))
+        cost = (-(-tiles // NUM_SMS)) * (bn + 24)
+        if best is None or cost < best[0]:
+            best = (cost, bn)
     return best[1]
 
 

@@ -64,7 +64,7 @@ def bench_attn(B, iters, warm):
               f"{fl / ms / 1e9 / tf_peak:6.1%} of burst peak")
 
 
-def bench_igemm(B, iters, warm):
+def bench_igemm(B, iters, warm, filt=""):
     tf_peak, _ = peaks()
     print("== implicit GEMM (cb_igemm) ==")
     shapes = [
@@ -81,6 +81,8 @@ def bench_igemm(B, iters, warm):
         ("conv3x3 256->256 @256 vae", B // 2, 256, 256, 256, 256, 9), ("conv3x3 128->128 @512 vae", B // 2, 512, 512, 128, 128, 9),
     ]
     for name, n, h, w, cin, cout, taps in shapes:
+        if filt and filt not in name:
+            continue
         x = act(n, h, w, cin)
         wt = ops.pack_weight(torch.randn(cout, cin, 3 if taps == 9 else 1, 3 if taps == 9 else 1, device="cuda") * (taps * cin) ** -0.5)
         bias = torch.zeros(cout, device="cuda")
@@ -93,6 +95,8 @@ def bench_igemm(B, iters, warm):
     # GEGLU
     for name, m, dim in [("geglu 320->2560 @4096", B * 4096, 320), ("geglu 640->5120 @1024", B * 1024, 640),
                          ("geglu 1280->10240 @256", B * 256, 1280)]:
+        if filt and filt not in name:
+            continue
         x = act(m, dim)
         w = torch.randn(8 * dim, dim, device="cuda") * dim ** -0.5
         b = torch.zeros(8 * dim, device="cuda")
@@ -130,10 +134,11 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--warm", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--filter", default="", help="substring filter on igemm shape names")
     a = ap.parse_args()
     if a.only in ("all", "attn"):
         bench_attn(a.batch, a.iters, a.warm)
     if a.only in ("all", "igemm"):
-        bench_igemm(a.batch, a.iters, a.warm)
+        bench_igemm(a.batch, a.iters, a.warm, a.filter)
     if a.only in ("all", "norm"):
         bench_norm(a.batch, a.iters, a.warm)
