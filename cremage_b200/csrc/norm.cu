@@ -193,6 +193,135 @@ __global__ void gn_apply_kernel(const act_t* __restrict__ x0, int c0, const act_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// GroupNorm, single pass for tensors whose per-image group slab fits the shared memory of one thread-block cluster
+// (every GroupNorm of the UNet): a cluster of 8 CTAs owns (image n, a set of `gset` groups); CTA r loads pixels
+// [r*ppc, (r+1)*ppc) of those channels ONCE into shared memory while accumulating statistics, the 8 partials are
+// exchanged through distributed shared memory (fixed order -> deterministic), then each CTA normalises its slab from
+// shared memory and writes it.  HBM traffic = one read + one write, the algorithmic minimum.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int GN_CLUSTER = 8;
+
+__global__ void gn_cluster_kernel(const act_t* __restrict__ x0, int c0, const act_t* __restrict__ x1, int c1,
+                                  long long hw, int groups, int gset, int P, int ppc, float eps,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                  act_t* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  const int C = c0 + c1;
+  const int gs = C / groups;
+  const int nch = gset * gs;               // channels of this cluster (multiple of 8)
+  const int cvs = nch >> 3;
+  uint4* slab = reinterpret_cast<uint4*>(gn_smem);                                   // [ppc][cvs] 16-byte vectors
+  float* s_part = reinterpret_cast<float*>(gn_smem + (size_t)ppc * cvs * 16);        // [2][P][nch]
+  float* s_grp = s_part + 2 * P * nch;                                               // [gset][2] this CTA's partial
+  float* s_stat = s_grp + 2 * gset;                                                  // [gset][2] mean, rstd
+  const unsigned rank = blockIdx.x;  // cluster spans gridDim.x == GN_CLUSTER
+  const int n = blockIdx.z;
+  const int c_lo = blockIdx.y * nch;
+  const int cv = threadIdx.x % cvs;
+  const int lp = threadIdx.x / cvs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int c = c_lo + (cv << 3);
+  const act_t* src;
+  long long ld;
+  if (c < c0) { src = x0 + (long long)n * hw * c0 + c; ld = c0; }
+  else        { src = x1 + (long long)n * hw * c1 + (c - c0); ld = c1; }
+  const long long p_lo = (long long)rank * ppc;
+  long long p_hi = p_lo + ppc;
+  if (p_hi > hw) p_hi = hw;
+
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  if (lp < P) {
+    long long pp = p_lo + lp;
+    for (; pp + 3LL * P < p_hi; pp += 4LL * P) {   // four independent 16-byte loads in flight
+      uint4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const uint4*>(src + (pp + (long long)u * P) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        slab[(pp + (long long)u * P - p_lo) * cvs + cv] = t[u];
+        Vec8 v; v.u[0] = t[u].x; v.u[1] = t[u].y; v.u[2] = t[u].z; v.u[3] = t[u].w;
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      }
+    }
+    for (; pp < p_hi; pp += P) {
+      const uint4 t = *reinterpret_cast<const uint4*>(src + pp * ld);
+      slab[(pp - p_lo) * cvs + cv] = t;
+      Vec8 v; v.u[0] = t.x; v.u[1] = t.y; v.u[2] = t.z; v.u[3] = t.w;
+      float f[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+    }
+    float* ps = s_part + (long long)lp * nch + (cv << 3);
+    float* pq = s_part + (long long)(P + lp) * nch + (cv << 3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ps[i] = s[i]; pq[i] = q[i]; }
+  }
+  __syncthreads();
+  for (int g = warp; g < gset; g += nwarps) {
+    float a = 0.f, b = 0.f;
+    for (int e = lane; e < gs * P; e += 32) {
+      const int l = e / gs, ch = g * gs + (e - l * gs);
+      a += s_part[(long long)l * nch + ch];
+      b += s_part[(long long)(P + l) * nch + ch];
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) { s_grp[2 * g] = a; s_grp[2 * g + 1] = b; }
+  }
+  // cluster barrier #1: every CTA's partials are written
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if ((int)threadIdx.x < gset) {
+    const int g = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    const uint32_t local = smem_u32(s_grp + 2 * g);
+    for (unsigned r = 0; r < GN_CLUSTER; ++r) {   // fixed rank order: deterministic
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+      float ra, rb;
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(ra) : "r"(remote) : "memory");
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(rb) : "r"(remote + 4u) : "memory");
+      a += ra;
+      b += rb;
+    }
+    const float inv_cnt = 1.f / (float(gs) * float(hw));
+    const float mean = a * inv_cnt;
+    const float var = fmaxf(b * inv_cnt - mean * mean, 0.f);
+    s_stat[2 * g] = mean;
+    s_stat[2 * g + 1] = rsqrtf(var + eps);
+  }
+  // cluster barrier #2: all remote reads are done (a CTA may exit afterwards) and s_stat is visible CTA-wide
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (lp >= P) return;
+  float ga[8], gb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = ((cv << 3) + i) / gs;
+    const float mean = s_stat[2 * g], rstd = s_stat[2 * g + 1];
+    ga[i] = rstd * gamma[c + i];
+    gb[i] = beta[c + i] - mean * ga[i];
+  }
+  act_t* dst = out + (long long)n * hw * C + c;
+  for (long long pp = p_lo + lp; pp < p_hi; pp += P) {
+    const uint4 t = slab[(pp - p_lo) * cvs + cv];
+    Vec8 v; v.u[0] = t.x; v.u[1] = t.y; v.u[2] = t.z; v.u[3] = t.w;
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float y = fmaf(f[i], ga[i], gb[i]);
+      f[i] = silu ? silu_f(y) : y;
+    }
+    st_vec8(dst + pp * C, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row lives in registers (two-pass mean / variance, exact in fp32).
 // ------------------------------------------------------------------------------------------------------------
 template <int MAXV>
@@ -347,6 +476,54 @@ extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int
   CB_REQUIRE(groups > 0 && C % groups == 0, "cb_groupnorm_nhwc: %lld channels not divisible into %d groups", (long long)C, groups);
   CB_REQUIRE(n > 0 && hw > 0, "cb_groupnorm_nhwc: empty input");
   CB_REQUIRE(C / 8 <= 1024, "cb_groupnorm_nhwc: more than 8192 channels unsupported");
+  // ---- single-pass cluster kernel when the per-image slab of a group set fits 8 CTAs' shared memory
+  {
+    const int gs = int(C / groups);
+    const int ppc = int((hw + GN_CLUSTER - 1) / GN_CLUSTER);
+    int gset = 0;
+    // largest group set (longest contiguous per-pixel run, fewest clusters) whose slab fits and that still yields
+    // >= 256 CTAs; measured better than many tiny clusters (cluster launch + two cluster barriers per CTA dominate)
+    for (int cand = groups; cand >= 1; cand >>= 1) {
+      const long long nch = (long long)cand * gs;
+      if (groups % cand || nch % 8 || nch * 2 < 64) continue;
+      if ((long long)ppc * nch * 2 <= 96 * 1024 && (long long)n * (groups / cand) * GN_CLUSTER >= 256) { gset = cand; break; }
+    }
+    if (gset == 0) {  // small batch: take the largest set that fits
+      for (int cand = groups; cand >= 1; cand >>= 1) {
+        const long long nch = (long long)cand * gs;
+        if (groups % cand || nch % 8 || nch * 2 < 64) continue;
+        if ((long long)ppc * nch * 2 <= 96 * 1024) { gset = cand; break; }
+      }
+    }
+    if (gset > 0 && hw >= GN_CLUSTER && n <= 65535) {
+      const int nch = gset * gs, cvs = nch / 8;
+      int P = 256 / cvs;
+      if (P < 1) P = 1;
+      if (P > ppc) P = ppc;
+      const int threads = (cvs * P + 31) / 32 * 32;
+      if (threads <= 1024) {
+        const size_t smem = (size_t)ppc * nch * 2 + sizeof(float) * (2 * (size_t)P * nch + 4 * (size_t)gset) + 16;
+        static thread_local bool cfg = false;
+        if (!cfg) {
+          CB_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          cfg = true;
+        }
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(GN_CLUSTER, (unsigned)(groups / gset), (unsigned)n);
+        lc.blockDim = dim3((unsigned)threads);
+        lc.dynamicSmemBytes = smem;
+        lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = GN_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        CB_CHECK_CUDA(cudaLaunchKernelEx(&lc, gn_cluster_kernel, (const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1,
+                                         (long long)hw, groups, gset, P, ppc, eps, gamma, beta, silu, (act_t*)out));
+        CB_LAUNCHED(1);
+        return CB_OK;
+      }
+    }
+  }
   const GnPlan g = gn_plan(n, hw, C);
   CB_REQUIRE(g.smem <= 160 * 1024, "cb_groupnorm_nhwc: needs %zu bytes of shared memory", g.smem);
   // workspace: [n][groups][2] final sums | [n][splits][groups][2] partials | [n] ticket counters
