@@ -35,6 +35,8 @@ WORKLOADS = {
     "euler20_b8": (8, "euler_a", 20),
     "euler20_b1": (1, "euler_a", 20),
     "dpmpp2m30_b8": (8, "dpmpp_2m", 30),
+    # BASELINE.json configs[3]: hires-fix 512 -> 1024, denoise 0.5 (20-step DDIM, 10 steps at 128x128 latents), 4 / GPU
+    "hires20_b4": (4, "hires", 20),
 }
 CFG_SCALE = 7.5
 # algorithmic work per image (BASELINE.md section 3, 2*MACs of the reference graph)
@@ -145,6 +147,16 @@ def make_runner(ldm, workload):
     from cremage_b200.ldm.models.diffusion.ddim import DDIMSampler
     from cremage_b200.ldm.models.diffusion.ldm_wrapper_for_k_diffusion import LDMWrapperForKDiffusion
     b, sampler, steps = WORKLOADS[workload]
+    if sampler == "hires":
+        from cremage_b200.hires import hires_fix_latent
+        smp = DDIMSampler(ldm)
+
+        def run(x_T, cond, uncond, noise):
+            z, _ = smp.sample(S=steps, batch_size=b, shape=[4, 64, 64], conditioning=cond, eta=0.0, x_T=x_T,
+                              unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=uncond, verbose=False)
+            z = hires_fix_latent(smp, z, cond, uncond, CFG_SCALE, sampling_steps=steps, strength=0.5, noise=noise)
+            return ldm.decode_first_stage(z, to_uint8=True)
+        return run
     if sampler == "ddim":
         smp = DDIMSampler(ldm)
 
@@ -220,9 +232,12 @@ def run_ours(args):
     h_uncond = torch.randn(b, 77, 768, generator=gen).pin_memory()
     h_xT = torch.randn(b, 4, 64, 64, generator=gen).pin_memory()
     noise = torch.randn(steps, b, 4, 64, 64, generator=gen).cuda() if sampler == "euler_a" else None
-    h_img = torch.empty(b, 512, 512, 3, dtype=torch.uint8).pin_memory()
+    if sampler == "hires":
+        noise = torch.randn(b, 4, 128, 128, generator=gen).cuda()
+    out_px = 1024 if sampler == "hires" else 512
+    h_img = torch.empty(b, out_px, out_px, 3, dtype=torch.uint8).pin_memory()
     d_cond, d_uncond, d_xT = h_cond.cuda(), h_uncond.cuda(), h_xT.cuda()
-    gathered = torch.empty(world * b, 512, 512, 3, dtype=torch.uint8, device="cuda") if world > 1 else None
+    gathered = torch.empty(world * b, out_px, out_px, 3, dtype=torch.uint8, device="cuda") if world > 1 else None
 
     def step_resident():
         img = run(d_xT, d_cond, d_uncond, noise)
@@ -299,6 +314,8 @@ def run_ours(args):
                 e["frac_of_hbm"] = round(e["gbs"] / pk["hbm_gbs"], 4)
             kernels[f"{phase}/{name}"] = e
     gf_per_image = steps * 2 * GF_UNET_PER_SAMPLE_FWD + GF_VAE_PER_IMAGE
+    if sampler == "hires":  # + 10 CFG steps at 128x128 latents (9348 GF each) and a 1024x1024 decode (~10.5 TF), BASELINE.md section 3
+        gf_per_image = steps * 2 * GF_UNET_PER_SAMPLE_FWD + int(0.5 * steps) * 9348.0 + 10500.0
     cpu = cpu_baseline_sample(steps) if world == 1 and not args.no_cpu_baseline else None
     line = {
         "metric": "SD1.5 512x512 images/sec (UNet + sampler + VAE decode)", "value": round(value, 4),

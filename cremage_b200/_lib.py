@@ -72,6 +72,7 @@ SIGNATURES = {
     "cb_step_euler_ancestral": [_vp, _vp, _vp, _int, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
     "cb_step_dpmpp_2m": [_vp, _vp, _vp, _int, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
     "cb_step_ddim": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "cb_bilinear_upsample_f32": [_vp, _i64, _i64, _i64, _int, _vp, _vp],
     "cb_image_to_u8": [_vp, _i64, _i64, _i64, _vp, _vp],
 }
 _RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64, "cb_groupnorm_workspace_bytes": C.c_int64}

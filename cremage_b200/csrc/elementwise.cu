@@ -183,6 +183,31 @@ __global__ void silu_add_kernel(const act_t* __restrict__ x, const act_t* __rest
   out[i] = to_act(silu_f(v));
 }
 
+// bilinear upsample by an integer factor, align_corners=False (F.interpolate semantics: src = (dst + 0.5) / scale - 0.5,
+// clamped at 0; neighbours clamped at the last index), fp32 planes [planes][h][w] -> [planes][h*f][w*f]
+__global__ void bilinear_upsample_kernel(const float* __restrict__ src, long long planes, int h, int w, int f,
+                                         float* __restrict__ dst) {
+  const int oh = h * f, ow = w * f;
+  const long long total = planes * oh * ow;
+  const float rs = 1.f / float(f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = int(i % ow);
+    long long t = i / ow;
+    const int oy = int(t % oh);
+    const long long pl = t / oh;
+    float sy = (float(oy) + 0.5f) * rs - 0.5f;
+    float sx = (float(ox) + 0.5f) * rs - 0.5f;
+    sy = sy < 0.f ? 0.f : sy;
+    sx = sx < 0.f ? 0.f : sx;
+    const int y0 = int(sy), x0 = int(sx);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = sy - float(y0), lx = sx - float(x0);
+    const float* sp = src + pl * h * w;
+    const float v00 = sp[y0 * w + x0], v01 = sp[y0 * w + x1], v10 = sp[y1 * w + x0], v11 = sp[y1 * w + x1];
+    dst[i] = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  }
+}
+
 __global__ void image_to_u8_kernel(const float* __restrict__ src, long long npix, long long c_ld,
                                    uint8_t* __restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -307,6 +332,16 @@ extern "C" int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64
 extern "C" int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream) {
   CB_REQUIRE(x && out && count > 0, "cb_silu_add: bad arguments");
   silu_add_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>((const act_t*)x, (const act_t*)add, count, (act_t*)out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_bilinear_upsample_f32(const float* src, int64_t planes, int64_t h, int64_t w, int factor, float* dst,
+                                       cudaStream_t stream) {
+  CB_REQUIRE(src && dst && planes > 0 && h > 0 && w > 0 && factor >= 1, "cb_bilinear_upsample_f32: bad arguments");
+  const long long total = planes * h * factor * w * factor;
+  bilinear_upsample_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, planes, (int)h, (int)w, factor, dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

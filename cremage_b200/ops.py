@@ -388,6 +388,16 @@ def silu_add(x: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tenso
     return out
 
 
+def bilinear_upsample(x: torch.Tensor, factor: int) -> torch.Tensor:
+    """F.interpolate(x, scale_factor=factor, mode='bilinear', align_corners=False) for fp32 NCHW latents."""
+    _need_cuda(x)
+    x = x.float().contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, h * factor, w * factor), dtype=torch.float32, device=x.device)
+    _launch("cb_bilinear_upsample_f32", lambda: _lib.load().cb_bilinear_upsample_f32(_p(x), n * c, h, w, factor, _p(out), _stream()))
+    return out
+
+
 def image_to_u8(x: torch.Tensor) -> torch.Tensor:
     """x: fp32 NHWC [N,H,W,C_ld>=3] in [-1,1] -> uint8 [N,H,W,3]."""
     _need_cuda(x)

@@ -172,6 +172,10 @@ int cb_step_dpmpp_2m(const float* x, const float* eps_u, const float* eps_c, int
 int cb_step_ddim(const float* x, const float* eps_u, const float* eps_c, const float* noise, int64_t count,
                  float cfg_scale, float sqrt_at, float sqrt_one_minus_at, float sqrt_aprev, float dir_coef, float sigma_t,
                  float* x_out, float* pred_x0_out, cudaStream_t stream);
+/* hires-fix latent upscale (sd/image_generator.py:975: F.interpolate(samples, scale_factor, 'bilinear',
+ * align_corners=False)): fp32 [planes][h][w] -> [planes][h*factor][w*factor] */
+int cb_bilinear_upsample_f32(const float* src, int64_t planes, int64_t h, int64_t w, int factor, float* dst,
+                             cudaStream_t stream);
 /* image post-process (sd/image_generator.py:1017-1018,1151-1152): NHWC fp32 [n][hw][c_ld] -> uint8 HWC [n][hw][3],
  * clamp((x+1)/2,0,1)*255 truncated */
 int cb_image_to_u8(const void* src, int64_t n, int64_t hw, int64_t c_ld, uint8_t* dst, cudaStream_t stream);

@@ -115,6 +115,19 @@ def _sampler_goldens(unet, cfg_scale, cond, uncond, x_T, noise, steps_euler, ste
                           img_callback=lambda pred_x0, i: inter.append(pred_x0.clone()))
         out["ddim_final"] = x.numpy()
         out["ddim_pred_x0_trace"] = torch.stack(inter).numpy()
+        # hires-fix second pass, latent upscaler (sd/image_generator.py:969-999 -> img2img_sampling DDIM branch)
+        import torch.nn.functional as F
+        strength = 0.6
+        smp.make_schedule(ddim_num_steps=steps_ddim, ddim_eta=0.0, verbose=False)
+        up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        t_enc = int(strength * steps_ddim)
+        hnoise = randn(tuple(up.shape), 77)
+        z_enc = smp.stochastic_encode(up, torch.tensor([t_enc] * x.shape[0]), noise=hnoise)
+        xh = smp.decode(z_enc, cond, t_enc, unconditional_guidance_scale=cfg_scale, unconditional_conditioning=uncond)
+        out["hires_strength"] = np.float32(strength)
+        out["hires_noise"] = hnoise.numpy()
+        out["hires_upsampled"] = up.numpy()
+        out["hires_final"] = xh.numpy()
     return out
 
 

@@ -602,3 +602,44 @@ def ddim_sample(eps_fn: Callable[[Tensor, Tensor, Tensor], Tensor], alphas_cumpr
         if trace is not None:
             trace.append(img.clone())
     return img
+
+
+def ddim_stochastic_encode(alphas_cumprod: Tensor, x0: Tensor, t_index: int, S: int, noise: Tensor) -> Tensor:
+    """DDIMSampler.stochastic_encode, ddim.py:615-655 (use_original_steps=False): index into the S-step DDIM tables."""
+    ts = make_ddim_timesteps(S, alphas_cumprod.shape[0])
+    _, alphas, _ = make_ddim_sampling_parameters(alphas_cumprod.cpu(), ts, 0.0)
+    sqrt_a = torch.sqrt(alphas)
+    sqrt_1ma = np.sqrt(1.0 - alphas)
+    return float(sqrt_a[t_index]) * x0 + float(sqrt_1ma[t_index]) * noise
+
+
+def ddim_decode(eps_fn, alphas_cumprod: Tensor, x_latent: Tensor, cond: Tensor, uncond: Tensor, cfg_scale: float,
+                S: int, t_start: int) -> Tensor:
+    """DDIMSampler.decode, ddim.py:657-676: the last `t_start` DDIM steps (eta = 0) with classifier-free guidance."""
+    ts_all = make_ddim_timesteps(S, alphas_cumprod.shape[0])
+    sig, alphas, alphas_prev = make_ddim_sampling_parameters(alphas_cumprod.cpu(), ts_all, 0.0)
+    sqrt_one_minus_alphas = np.sqrt(1.0 - alphas)
+    timesteps = ts_all[:t_start]
+    x = x_latent
+    b = x.shape[0]
+    total = timesteps.shape[0]
+    for i, step in enumerate(np.flip(timesteps)):
+        index = total - i - 1
+        ts = torch.full((b,), int(step), device=x.device, dtype=torch.long)
+        e_u, e_c = eps_fn(torch.cat([x] * 2), torch.cat([ts] * 2), torch.cat([uncond, cond])).chunk(2)
+        e_t = e_u + cfg_scale * (e_c - e_u)
+        a_t = torch.full((b, 1, 1, 1), alphas[index])
+        a_prev = torch.full((b, 1, 1, 1), alphas_prev[index])
+        s1 = torch.full((b, 1, 1, 1), sqrt_one_minus_alphas[index])
+        pred_x0 = (x - s1 * e_t) / a_t.sqrt()
+        x = a_prev.sqrt() * pred_x0 + (1.0 - a_prev).sqrt() * e_t
+    return x
+
+
+def hires_fix_latent_ddim(eps_fn, alphas_cumprod: Tensor, samples: Tensor, cond: Tensor, uncond: Tensor, cfg_scale: float,
+                          S: int, strength: float, noise: Tensor, factor: int = 2) -> Tensor:
+    """sd/image_generator.py:969-999 (latent upscaler) + img2img_sampling :147-248 (DDIM branch)."""
+    up = F.interpolate(samples, scale_factor=factor, mode="bilinear", align_corners=False)
+    t_enc = int(strength * S)
+    z_enc = ddim_stochastic_encode(alphas_cumprod, up, t_enc, S, noise)
+    return ddim_decode(eps_fn, alphas_cumprod, z_enc, cond, uncond, cfg_scale, S, t_enc)
