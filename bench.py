@@ -37,8 +37,15 @@ WORKLOADS = {
     "dpmpp2m30_b8": (8, "dpmpp_2m", 30),
     # BASELINE.json configs[3]: hires-fix 512 -> 1024, denoise 0.5 (20-step DDIM, 10 steps at 128x128 latents), 4 / GPU
     "hires20_b4": (4, "hires", 20),
+    # BASELINE.json configs[4]: SDXL base 1024x1024, 30-step DPM++ 2M Karras (sgm DPMPP2MSampler + EDMDiscretization),
+    # VanillaCFG, dual text-encoder context [77, 2048] + pooled/size vector [2816]; batch 8 over 8 GPUs = 1 / GPU
+    "sdxl30_b1": (1, "sdxl", 30),
+    "sdxl30_b4": (4, "sdxl", 30),
 }
 CFG_SCALE = 7.5
+# dram__bytes_read.sum + dram__bytes_write.sum of the igemm launches of one UNet forward (ncu --set full capture,
+# profiles/): filled in from the committed capture; null until one exists for the current kernel
+IGEMM_DRAM_TRAFFIC_NOTE = None
 # algorithmic work per image (BASELINE.md section 3, 2*MACs of the reference graph)
 GF_UNET_PER_SAMPLE_FWD = 803.27
 GF_VAE_PER_IMAGE = 2514.5
@@ -46,6 +53,13 @@ GF_VAE_PER_IMAGE = 2514.5
 SD15_UNET = dict(image_size=32, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
                  num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
                  transformer_depth=1, context_dim=768, use_checkpoint=True, legacy=False)
+SDXL_UNET = dict(adm_in_channels=2816, num_classes="sequential", use_checkpoint=True, in_channels=4, out_channels=4,
+                 model_channels=320, attention_resolutions=[4, 2], num_res_blocks=2, channel_mult=[1, 2, 4],
+                 num_head_channels=64, use_linear_in_transformer=True, transformer_depth=[1, 2, 10], context_dim=2048,
+                 spatial_transformer_attn_type="softmax-xformers")   # sdxl/configs/inference/sd_xl_base.yaml:17-33
+SDXL_CFG_SCALE = 5.0
+GF_SDXL_UNET_PER_CFG_PAIR = 13522.5
+GF_SDXL_VAE_PER_IMAGE = 10500.0
 SD15_VAE = dict(embed_dim=4, lossconfig=None,
                 ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
                               ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0))
@@ -140,8 +154,52 @@ def build_pipeline():
     return LatentDiffusion(unet, vae).cuda().eval()
 
 
-def make_runner(ldm, workload):
-    """Returns run(x_T, cond, uncond) -> uint8 images [b, 512, 512, 3] through the repo's public (reference-mirroring) API."""
+def build_sdxl_pipeline():
+    """DiffusionEngine of sd_xl_base.yaml (UNet + DiscreteDenoiser/EpsScaling + the same AutoencoderKL decoder graph)."""
+    from cremage_b200.sgm.models.autoencoder import AutoencoderKLInferenceWrapper
+    from cremage_b200.sgm.models.diffusion import DiffusionEngine
+    from cremage_b200.sgm.modules.diffusionmodules.denoiser import DiscreteDenoiser
+    from cremage_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+    with torch.device("meta"):
+        unet = UNetModel(**SDXL_UNET)
+        vae = AutoencoderKLInferenceWrapper(**SD15_VAE)
+    unet = unet.to_empty(device="cuda")
+    vae = vae.to_empty(device="cuda")
+    init_random_(unet, 0)
+    init_random_(vae, 1)
+    den = DiscreteDenoiser(scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+                           num_idx=1000,
+                           discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"})
+    return DiffusionEngine(unet, den, vae, scale_factor=0.13025, disable_first_stage_autocast=True).cuda().eval()
+
+
+def make_sdxl_runner(eng, workload):
+    from cremage_b200.sgm.modules.diffusionmodules.sampling import DPMPP2MSampler
+    b, _, steps = WORKLOADS[workload]
+    smp = DPMPP2MSampler(discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization",
+                                                "params": {"sigma_min": 0.0292, "sigma_max": 14.6146, "rho": 3.0}},
+                         num_steps=steps, guider_config={"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG",
+                                                         "params": {"scale": SDXL_CFG_SCALE}})
+    denoiser = lambda inp, sigma, c: eng.denoiser(eng.model, inp, sigma, c)
+
+    def run(inp):
+        cond = {"crossattn": inp["cond"], "vector": inp["cond_vec"]}
+        uc = {"crossattn": inp["uncond"], "vector": inp["uncond_vec"]}
+        z = smp(denoiser, inp["x_T"], cond=cond, uc=uc)
+        return eng.decode_first_stage(z, to_uint8=True)
+    return run
+
+
+def make_runner(pipe, workload):
+    """Returns run(inputs: dict of device tensors) -> uint8 images [b, H, W, 3] through the repo's public
+    (reference-mirroring) API."""
+    if WORKLOADS[workload][1] == "sdxl":
+        return make_sdxl_runner(pipe, workload)
+    f = _make_sd15_runner(pipe, workload)
+    return lambda inp: f(inp["x_T"], inp["cond"], inp["uncond"], inp.get("noise"))
+
+
+def _make_sd15_runner(ldm, workload):
     from cremage_b200.k_diffusion.external import CompVisDenoiser
     from cremage_b200.k_diffusion.sampling import get_sigmas_karras, sample_dpmpp_2m, sample_euler_ancestral
     from cremage_b200.ldm.models.diffusion.ddim import DDIMSampler
@@ -185,33 +243,59 @@ def make_runner(ldm, workload):
     return run
 
 
-def kernel_breakdown(ldm, b):
+def unet_probe_inputs(workload):
+    """One CFG-doubled UNet call of the workload (public forward signature) for the step-latency / breakdown probes."""
+    b, sampler, _ = WORKLOADS[workload]
+    if sampler == "sdxl":
+        return (torch.randn(2 * b, 4, 128, 128, device="cuda"), torch.full((2 * b,), 500.0, device="cuda")), \
+               dict(context=torch.randn(2 * b, 77, 2048, device="cuda"), y=torch.randn(2 * b, 2816, device="cuda"))
+    return (torch.randn(2 * b, 4, 64, 64, device="cuda"), torch.full((2 * b,), 500.0, device="cuda")), \
+           dict(context=torch.randn(2 * b, 77, 768, device="cuda"))
+
+
+def kernel_breakdown(unet, vae, workload):
     """One eager UNet forward (CFG batch 2b) + one VAE decode with CUDA events around every launch of this library:
     per-kernel time shares and achieved rates for the roofline section."""
     from cremage_b200 import ops
-    unet = ldm.model.diffusion_model
-    x = torch.randn(2 * b, 4, 64, 64, device="cuda")
-    t = torch.full((2 * b,), 500.0, device="cuda")
-    ctx = torch.randn(2 * b, 77, 768, device="cuda")
-    z = torch.randn(b, 4, 64, 64, device="cuda")
+    b, sampler, _ = WORKLOADS[workload]
+    args, kw = unet_probe_inputs(workload)
+    lat = 128 if sampler in ("sdxl", "hires") else 64
+    z = torch.randn(b, 4, lat, lat, device="cuda")
     saved = unet.use_cuda_graph
     unet.use_cuda_graph = False
     out = {}
     try:
         with torch.no_grad():
             for _ in range(2):
-                unet(x, t, context=ctx)
+                unet(*args, **kw)
             with ops.LaunchProfile() as prof:
                 for _ in range(3):
-                    unet(x, t, context=ctx)
+                    unet(*args, **kw)
             out["unet_fwd"] = {k: {kk: vv / 3 for kk, vv in v.items()} for k, v in prof.summary().items()}
-            ldm.first_stage_model.decode(z)
+            vae.decode(z)
             with ops.LaunchProfile() as prof:
-                ldm.first_stage_model.decode(z)
+                vae.decode(z)
             out["vae_decode"] = prof.summary()
     finally:
         unet.use_cuda_graph = saved
     return out
+
+
+def make_host_inputs(workload, rank):
+    """Pinned host buffers of one batch (what a caller hands over): latents, context (and SDXL vector conditioning)."""
+    b, sampler, steps = WORKLOADS[workload]
+    gen = torch.Generator().manual_seed(1000 + rank)
+    r = lambda *shape: torch.randn(*shape, generator=gen).pin_memory()
+    if sampler == "sdxl":
+        return {"cond": r(b, 77, 2048), "uncond": r(b, 77, 2048), "cond_vec": r(b, 2816), "uncond_vec": r(b, 2816),
+                "x_T": r(b, 4, 128, 128)}, {}
+    host = {"cond": r(b, 77, 768), "uncond": r(b, 77, 768), "x_T": r(b, 4, 64, 64)}
+    resident = {}
+    if sampler == "euler_a":   # injected ancestral noise (seeded, resident: the reference draws it on the device)
+        resident["noise"] = torch.randn(steps, b, 4, 64, 64, generator=gen).cuda()
+    if sampler == "hires":
+        resident["noise"] = torch.randn(b, 4, 128, 128, generator=gen).cuda()
+    return host, resident
 
 
 def run_ours(args):
@@ -224,30 +308,32 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     b, sampler, steps = WORKLOADS[args.workload]
-    ldm = build_pipeline()
-    run = make_runner(ldm, args.workload)
+    sdxl = sampler == "sdxl"
+    if sdxl:
+        pipe = build_sdxl_pipeline()
+        unet, vae = pipe.model.diffusion_model, pipe.first_stage_model
+    else:
+        pipe = build_pipeline()
+        unet, vae = pipe.model.diffusion_model, pipe.first_stage_model
+    run = make_runner(pipe, args.workload)
 
-    gen = torch.Generator().manual_seed(1000 + rank)
-    h_cond = torch.randn(b, 77, 768, generator=gen).pin_memory()
-    h_uncond = torch.randn(b, 77, 768, generator=gen).pin_memory()
-    h_xT = torch.randn(b, 4, 64, 64, generator=gen).pin_memory()
-    noise = torch.randn(steps, b, 4, 64, 64, generator=gen).cuda() if sampler == "euler_a" else None
-    if sampler == "hires":
-        noise = torch.randn(b, 4, 128, 128, generator=gen).cuda()
-    out_px = 1024 if sampler == "hires" else 512
+    host, resident = make_host_inputs(args.workload, rank)
+    out_px = 1024 if sampler in ("hires", "sdxl") else 512
     h_img = torch.empty(b, out_px, out_px, 3, dtype=torch.uint8).pin_memory()
-    d_cond, d_uncond, d_xT = h_cond.cuda(), h_uncond.cuda(), h_xT.cuda()
+    dev = {k: v.cuda() for k, v in host.items()}
+    dev.update(resident)
     gathered = torch.empty(world * b, out_px, out_px, 3, dtype=torch.uint8, device="cuda") if world > 1 else None
 
     def step_resident():
-        img = run(d_xT, d_cond, d_uncond, noise)
+        img = run(dev)
         if world > 1:
             dist.all_gather_into_tensor(gathered, img)
         return img
 
     def step_e2e():
-        x, c, u = h_xT.cuda(non_blocking=True), h_cond.cuda(non_blocking=True), h_uncond.cuda(non_blocking=True)
-        img = run(x, c, u, noise)
+        inp = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+        inp.update(resident)
+        img = run(inp)
         if world > 1:
             dist.all_gather_into_tensor(gathered, img)
         h_img.copy_(img, non_blocking=True)
@@ -281,13 +367,25 @@ def run_ours(args):
         ms_e2e = timed(step_e2e, args.steps)
         clk = clocks.stop()
         # UNet step latency (one CFG-doubled forward through the public API, graph replay)
-        unet = ldm.model.diffusion_model
-        x2 = torch.randn(2 * b, 4, 64, 64, device="cuda")
-        t2 = torch.full((2 * b,), 500.0, device="cuda")
-        c2 = torch.randn(2 * b, 77, 768, device="cuda")
-        unet(x2, t2, context=c2)
-        unet_ms = timed(lambda: unet(x2, t2, context=c2), 10) / 10
-        brk = kernel_breakdown(ldm, b) if rank == 0 else None
+        pa, pkw = unet_probe_inputs(args.workload)
+        unet(*pa, **pkw)
+        unet_ms = timed(lambda: unet(*pa, **pkw), 10) / 10
+        brk = kernel_breakdown(unet, vae, args.workload) if rank == 0 else None
+        also = {}
+        if rank == 0 and world == 1 and args.workload == "ddim50_b8" and not args.no_extra:
+            # BASELINE.json's metric is quoted as "20-step images/sec": the 20-step Euler-ancestral sampler of
+            # configs[0] (k-diffusion path) at the same batch 8 and at the reference's own batch 1, same pipeline
+            for wl in ("euler20_b8", "euler20_b1"):
+                h2, r2 = make_host_inputs(wl, rank)
+                d2 = {k: v.cuda() for k, v in h2.items()}
+                d2.update(r2)
+                run2 = make_runner(pipe, wl)
+                for _ in range(3):
+                    run2(d2)
+                k2 = max(args.steps, 3)
+                ms2 = timed(lambda: run2(d2), k2)
+                also[wl] = {"images_per_s": round(WORKLOADS[wl][0] * k2 / (ms2 / 1e3), 4),
+                            "ms_per_batch": round(ms2 / k2, 3), "batch": WORKLOADS[wl][0], "steps_timed": k2}
 
     if rank != 0:
         if world > 1:
@@ -316,25 +414,32 @@ def run_ours(args):
     gf_per_image = steps * 2 * GF_UNET_PER_SAMPLE_FWD + GF_VAE_PER_IMAGE
     if sampler == "hires":  # + 10 CFG steps at 128x128 latents (9348 GF each) and a 1024x1024 decode (~10.5 TF), BASELINE.md section 3
         gf_per_image = steps * 2 * GF_UNET_PER_SAMPLE_FWD + int(0.5 * steps) * 9348.0 + 10500.0
-    cpu = cpu_baseline_sample(steps) if world == 1 and not args.no_cpu_baseline else None
+    if sdxl:
+        gf_per_image = steps * GF_SDXL_UNET_PER_CFG_PAIR + GF_SDXL_VAE_PER_IMAGE
+    cpu = cpu_baseline_sample(steps) if world == 1 and not args.no_cpu_baseline and not sdxl else None
+    model = "SDXL base txt2img 1024x1024" if sdxl else "SD1.5 txt2img 512x512"
+    scale = SDXL_CFG_SCALE if sdxl else CFG_SCALE
+    wgt_gb = "5.1 GB" if sdxl else "1.8 GB"
     line = {
-        "metric": "SD1.5 512x512 images/sec (UNet + sampler + VAE decode)", "value": round(value, 4),
+        "metric": ("SDXL 1024x1024 images/sec (UNet + sampler + VAE decode)" if sdxl else
+                   "SD1.5 512x512 images/sec (UNet + sampler + VAE decode)"), "value": round(value, 4),
         "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": _dtype_name(), "data": "synthetic",
-        "config": {"workload": f"SD1.5 txt2img 512x512, batch {b}/GPU, {steps}-step {sampler}, CFG {CFG_SCALE}, "
+        "config": {"workload": f"{model}, batch {b}/GPU, {steps}-step {sampler}, CFG {scale}, "
                                f"random-init weights, + AutoencoderKL decode to uint8 ({args.workload})",
                    "global_batch": b * world, "parallelism": f"dp{world} (batch sharded, NCCL all_gather of uint8 images)",
-                   "l2": "no flush: weights (1.8 GB) + activations per step exceed the 126 MB L2",
+                   "l2": f"no flush: weights ({wgt_gb}) + activations per step exceed the 126 MB L2",
                    "algorithmic_gflop_per_image": round(gf_per_image, 1)},
         "e2e": {"value": round(e2e_value, 4), "unit": "images/s",
-                "h2d_bytes_per_step": int(h_xT.numel() * 4 + h_cond.numel() * 4 + h_uncond.numel() * 4),
+                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values())),
                 "d2h_bytes_per_step": int(h_img.numel())},
         "gpu_launches": int(launches),
         "unet_step_ms": round(unet_ms, 3),
         "model_tflops": round(value * gf_per_image / 1e3, 1),
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": pk["bf16_tflops_sustained"],
-                     "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4), "traffic": None,
+                     "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4),
+                     "traffic": IGEMM_DRAM_TRAFFIC_NOTE if not sdxl else None,
                      "kernel": "igemm_kernel (tcgen05 implicit GEMM: conv3x3 / conv1x1 / linear), all launches of one "
                                f"UNet forward at batch {2 * b}; share of UNet kernel time {ig['ms'] / total_ms:.3f}",
                      "peak_source": pk["source"] + " bf16_tflops_sustained"},
@@ -342,6 +447,8 @@ def run_ours(args):
         "clocks": clk,
         "cpu_baseline": cpu,
     }
+    if also:
+        line["metric_20step"] = also
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -395,6 +502,8 @@ def run_reference(args):
     b, sampler, steps = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if sampler == "sdxl":
+        return run_reference_sdxl(args, world, steps, cores)
     O, usd, vsd = _cpu_models()
     g = torch.Generator().manual_seed(5)
     x = torch.randn(2, 4, 64, 64, generator=g)
@@ -428,6 +537,42 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_sdxl(args, world, steps, cores):
+    """CPU arm of the SDXL workload: oracle port of the sgm UNet (one CFG pair at 128x128 latents) + one 1024x1024
+    VAE decode, extrapolated to the 30-step image."""
+    from oracle import sd_oracle as O
+    from oracle import sgm_oracle as S
+    usd = O.make_weights(S.sgm_unet_param_shapes(S.SDXL_UNET), seed=0)
+    vsd = O.make_weights(O.decoder_param_shapes(O.SD15_VAE), seed=1)
+    g = torch.Generator().manual_seed(5)
+    x, t = torch.randn(2, 4, 128, 128, generator=g), torch.tensor([500, 500])
+    ctx, y = torch.randn(2, 77, 2048, generator=g), torch.randn(2, 2816, generator=g)
+    k = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(k):
+            S.sgm_unet_forward(usd, S.SDXL_UNET, x, t, ctx, y)
+    t_unet = (time.perf_counter() - t0) / k
+    z = torch.randn(1, 4, 128, 128, generator=g)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.vae_decode(vsd, O.SD15_VAE, z)
+    t_vae = time.perf_counter() - t0
+    per_image = steps * t_unet + t_vae
+    value = 1.0 / per_image
+    sample = (f"each step = 1 CFG-pair sgm UNet forward at B=1, 128x128 latents ({t_unet:.1f} s, mean of {k}); + 1 VAE decode "
+              f"to 1024x1024 ({t_vae:.1f} s); extrapolated to {steps} steps + decode per image; oracle port, fp32, {cores} host threads")
+    line = {"impl": "reference", "metric": "SDXL 1024x1024 images/sec (UNet + sampler + VAE decode)",
+            "value": round(value, 6), "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(per_image * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"SDXL base txt2img 1024x1024, {steps}-step DPM++ 2M, CFG {SDXL_CFG_SCALE}, random-init "
+                                   f"weights, + decode ({args.workload}); CPU, bounded sample at batch 1"},
+            "cpu_baseline": {"value": round(value, 6), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 6), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -436,6 +581,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ddim50_b8", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the additional 20-step Euler-a measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -204,6 +204,8 @@ class BasicTransformerBlock(PackedModule):
 
 
 class SpatialTransformer(PackedModule):
+    _HONOR_USE_LINEAR = False  # the ldm class ignores `use_linear`; the sgm mirror (SDXL) honours it
+
     """attention.py:915-1057. GroupNorm(eps 1e-6) -> 1x1 proj_in -> transformer blocks on [b, hw, c] -> 1x1 proj_out
     -> + x_in.  In NHWC the two rearranges are free and the 1x1 convs are plain GEMMs. `use_linear` is accepted and
     ignored exactly like the reference (docstring at attention.py:930-945)."""
@@ -221,12 +223,19 @@ class SpatialTransformer(PackedModule):
         inner_dim = n_heads * d_head
         self.inner_dim = inner_dim
         self.norm = Normalize(in_channels)
-        self.proj_in = nn.Conv2d(in_channels, inner_dim, kernel_size=1, stride=1, padding=0)
+        self.use_linear = bool(use_linear) and self._HONOR_USE_LINEAR
+        if self.use_linear:  # sgm/modules/attention.py:999,1056: nn.Linear on the [b, hw, c] view -- the same GEMM
+            self.proj_in = nn.Linear(in_channels, inner_dim)
+        else:
+            self.proj_in = nn.Conv2d(in_channels, inner_dim, kernel_size=1, stride=1, padding=0)
         self.transformer_blocks = nn.ModuleList([
             BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim[d],
                                   disable_self_attn=disable_self_attn, checkpoint=use_checkpoint)
             for d in range(depth)])
-        self.proj_out = nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0)
+        if self.use_linear:
+            self.proj_out = nn.Linear(inner_dim, in_channels)
+        else:
+            self.proj_out = nn.Conv2d(inner_dim, in_channels, kernel_size=1, stride=1, padding=0)
         with torch.no_grad():  # zero_module, attention.py:1002
             self.proj_out.weight.zero_()
             self.proj_out.bias.zero_()

@@ -221,7 +221,13 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
 
 
 class UNetModel(PackedModule):
-    """openaimodel.py:417-816 -- the full UNet with attention and timestep embedding."""
+    """openaimodel.py:417-816 -- the full UNet with attention and timestep embedding.
+
+    Also the implementation behind the sgm (SDXL) mirror `cremage_b200.sgm...openaimodel.UNetModel`, which adds
+    per-level `transformer_depth`, honoured `use_linear_in_transformer` and the `num_classes="sequential"` vector
+    conditioning `y` (sgm/modules/diffusionmodules/openaimodel.py:506-534,617-625,828-874)."""
+
+    _ST_CLS = SpatialTransformer
 
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
@@ -230,7 +236,7 @@ class UNetModel(PackedModule):
                  use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True,
                  disable_self_attentions=None, num_attention_blocks=None, disable_middle_self_attn=False,
                  use_linear_in_transformer=False, lora_ranks: List[int] = None, lora_weights: List[float] = None,
-                 ipa_scale=1.0, ipa_num_tokens=0):
+                 ipa_scale=1.0, ipa_num_tokens=0, adm_in_channels=None):
         super().__init__()
         if use_spatial_transformer:
             assert context_dim is not None, "context_dim is required with use_spatial_transformer"
@@ -244,8 +250,15 @@ class UNetModel(PackedModule):
         if dims != 2 or use_scale_shift_norm or resblock_updown or n_embed is not None or not conv_resample:
             raise NotImplementedError("cremage_b200: dims!=2 / use_scale_shift_norm / resblock_updown / n_embed / "
                                       "conv_resample=False are not implemented")
-        if num_classes is not None:
-            raise NotImplementedError("cremage_b200: class-conditional ldm UNet (num_classes) is not implemented")
+        if num_classes is not None and num_classes != "sequential":
+            raise NotImplementedError("cremage_b200: only num_classes=None or 'sequential' (SDXL vector conditioning) "
+                                      "is implemented")
+        if num_classes == "sequential":
+            assert adm_in_channels is not None, "num_classes='sequential' needs adm_in_channels"
+        if isinstance(transformer_depth, int):
+            transformer_depth = len(channel_mult) * [transformer_depth]
+        transformer_depth = list(transformer_depth)
+        assert len(transformer_depth) == len(channel_mult), "transformer_depth must be an int or one entry per level"
         if lora_ranks:
             raise NotImplementedError("cremage_b200: merge LoRA weights before loading (lora_ranks must be empty)")
         if ipa_num_tokens:
@@ -285,10 +298,10 @@ class UNetModel(PackedModule):
         self.predict_codebook_ids = False
         self.context_dim = context_dim
 
-        def make_st(ch, heads, dim_head, disabled_sa=False):
-            return SpatialTransformer(ch, heads, dim_head, depth=transformer_depth, context_dim=context_dim,
-                                      disable_self_attn=disabled_sa, use_linear=use_linear_in_transformer,
-                                      use_checkpoint=use_checkpoint)
+        def make_st(ch, heads, dim_head, depth, disabled_sa=False):
+            return self._ST_CLS(ch, heads, dim_head, depth=depth, context_dim=context_dim,
+                                disable_self_attn=disabled_sa, use_linear=use_linear_in_transformer,
+                                use_checkpoint=use_checkpoint)
 
         def head_cfg(ch, heads):
             if num_head_channels == -1:
@@ -303,6 +316,10 @@ class UNetModel(PackedModule):
         time_embed_dim = model_channels * 4
         self.time_embed = nn.Sequential(linear(model_channels, time_embed_dim), nn.SiLU(),
                                         linear(time_embed_dim, time_embed_dim))
+        if num_classes == "sequential":  # sgm openaimodel.py:617-625
+            self.adm_in_channels = adm_in_channels
+            self.label_emb = nn.Sequential(nn.Sequential(linear(adm_in_channels, time_embed_dim), nn.SiLU(),
+                                                         linear(time_embed_dim, time_embed_dim)))
         self.input_blocks = nn.ModuleList(
             [TimestepEmbedSequential(conv_nd(dims, in_channels, model_channels, 3, padding=1))])
         self._feature_size = model_channels
@@ -318,7 +335,7 @@ class UNetModel(PackedModule):
                     heads, dim_head = head_cfg(ch, num_heads)
                     disabled_sa = disable_self_attentions[level] if disable_self_attentions is not None else False
                     if num_attention_blocks is None or nr < num_attention_blocks[level]:
-                        layers.append(make_st(ch, heads, dim_head, disabled_sa))
+                        layers.append(make_st(ch, heads, dim_head, transformer_depth[level], disabled_sa))
                 self.input_blocks.append(TimestepEmbedSequential(*layers))
                 self._feature_size += ch
                 input_block_chans.append(ch)
@@ -334,7 +351,7 @@ class UNetModel(PackedModule):
         heads, dim_head = head_cfg(ch, num_heads)
         self.middle_block = TimestepEmbedSequential(
             ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint),
-            make_st(ch, heads, dim_head, disable_middle_self_attn),
+            make_st(ch, heads, dim_head, transformer_depth[-1], disable_middle_self_attn),
             ResBlock(ch, time_embed_dim, dropout, dims=dims, use_checkpoint=use_checkpoint))
         self._feature_size += ch
 
@@ -349,7 +366,7 @@ class UNetModel(PackedModule):
                     heads, dim_head = head_cfg(ch, num_heads_upsample)
                     disabled_sa = disable_self_attentions[level] if disable_self_attentions is not None else False
                     if num_attention_blocks is None or i < num_attention_blocks[level]:
-                        layers.append(make_st(ch, heads, dim_head, disabled_sa))
+                        layers.append(make_st(ch, heads, dim_head, transformer_depth[level], disabled_sa))
                 if level and i == self.num_res_blocks[level]:
                     out_ch = ch
                     layers.append(Upsample(ch, conv_resample, dims=dims, out_channels=out_ch))
@@ -374,6 +391,8 @@ class UNetModel(PackedModule):
     # -- packing -------------------------------------------------------------------------------------------------
     def _own_params(self):
         ps = list(self.time_embed.parameters()) + list(self.input_blocks[0].parameters()) + list(self.out.parameters())
+        if self.num_classes is not None:
+            ps += list(self.label_emb.parameters())
         for rb in self._res_blocks:
             ps += list(rb.emb_layers.parameters())
         return ps
@@ -385,7 +404,13 @@ class UNetModel(PackedModule):
                           for rb in self._res_blocks], 0)
         embb = torch.cat([rb.emb_layers[1].bias.detach().to(device=device, dtype=torch.float32)
                           for rb in self._res_blocks], 0)
+        extra = {}
+        if self.num_classes is not None:
+            le = self.label_emb[0]
+            extra = {"le0w": packw(le[0].weight, device), "le0b": f32(le[0].bias, device),
+                     "le2w": packw(le[2].weight, device), "le2b": f32(le[2].bias, device)}
         return {
+            **extra,
             "freqs": timestep_freqs(self.model_channels).to(device),
             "te0w": packw(self.time_embed[0].weight, device), "te0b": f32(self.time_embed[0].bias, device),
             "te2w": packw(self.time_embed[2].weight, device), "te2b": f32(self.time_embed[2].bias, device),
@@ -397,7 +422,7 @@ class UNetModel(PackedModule):
         }
 
     # -- forward -------------------------------------------------------------------------------------------------
-    def _forward_impl(self, x: torch.Tensor, t: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+    def _forward_impl(self, x: torch.Tensor, t: torch.Tensor, context: torch.Tensor, y: torch.Tensor = None) -> torch.Tensor:
         dev = x.device
         p = self.packed(dev)
         n, c, hh, ww = x.shape
@@ -405,7 +430,13 @@ class UNetModel(PackedModule):
         # timestep embedding -> time_embed MLP (SiLU fused) -> all per-block projections in one GEMM
         temb = ops.timestep_embedding(t, mc, p["freqs"])
         e = ops.igemm(temb, p["te0w"], ted, bias=p["te0b"], act=ops.ACT_SILU)
-        semb = ops.igemm(e, p["te2w"], ted, bias=p["te2b"], act=ops.ACT_SILU)  # silu(emb): every consumer applies SiLU first
+        if self.num_classes is None:
+            semb = ops.igemm(e, p["te2w"], ted, bias=p["te2b"], act=ops.ACT_SILU)  # silu(emb): every consumer applies SiLU first
+        else:  # emb = time_embed(t_emb) + label_emb(y)   (sgm openaimodel.py:851-859), then the shared SiLU
+            emb_t = ops.igemm(e, p["te2w"], ted, bias=p["te2b"])
+            l0 = ops.igemm(y.to(ACT).contiguous(), p["le0w"], ted, bias=p["le0b"], act=ops.ACT_SILU)
+            emb = ops.igemm(l0, p["le2w"], ted, bias=p["le2b"], residual=emb_t)
+            semb = ops.silu_add(emb)
         emb_all = ops.igemm(semb, p["embw"], self._emb_total, bias=p["embb"], out_f32=True)
         nk = context.shape[1]
         ctx2d = context.reshape(n * nk, context.shape[-1]).to(ACT).contiguous()
@@ -433,18 +464,21 @@ class UNetModel(PackedModule):
             raise ValueError("UNetModel.forward needs timesteps and context")
         if x.shape[0] != timesteps.shape[0] or x.shape[0] != context.shape[0]:
             raise ValueError("batch sizes of x, timesteps and context differ")
+        if y is not None:
+            assert y.shape[0] == x.shape[0] and y.shape[1] == self.adm_in_channels, "bad vector conditioning shape"
         if x.shape[2] % (2 ** (len(self.channel_mult) - 1)) or x.shape[3] % (2 ** (len(self.channel_mult) - 1)):
             raise ValueError("latent height/width must be divisible by the total downsampling factor")
         t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
         ctx = context.to(device=x.device)
         xin = x.contiguous()
+        extra = () if y is None else (y.to(device=x.device).contiguous(),)
         if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
             if self._graphed is None:
                 self._graphed = GraphedCall(self._forward_impl)
             self.packed(x.device)  # refresh packs (and drop stale graphs) if parameters changed
-            out = self._graphed(xin, t, ctx)
+            out = self._graphed(xin, t, ctx, *extra)
         else:
-            out = self._forward_impl(xin, t, ctx)
+            out = self._forward_impl(xin, t, ctx, *extra)
         return out.to(x.dtype)
 
     def packed(self, device):

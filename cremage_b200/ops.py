@@ -57,8 +57,20 @@ class LaunchProfile:
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, flops, nbytes, e0, e1 in self.records:
+        for name, flops, nbytes, e0, e1, _tag in self.records:
             d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+    def by_shape(self):
+        """Per (kernel, shape tag): launches, total ms, algorithmic flops / bytes -- the per-shape time budget."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, nbytes, e0, e1, tag in self.records:
+            d = out.setdefault((name, tag), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += flops
@@ -69,7 +81,7 @@ class LaunchProfile:
 _PROF: Optional[LaunchProfile] = None
 
 
-def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0) -> None:
+def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0, tag: str = "") -> None:
     if _PROF is None:
         check(fn(), name)
         return
@@ -78,7 +90,7 @@ def _launch(name: str, fn, flops: float = 0.0, nbytes: float = 0.0) -> None:
     e0.record()
     check(fn(), name)
     e1.record()
-    _PROF.records.append((name, flops, nbytes, e0, e1))
+    _PROF.records.append((name, flops, nbytes, e0, e1, tag))
 
 
 def ceil64(c: int) -> int:
@@ -244,7 +256,10 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     d.bn, d.stages = bn, stages
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
-            flops=2.0 * rows * len(dw) * (c0 + c1) * ncols)
+            flops=2.0 * rows * len(dw) * (c0 + c1) * ncols,
+            tag=f"M={rows} K={len(dw) * (c0 + c1)} N={ncols} taps={len(dw)} bn={bn} epi={mode}"
+                f"{'+res' if residual is not None else ''}{'+rowb' if rowbias is not None else ''}"
+                f"{'+act' if act else ''}{'+f32' if out_f32 else ''}" if _PROF is not None else "")
     return out
 
 
@@ -258,7 +273,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, hea
     if out is None:
         out = torch.empty((batch * nq, heads * d), dtype=ACT, device=q.device)
     _launch("cb_attention", lambda: _lib.load().cb_attention(_p(q), _p(k), _p(v), _p(out), batch, heads, nq, nk, d, dpad, scale, _stream()),
-            flops=4.0 * batch * heads * nq * nk * d)
+            flops=4.0 * batch * heads * nq * nk * d, tag=f"bh={batch * heads} nq={nq} nk={nk} d={d}")
     return out
 
 
@@ -306,7 +321,8 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     stats = torch.empty((ws // 4,), dtype=torch.float32, device=x0.device)
     _launch("cb_groupnorm_nhwc", lambda: _lib.load().cb_groupnorm_nhwc(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(gamma), _p(beta), int(silu),
                                         _p(out), _p(stats), _stream()),
-            nbytes=4.0 * n * hw * (c0 + c1))  # algorithmic: one bf16 read + one bf16 write per element
+            nbytes=4.0 * n * hw * (c0 + c1),  # algorithmic: one bf16 read + one bf16 write per element
+            tag=f"n={n} hw={hw} c={c0}+{c1}")
     return out
 
 
@@ -317,7 +333,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     rows = x.numel() // c
     out = torch.empty_like(x)
     _launch("cb_layernorm", lambda: _lib.load().cb_layernorm(_p(x), rows, c, eps, _p(gamma), _p(beta), _p(out), _stream()),
-            nbytes=4.0 * rows * c)
+            nbytes=4.0 * rows * c, tag=f"rows={rows} c={c}")
     return out
 
 
