@@ -62,8 +62,9 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // Encode a tiled act_t (fp16 / bf16) tensor map (rank 2..5), SWIZZLE_128B, zero OOB fill.
 // dims / strides are in ELEMENTS (strides[0] is implied = 1); box in elements.
+// swizzle_bytes: 128 (operand tiles, 64-element inner box) or 64 (epilogue panels, 32-element inner box).
 int make_tmap_act(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_elems, const uint32_t* box);
+                   const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes = 128);
 
 // ----------------------------------------------------------------------------------------------
 // small device utilities
@@ -138,6 +139,18 @@ CB_DEVINL void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+
+// TMA store (tile mode) shared -> global, bulk-group completion
+CB_DEVINL void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+CB_DEVINL void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+CB_DEVINL void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA reads of a tile written with st.shared)
 CB_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -253,6 +266,23 @@ CB_DEVINL float from_act(act_t x) { return __bfloat162float(x); }
 #endif
 CB_DEVINL float silu_f(float x) { return x / (1.f + __expf(-x)); }
 CB_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the 16-bit output rounding): one MUFU.RCP, one
+// MUFU.EX2 and 8 FMA-pipe instructions instead of libdevice erff's two-branch polynomial -- the GEGLU epilogue applies
+// it to 84 M elements per top-level feed-forward.
+CB_DEVINL float gelu_fast_f(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  const float erf_abs = fmaf(-p * t, e, 1.f);             // erf(|x|/sqrt2)
+  const float hx = 0.5f * x;
+  return fmaf(copysignf(erf_abs, x), hx, hx);              // 0.5 x (1 + erf)
+}
 
 CB_DEVINL float warp_sum(float v) {
 #pragma unroll

@@ -13,8 +13,14 @@
 //   removes the weight re-reads that otherwise make K <= 640 shapes L2-bandwidth bound.
 // * tcgen05.mma (cta_group::1, M=128, N=BN, K=16) issued by one thread; TWO fp32 accumulators in TMEM.
 // * Persistent: one CTA per SM loops over tiles.  Warp roles: warp0 = TMA producer (runs ahead across tile
-//   boundaries), warp1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue (tcgen05.ld -> bias / per-image bias /
-//   SiLU / residual / GEGLU / per-head scatter -> global) draining accumulator i while the MMAs fill i+1.
+//   boundaries), warp1 = TMEM alloc + MMA issuer, warps 2..9 = epilogue (two warps per TMEM lane quarter, each
+//   taking alternate 32-column chunks) draining accumulator i while the MMAs fill i+1.
+// * Epilogue, two forms.  DIRECT: tcgen05.ld -> bias / per-image bias / SiLU / residual / per-head scatter ->
+//   16-byte global stores from the thread that owns the row (large-K convs, where the epilogue hides under the
+//   next tile's MMAs, and the ragged / fp32 / per-head outputs).  STAGED (small K, where the epilogue IS the
+//   kernel): the residual panel of every chunk is prefetched by TMA into a 64B-swizzled shared-memory panel
+//   while the tile's MMAs run, the thread adds it in place and the panel leaves by TMA store (bulk, asynchronous,
+//   full-sector writes; rows / columns outside the tensor are clipped by the tensor map).
 #include "common.cuh"
 #include "cremage_b200.h"
 
@@ -23,7 +29,9 @@ namespace cb {
 constexpr int BM = 128;          // rows per tile (UMMA M)
 constexpr int BK = 64;           // K elements per pipeline stage (= one 128-byte swizzle row)
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // 320
+constexpr int PANEL_BYTES = 32 * 32 * 2;           // one staged epilogue panel: 32 rows x 32 columns, 16-bit
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct IGemmKParams {
@@ -55,6 +63,8 @@ struct IGemmKParams {
   // heads mode
   int hd, hdpad, hheads, htokens;
   long long hwhich_stride;
+  // staged epilogue: panels per epilogue warp, and the pixel box {pbw, pbh, 32 / (pbw * pbh)} of a warp's 32 rows
+  int npan, pbw, pbh;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == CB_ACT_SILU ? silu_f(v) : v; }
@@ -176,74 +186,96 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmKParams& p, const uint
   }
 }
 
-// epilogue of one 128 x bn accumulator tile (thread = one row); `trow` = TMEM address of this thread's lane, column 0
+// DIRECT epilogue of this warp's share of one 128 x bn accumulator tile (thread = one row): chunks hh, hh+2, ...
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const IGemmKParams& p, uint32_t trow, const float* __restrict__ sbias,
-                                              int nt, int n, bool row_ok, long long row) {
-  if (EPI == EPI_GEGLU) {
-    // tile columns [0, bn/2) hold x, [bn/2, bn) hold the gate (weights were interleaved per tile on the host)
-    const int half = p.bn >> 1;
-    for (int c = 0; c < half; c += 32) {
-      uint32_t xv[32], gv[32];
-      tmem_ld32(trow + uint32_t(c), xv);
-      tmem_ld32(trow + uint32_t(half + c), gv);
-      tmem_ld_wait();
-      if (row_ok) {
-        const int ocol0 = nt * half + c;  // output column
-        act_t* optr = reinterpret_cast<act_t*>(p.out) + row * p.out_ld + ocol0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (ocol0 + j < p.cout) {  // cout here = number of OUTPUT columns (inner dim), multiple of 8
-            uint32_t packed[4];
-            const float4 bx0 = *reinterpret_cast<const float4*>(sbias + c + j);
-            const float4 bx1 = *reinterpret_cast<const float4*>(sbias + c + j + 4);
-            const float4 bg0 = *reinterpret_cast<const float4*>(sbias + half + c + j);
-            const float4 bg1 = *reinterpret_cast<const float4*>(sbias + half + c + j + 4);
-            const float bx[8] = {bx0.x, bx0.y, bx0.z, bx0.w, bx1.x, bx1.y, bx1.z, bx1.w};
-            const float bg[8] = {bg0.x, bg0.y, bg0.z, bg0.w, bg1.x, bg1.y, bg1.z, bg1.w};
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              const float x0 = __uint_as_float(xv[j + e]) + bx[e];
-              const float x1 = __uint_as_float(xv[j + e + 1]) + bx[e + 1];
-              const float g0 = __uint_as_float(gv[j + e]) + bg[e];
-              const float g1 = __uint_as_float(gv[j + e + 1]) + bg[e + 1];
-              packed[e >> 1] = pack_act2(x0 * gelu_erf_f(g0), x1 * gelu_erf_f(g1));
-            }
-            *reinterpret_cast<uint4*>(optr + j) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-          }
-        }
-      }
-    }
-    return;
-  }
-  // two register buffers: the TMEM load of chunk c+32 is in flight while chunk c is converted and stored
-  uint32_t va[32], vb[32];
-  tmem_ld32(trow, va);
-  for (int c = 0; c < p.bn; c += 64) {
+__device__ __forceinline__ void epilogue_tile_direct(const IGemmKParams& p, uint32_t trow, const float* __restrict__ sbias,
+                                                     int nt, int n, bool row_ok, long long row, int hh) {
+  for (int c = hh * 32; c < p.bn; c += 64) {
+    if (nt * p.bn + c >= p.cout) break;
+    uint32_t v[32];
+    tmem_ld32(trow + uint32_t(c), v);
     tmem_ld_wait();
-    const bool more_b = (c + 32 < p.bn);
-    if (more_b) tmem_ld32(trow + uint32_t(c + 32), vb);
-    if (row_ok) epilogue_chunk<EPI>(p, va, sbias, nt, c, n, row);
-    if (more_b) {
-      tmem_ld_wait();
-      if (c + 64 < p.bn) tmem_ld32(trow + uint32_t(c + 64), va);
-      if (row_ok) epilogue_chunk<EPI>(p, vb, sbias, nt, c + 32, n, row);
-    }
+    if (row_ok) epilogue_chunk<EPI>(p, v, sbias, nt, c, n, row);
   }
 }
 
+CB_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+CB_DEVINL uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+
+// STAGED epilogue of one 32-column chunk: registers (+bias, +per-image bias, +residual read from the panel) -> the
+// 64B-swizzled panel (row = lane, 16-byte piece j at  j ^ ((lane >> 1) & 3)), ready for the TMA store.
 template <int EPI>
+__device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32_t (&v)[32], const uint32_t (&g)[32],
+                                             const float* __restrict__ sbx, const float* __restrict__ sbg,
+                                             const float* __restrict__ rowb, bool rowb_ok, int col0, uint32_t panel, int lane) {
+  const uint32_t rowaddr = panel + uint32_t(lane) * 64u;
+  const uint32_t sw = uint32_t(lane >> 1) & 3u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float f[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(sbx + 8 * j);
+    const float4 b1 = *reinterpret_cast<const float4*>(sbx + 8 * j + 4);
+    f[0] = __uint_as_float(v[8 * j + 0]) + b0.x; f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
+    f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
+    f[4] = __uint_as_float(v[8 * j + 4]) + b1.x; f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
+    f[6] = __uint_as_float(v[8 * j + 6]) + b1.z; f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+    const uint32_t addr = rowaddr + ((uint32_t(j) ^ sw) << 4);
+    if (EPI == EPI_GEGLU) {
+      const float4 g0 = *reinterpret_cast<const float4*>(sbg + 8 * j);
+      const float4 g1 = *reinterpret_cast<const float4*>(sbg + 8 * j + 4);
+      const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(__uint_as_float(g[8 * j + e]) + gb[e]);
+    }
+    if (EPI == EPI_ROWBIAS) {
+      if (rowb_ok && col0 + 8 * j + 8 <= p.cout) {
+        const float* rb = rowb + col0 + 8 * j;
+        if (p.rowbias_vec) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(rb));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+          f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+          f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += __ldg(rb + e);
+        }
+      }
+    }
+    if (EPI == EPI_RES) {
+      const uint4 rv = ld_shared_v4(addr);
+      const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack_act2(ru[e]);
+        f[2 * e] += t.x;
+        f[2 * e + 1] += t.y;
+      }
+    }
+    st_shared_v4(addr, pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+  }
+}
+
+template <int EPI, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-             const __grid_constant__ CUtensorMap mapB, const IGemmKParams p) {
+             const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
+             const __grid_constant__ CUtensorMap mapR, const IGemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve (1024-aligned): [resident B: num_k x bn*128] [ring: stages x (A 16K [+ B bn*128])] [barriers] [bias x2]
+  // carve (1024-aligned): [resident B: num_k x bn*128] [ring: stages x (A 16K [+ B bn*128])]
+  //                       [staging: EPI_WARPS x npan x 2K] [barriers] [bias x2]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_chunk_bytes = uint32_t(p.bn) * 128u;
   const uint32_t res_bytes = p.resident_b ? uint32_t(p.num_k) * b_chunk_bytes : 0u;
   const uint32_t stage_bytes = A_STAGE_BYTES + (p.resident_b ? 0u : b_chunk_bytes);
   const uint32_t ring_base = smem_base + res_bytes;
-  const uint32_t bar_base = ring_base + uint32_t(p.stages) * stage_bytes;
+  const uint32_t stg_base = ring_base + uint32_t(p.stages) * stage_bytes;
+  const uint32_t bar_base = stg_base + (STAGED ? uint32_t(EPI_WARPS * p.npan) * PANEL_BYTES : 0u);
   auto full_bar = [&](int s) { return bar_base + 8u * uint32_t(s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * uint32_t(p.stages + s); };
   const uint32_t misc = bar_base + 16u * uint32_t(p.stages);
@@ -251,7 +283,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   auto acc_empty = [&](int b) { return misc + 16u + 8u * uint32_t(b); };
   const uint32_t bres_bar = misc + 32u;
   const uint32_t tmem_slot = misc + 40u;
-  const uint32_t bias_smem = (misc + 48u + 15u) & ~15u;  // float[2][256]: the tile's bias slice, double buffered
+  auto resid_bar = [&](int ew) { return misc + 48u + 8u * uint32_t(ew); };
+  const uint32_t bias_smem = (misc + 48u + 8u * EPI_WARPS + 15u) & ~15u;  // float[2][256]: the tile's bias slice, double buffered
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -263,15 +296,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     tma_prefetch_desc(&mapA0);
     if (p.chunks1 > 0) tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
+    if (STAGED) {
+      tma_prefetch_desc(&mapO);
+      if (EPI == EPI_RES) tma_prefetch_desc(&mapR);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 128);
+      mbar_init(acc_empty(b), 32 * EPI_WARPS);
     }
     mbar_init(bres_bar, 1);
+    for (int e = 0; e < EPI_WARPS; ++e) mbar_init(resid_bar(e), 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -350,13 +388,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
     const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int hh = ew >> 2;             // which alternate 32-column chunks this warp takes
     const int r = q * 32 + lane;        // row of the tile
     const int rn = r / (p.TW * p.TH);
     const int rh = (r / p.TW) % p.TH;
     const int rw = r % p.TW;
+    // origin of this warp's 32-row pixel box inside the tile (staged form)
+    const int r0 = q * 32;
+    const int bw0 = r0 % p.TW, bh0 = (r0 / p.TW) % p.TH, bn0 = r0 / (p.TW * p.TH);
+    const uint32_t my_stg = stg_base + uint32_t(ew * p.npan) * PANEL_BYTES;
+    uint32_t rphase = 0;
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
+    constexpr bool GEGLU = (EPI == EPI_GEGLU);
+    const int ocols = GEGLU ? (p.bn >> 1) : p.bn;   // output columns per tile
     int mt, nt;
     for (int i = 0; sched.get(i, mt, nt); ++i) {
       const int buf = i & 1;
@@ -367,22 +414,62 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const int n = tn * p.TN + rn, h = th * p.TH + rh, w = tw * p.TW + rw;
       const bool row_ok = (n < p.n_img) && (h < p.H) && (w < p.W);
       const long long row = (static_cast<long long>(n) * p.H + h) * p.W + w;
+      const int bxw = tw * p.TW + bw0, bxh = th * p.TH + bh0, bxn = tn * p.TN + bn0;
+      if (STAGED) {
+        // the previous tile's TMA stores have finished reading this warp's panels
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        if (EPI == EPI_RES && lane == 0) {
+          int cnt = 0;
+          for (int c = hh * 32; c < ocols && nt * ocols + c < p.cout; c += 64) ++cnt;
+          if (cnt > 0) {
+            mbar_expect_tx(resid_bar(ew), uint32_t(cnt) * PANEL_BYTES);
+            int k = 0;
+            for (int c = hh * 32; c < ocols && nt * ocols + c < p.cout; c += 64, ++k)
+              tma_load_4d(my_stg + uint32_t(k) * PANEL_BYTES, &mapR, resid_bar(ew), nt * ocols + c, bxw, bxh, bxn);
+          }
+        }
+      }
       // stage this tile's bias slice (overlaps the MMAs of this tile); the named barrier also orders the reuse of
       // the slot against the slowest warp's reads two tiles ago
       float* sb = sbias_all + buf * 256;
-      for (int c = threadIdx.x - 64; c < p.bn; c += 128) {
+      for (int c = threadIdx.x - 64; c < p.bn; c += 32 * EPI_WARPS) {
         const int bc = nt * p.bn + c;
         sb[c] = (p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
 
       mbar_wait(acc_full(buf), use & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + uint32_t(buf) * p.acc_stride + (uint32_t(q * 32) << 16);
-      epilogue_tile<EPI>(p, trow, sb, nt, n, row_ok, row);
+      if (STAGED) {
+        const bool have = (hh * 32 < ocols) && (nt * ocols + hh * 32 < p.cout);
+        if (EPI == EPI_RES && have) { mbar_wait(resid_bar(ew), rphase); rphase ^= 1u; }
+        const float* rowb = (EPI == EPI_ROWBIAS) ? (p.rowbias + static_cast<long long>(n < p.n_img ? n : 0) * p.rowbias_ld) : nullptr;
+        int k = 0;
+        for (int c = hh * 32; c < ocols; c += 64, ++k) {
+          const int col0 = nt * ocols + c;
+          if (col0 >= p.cout) break;
+          uint32_t v[32], g[32];
+          tmem_ld32(trow + uint32_t(c), v);
+          if (GEGLU) tmem_ld32(trow + uint32_t(ocols + c), g);
+          tmem_ld_wait();
+          const uint32_t panel = my_stg + uint32_t(k) * PANEL_BYTES;
+          staged_chunk<EPI>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&mapO, panel, col0, bxw, bxh, bxn);
+            tma_store_commit();
+          }
+        }
+      } else {
+        epilogue_tile_direct<EPI>(p, trow, sb, nt, n, row_ok, row, hh);
+      }
       tc_fence_before();
-      mbar_arrive(acc_empty(buf));   // 128 arrivals: every epilogue thread has drained its TMEM lanes
+      mbar_arrive(acc_empty(buf));   // 256 arrivals: every epilogue thread has drained its TMEM lanes
     }
+    if (STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -482,39 +569,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.hd = d->heads_d; p.hdpad = d->heads_dpad; p.hheads = d->heads_h; p.htokens = d->heads_tokens;
   p.hwhich_stride = d->heads_which_stride;
 
-  // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
-  //      that N tile gets several M tiles; otherwise stream A and B through the ring
-  const size_t fixed = 1024 + 16 * 12 + 64 + sizeof(float) * 512 + 64;
-  const size_t b_chunk = (size_t)d->bn * 128;
-  const size_t res_bytes = (size_t)num_k * b_chunk;
-  int resident = 0;
-  unsigned grid = 0;
-  if (d->stages <= 0 && p.n_tiles <= g_num_sms && res_bytes + 4 * (size_t)A_STAGE_BYTES + fixed <= (size_t)SMEM_LIMIT) {
-    const int ctas_per_nt = g_num_sms / p.n_tiles;
-    if (ctas_per_nt >= 1 && p.m_tiles >= 3 * ctas_per_nt) {
-      resident = 1;
-      grid = (unsigned)(ctas_per_nt * p.n_tiles);
-      p.m_step = ctas_per_nt;
-    }
-  }
-  p.resident_b = resident;
-  const size_t stage_bytes = A_STAGE_BYTES + (resident ? 0 : b_chunk);
-  int stages = d->stages;
-  if (stages <= 0) {
-    stages = int(((size_t)SMEM_LIMIT - fixed - (resident ? res_bytes : 0)) / stage_bytes);
-    if (stages > 8) stages = 8;
-  }
-  CB_REQUIRE(stages >= 2 && stages <= 12, "cb_igemm: %d pipeline stages do not fit / out of range", stages);
-  p.stages = stages;
-  const size_t smem = 1024 + (resident ? res_bytes : 0) + (size_t)stages * stage_bytes + 16 * (size_t)stages + 64 +
-                      sizeof(float) * 512 + 64;
-  CB_REQUIRE(smem <= (size_t)SMEM_LIMIT, "cb_igemm: tile needs %zu bytes of shared memory", smem);
-  if (!resident) {
-    const long long total = (long long)p.m_tiles * p.n_tiles;
-    grid = (unsigned)(total < g_num_sms ? total : g_num_sms);
-  }
-
-  // epilogue specialisation
+  // ---- epilogue specialisation
   int epi = EPI_GENERIC;
   const bool simple16 = !d->out_f32 && d->act == CB_ACT_NONE && p.out_scale == 1.f && d->cout % 8 == 0;
   if (d->mode == CB_EPI_GEGLU) epi = EPI_GEGLU;
@@ -526,16 +581,87 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   }
   CB_REQUIRE(d->mode != CB_EPI_HEADS || epi == EPI_HEADS, "cb_igemm: the heads epilogue takes bias only (no activation / residual / row bias / scale)");
 
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IGemmKParams);
-  static const KernelFn kernels[EPI_COUNT] = {igemm_kernel<EPI_GENERIC>, igemm_kernel<EPI_PLAIN>, igemm_kernel<EPI_RES>,
-                                              igemm_kernel<EPI_ROWBIAS>, igemm_kernel<EPI_GEGLU>, igemm_kernel<EPI_HEADS>};
+  // staged (TMA in / TMA out) epilogue: the small-K launches whose run time IS the epilogue; large-K convs keep the
+  // direct form (their epilogue hides under the next tile's MMAs and the ring keeps its depth)
+  const bool tma_ok = (d->out_ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->out) & 15u) == 0) &&
+                      (!d->residual || (d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15u) == 0));
+  bool staged = false;
+  if (epi == EPI_GEGLU) {
+    CB_REQUIRE(tma_ok, "cb_igemm: the GEGLU epilogue needs a 16-byte aligned output with out_ld %% 8 == 0");
+    staged = true;
+  } else if (epi == EPI_PLAIN || epi == EPI_RES || epi == EPI_ROWBIAS) {
+    staged = tma_ok && (d->epilogue == CB_EPILOGUE_STAGED || (d->epilogue == CB_EPILOGUE_AUTO && num_k <= 48));
+  }
+  const int ocols = (epi == EPI_GEGLU) ? d->bn / 2 : d->bn;
+  p.npan = staged ? (ocols + 63) / 64 : 0;
+  p.pbw = d->tw < 32 ? d->tw : 32;
+  p.pbh = d->th < 32 / p.pbw ? d->th : 32 / p.pbw;
+  const size_t staging = (size_t)EPI_WARPS * p.npan * PANEL_BYTES;
+
+  CUtensorMap mapO = mapA0, mapR = mapA0;
+  if (staged) {
+    uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+    uint64_t str[4] = {1, (uint64_t)d->out_ld, (uint64_t)d->out_ld * d->w, (uint64_t)d->out_ld * d->w * d->h};
+    uint32_t box[4] = {32, (uint32_t)p.pbw, (uint32_t)p.pbh, (uint32_t)(32 / (p.pbw * p.pbh))};
+    int rc = make_tmap_act(&mapO, d->out, 4, dims, str, box, 64);
+    if (rc) return rc;
+    if (epi == EPI_RES) {
+      uint64_t rstr[4] = {1, (uint64_t)d->res_ld, (uint64_t)d->res_ld * d->w, (uint64_t)d->res_ld * d->w * d->h};
+      rc = make_tmap_act(&mapR, d->residual, 4, dims, rstr, box, 64);
+      if (rc) return rc;
+    }
+  }
+
+  // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
+  //      that N tile gets several M tiles; otherwise stream A and B through the ring
+  const size_t fixed = 1024 + 16 * 12 + 128 + 16 + sizeof(float) * 512 + 64;
+  const size_t b_chunk = (size_t)d->bn * 128;
+  const size_t res_bytes = (size_t)num_k * b_chunk;
+  int resident = 0;
+  unsigned grid = 0;
+  if (d->stages <= 0 && p.n_tiles <= g_num_sms &&
+      res_bytes + 4 * (size_t)A_STAGE_BYTES + staging + fixed <= (size_t)SMEM_LIMIT) {
+    const int ctas_per_nt = g_num_sms / p.n_tiles;
+    if (ctas_per_nt >= 1 && p.m_tiles >= 3 * ctas_per_nt) {
+      resident = 1;
+      grid = (unsigned)(ctas_per_nt * p.n_tiles);
+      p.m_step = ctas_per_nt;
+    }
+  }
+  p.resident_b = resident;
+  const size_t stage_bytes = A_STAGE_BYTES + (resident ? 0 : b_chunk);
+  int stages = d->stages;
+  if (stages <= 0) {
+    stages = int(((size_t)SMEM_LIMIT - fixed - staging - (resident ? res_bytes : 0)) / stage_bytes);
+    if (stages > 8) stages = 8;
+  }
+  CB_REQUIRE(stages >= 2 && stages <= 12, "cb_igemm: %d pipeline stages do not fit / out of range", stages);
+  p.stages = stages;
+  const size_t smem = (resident ? res_bytes : 0) + (size_t)stages * stage_bytes + staging + fixed;
+  CB_REQUIRE(smem <= (size_t)SMEM_LIMIT, "cb_igemm: tile needs %zu bytes of shared memory", smem);
+  if (!resident) {
+    const long long total = (long long)p.m_tiles * p.n_tiles;
+    grid = (unsigned)(total < g_num_sms ? total : g_num_sms);
+  }
+
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const IGemmKParams);
+  static const KernelFn kernels[2][EPI_COUNT] = {
+      {igemm_kernel<EPI_GENERIC, false>, igemm_kernel<EPI_PLAIN, false>, igemm_kernel<EPI_RES, false>,
+       igemm_kernel<EPI_ROWBIAS, false>, nullptr, igemm_kernel<EPI_HEADS, false>},
+      {nullptr, igemm_kernel<EPI_PLAIN, true>, igemm_kernel<EPI_RES, true>, igemm_kernel<EPI_ROWBIAS, true>,
+       igemm_kernel<EPI_GEGLU, true>, nullptr}};
   static thread_local bool configured = false;
   if (!configured) {
-    for (int i = 0; i < EPI_COUNT; ++i)
-      CB_CHECK_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    for (int st = 0; st < 2; ++st)
+      for (int i = 0; i < EPI_COUNT; ++i)
+        if (kernels[st][i])
+          CB_CHECK_CUDA(cudaFuncSetAttribute(kernels[st][i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
-  kernels[epi]<<<grid, NUM_THREADS, smem, stream>>>(mapA0, mapA1, mapB, p);
+  const KernelFn kfn = kernels[staged ? 1 : 0][epi];
+  CB_REQUIRE(kfn != nullptr, "cb_igemm: internal: no kernel for epilogue %d staged %d", epi, (int)staged);
+  kfn<<<grid, NUM_THREADS, smem, stream>>>(mapA0, mapA1, mapB, mapO, mapR, p);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

@@ -44,7 +44,7 @@ static EncodeTiledFn resolve_encode() {
 }
 
 int make_tmap_act(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                   const uint32_t* box) {
+                   const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = resolve_encode();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver): the CUDA path cannot run on this host");
@@ -79,7 +79,9 @@ int make_tmap_act(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     }
   }
   CUresult r = fn(out, CB_TMAP_DTYPE, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, gbox,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu,%llu,... box %u,%u,...)", (int)r, rank,

@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import IGemmDesc, check
 
 EPI_LINEAR, EPI_GEGLU, EPI_HEADS = 0, 1, 2
+EPILOGUE_AUTO, EPILOGUE_DIRECT, EPILOGUE_STAGED = 0, 1, 2
 ACT_NONE, ACT_SILU = 0, 1
 
 # 16-bit activation / weight dtype of the loaded library build (fp16 unless CREMAGE_B200_DTYPE=bf16)
@@ -199,7 +200,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
           mode: int = EPI_LINEAR, out: Optional[torch.Tensor] = None, out_f32: bool = False, out_ld: Optional[int] = None,
           out_scale: float = 1.0, heads: Optional[Tuple[int, int, int, int, int]] = None, bn: Optional[int] = None,
-          stages: int = 0) -> torch.Tensor:
+          stages: int = 0, epilogue: int = 0) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
@@ -253,7 +254,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     d.out_scale = out_scale
     if heads is not None:
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
-    d.bn, d.stages = bn, stages
+    d.bn, d.stages, d.epilogue = bn, stages, epilogue
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
             flops=2.0 * rows * len(dw) * (c0 + c1) * ncols,

@@ -50,6 +50,8 @@ int64_t cb_launch_count(void);
  * ------------------------------------------------------------------------------------------------------------- */
 enum { CB_EPI_LINEAR = 0, CB_EPI_GEGLU = 1, CB_EPI_HEADS = 2 };
 enum { CB_ACT_NONE = 0, CB_ACT_SILU = 1 };
+/* epilogue form: AUTO picks STAGED (residual panel in by TMA, result out by TMA store) for the small-K launches */
+enum { CB_EPILOGUE_AUTO = 0, CB_EPILOGUE_DIRECT = 1, CB_EPILOGUE_STAGED = 2 };
 
 typedef struct cb_igemm_desc {
   /* A operand: one or two NHWC bf16 tensors [a_n][a_h][a_w][c] sharing the pixel grid; channels of source 1
@@ -82,6 +84,7 @@ typedef struct cb_igemm_desc {
   /* tiling */
   int bn;                /* N tile, multiple of 32, <= 256 */
   int stages;            /* smem pipeline depth, 0 = auto */
+  int epilogue;          /* CB_EPILOGUE_* (tuning / test knob; results are identical) */
 } cb_igemm_desc;
 
 int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);

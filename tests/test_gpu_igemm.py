@@ -124,3 +124,68 @@ def test_heads_epilogue_scatter():
     got = qkv.view(3, batch, heads, tokens, dpad).float().cpu()
     _close(got[..., :d], y)
     assert got[..., d:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("m,k,n", [(128, 64, 32), (1000, 320, 320), (154, 768, 640), (4096, 1280, 1280), (300, 96, 72),
+                                   (65536, 320, 320)])
+@pytest.mark.parametrize("what", ["plain", "res", "rowbias"])
+def test_staged_epilogue_equals_direct(m, k, n, what):
+    """The staged (TMA in / TMA out) and the direct epilogue are two schedules of the same arithmetic: bit-identical
+    results, ragged M / N clipped by the tensor map."""
+    ops = _ops()
+    a = _rand(m, k, seed=1).to(ACT).cuda()
+    w = _rand(n, k, scale=k ** -0.5, seed=2)
+    b = _rand(n, seed=3).cuda()
+    wp = ops.pack_weight(w).cuda()
+    kw = {}
+    if what == "res":
+        kw["residual"] = _rand(m, n, seed=4).to(ACT).cuda()
+    if what == "rowbias":
+        kw["rowbias"] = _rand(1, n, seed=5).cuda()
+    guard = torch.full((m + 64, n), 7.0, dtype=ACT, device="cuda")   # rows past m must stay untouched
+    o_dir = ops.igemm(a, wp, n, bias=b, epilogue=ops.EPILOGUE_DIRECT, **kw)
+    o_stg = ops.igemm(a, wp, n, bias=b, epilogue=ops.EPILOGUE_STAGED, out=guard[:m], **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(o_dir, o_stg)
+    assert (guard[m:] == 7.0).all()
+    want = a.float().cpu() @ w.to(ACT).float().t() + b.cpu()
+    if what == "res":
+        want = want + kw["residual"].float().cpu()
+    if what == "rowbias":
+        want = want + kw["rowbias"].cpu()
+    _close(o_stg, want)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 128), (3, 8, 8, 128, 64), (1, 64, 64, 64, 160), (1, 12, 20, 64, 32),
+                                            (5, 4, 4, 64, 96)])
+def test_staged_epilogue_conv_tiles(n, h, w, cin, cout):
+    """Staged epilogue over 2-D / 3-D pixel tiles (the warp's 32 rows form a {w, h, n} box) incl. overhanging tiles."""
+    ops = _ops()
+    x = _rand(n, cin, h, w, seed=5).to(ACT)
+    wt = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=6)
+    b = _rand(cout, seed=7)
+    res = _rand(n, h, w, cout, seed=9).to(ACT)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    out = ops.igemm(x_nhwc, ops.pack_weight(wt).cuda(), cout, taps=ops.TAPS_3X3, bias=b.cuda(),
+                    residual=res.view(-1, cout).cuda(), epilogue=ops.EPILOGUE_STAGED)
+    ref = ops.igemm(x_nhwc, ops.pack_weight(wt).cuda(), cout, taps=ops.TAPS_3X3, bias=b.cuda(),
+                    residual=res.view(-1, cout).cuda(), epilogue=ops.EPILOGUE_DIRECT)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    want = F.conv2d(x.float(), wt.to(ACT).float(), b, padding=1) + res.float().permute(0, 3, 1, 2)
+    _close(out.view(n, h, w, cout).permute(0, 3, 1, 2), want)
+
+
+@pytest.mark.parametrize("m,dim", [(512, 64), (4096, 320), (1000, 128)])
+def test_geglu_epilogue_shapes(m, dim):
+    ops = _ops()
+    inner = 4 * dim
+    a = _rand(m, dim, seed=1).to(ACT)
+    w = _rand(2 * inner, dim, scale=dim ** -0.5, seed=2)
+    b = _rand(2 * inner, seed=3)
+    wq, bq = ops.pack_geglu(w, b, 128)
+    out = ops.igemm(a.cuda(), ops.pack_weight(wq).cuda(), inner, bias=bq.cuda(), mode=ops.EPI_GEGLU, bn=128)
+    torch.cuda.synchronize()
+    y = a.float() @ w.to(ACT).float().t() + b
+    xh, gate = y.chunk(2, dim=-1)
+    _close(out, xh * F.gelu(gate))
