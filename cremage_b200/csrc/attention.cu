@@ -2,15 +2,20 @@
 //
 //   S = Q K^T      tcgen05.mma  (A = Q tile [128 x dpad], B = K tile [128 x dpad], both K-major)  -> TMEM
 //   online softmax one thread per query row: tcgen05.ld of S, exp2 (packed 16-bit MUFU in the fp16 build), lazy
-//                  running-max rescale of the TMEM accumulator, P -> swizzled smem
-//   O += P V       tcgen05.mma  (A = P [128 x 128], B = V tile, MN-major)                          -> TMEM
+//                  running-max rescale of the TMEM accumulator, P packed to 16-bit pairs -> TMEM (tcgen05.st)
+//   O += P V       tcgen05.mma  (A = P straight from TMEM, B = V tile in smem, MN-major)           -> TMEM
+// P never touches shared memory: with d = 40 the P round trip (32 KB written + 32 KB read per tile and block) would
+// make the kernel co-bound by shared-memory bandwidth next to the MUFU pipe, and the freed space deepens the K/V ring.
 //
 // Warp-specialised, one CTA = up to two 128-row query tiles of one (batch, head) sharing every K/V tile:
 //   warp 0        TMA producer (Q once, K/V ring)
-//   warp 1        TMEM allocator + single-thread MMA issuer
+//   warp 1        TMEM allocator + single-thread MMA issuer of query tile 0      warp 10   MMA issuer of query tile 1
 //   warps 2..5    softmax warpgroup 0 (query tile 0)      warps 6..9    softmax warpgroup 1 (query tile 1)
-// The two warpgroups run half a phase apart: while one does exp/convert on its S tile the tensor core computes the
-// other's P*V and next Q*K^T, so MUFU / FMA issue and the tensor pipe stay busy together.
+// Decoupled issue: a warpgroup releases its S tile (s_free) the moment the scores are in registers, so its issuer
+// thread (one per query tile, each with its own blocking wait sequence; K/V stages are released by both) issues
+// Q*K^T of block j+1 while the warpgroup is still exponentiating block j; P*V of block j follows when P is written
+// (p_full) and signals pv_done, which the warpgroup only consults before it overwrites P or rescales O.  In steady state a warpgroup never waits for the
+// tensor core, and the two warpgroups keep the MUFU pipe (the bound for d = 40) busy back to back.
 // The softmax row sum costs nothing when dpad > d: column d of V holds 1.0 (contract of cb_attention), so the
 // tensor core accumulates sum_j P_ij into O[:, d].
 // Q/K/V arrive through 3-D TMA boxes from the per-head padded layout [bh][tokens][dpad] written by the QKV
@@ -24,11 +29,11 @@ namespace cb {
 constexpr int ATT_BM = 128;             // query rows per warpgroup tile
 constexpr int ATT_BN = 128;             // kv rows per iteration
 constexpr int PANEL_BYTES = 128 * 128;  // [128 rows][64 x 16-bit]
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 352;         // TMA warp, issuer warp (tile 0), 8 softmax warps, issuer warp (tile 1)
 constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
-  int nq, nk, d, dpad, np, heads, stages, nwg, use_ones;
+  int nq, nk, d, dpad, np, heads, stages, nwg, use_ones, p_alias;
   float scale_log2;
   uint32_t idesc_qk, idesc_pv, tmem_cols;
   act_t* out;
@@ -61,16 +66,17 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const uint32_t sQ = base;                                    // [nwg]
   const uint32_t sK = sQ + uint32_t(p.nwg) * tile_bytes;       // [stages]
   const uint32_t sV = sK + uint32_t(p.stages) * tile_bytes;    // [stages]
-  const uint32_t sP = sV + uint32_t(p.stages) * tile_bytes;    // [nwg][2 panels]
-  const uint32_t bars = sP + uint32_t(p.nwg) * 2u * PANEL_BYTES;
+  const uint32_t bars = sV + uint32_t(p.stages) * tile_bytes;
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u + 8u * uint32_t(s); };
-  auto k_empty = [&](int s) { return bars + 24u + 8u * uint32_t(s); };
-  auto v_full = [&](int s) { return bars + 40u + 8u * uint32_t(s); };
-  auto v_empty = [&](int s) { return bars + 56u + 8u * uint32_t(s); };
-  auto s_full = [&](int w) { return bars + 72u + 8u * uint32_t(w); };
-  auto p_full = [&](int w) { return bars + 88u + 8u * uint32_t(w); };
-  const uint32_t tmem_slot = bars + 104u;
+  auto k_empty = [&](int s) { return bars + 40u + 8u * uint32_t(s); };
+  auto v_full = [&](int s) { return bars + 72u + 8u * uint32_t(s); };
+  auto v_empty = [&](int s) { return bars + 104u + 8u * uint32_t(s); };
+  auto s_full = [&](int w) { return bars + 136u + 8u * uint32_t(w); };
+  auto p_full = [&](int w) { return bars + 152u + 8u * uint32_t(w); };
+  auto s_free = [&](int w) { return bars + 168u + 8u * uint32_t(w); };
+  auto pv_done = [&](int w) { return bars + 184u + 8u * uint32_t(w); };
+  const uint32_t tmem_slot = bars + 200u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -84,10 +90,13 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
     mbar_init(q_full, 1);
+    for (int s = 0; s < 4; ++s) {   // a stage is free once the issuer of every active tile has committed it
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), uint32_t(nact));
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), uint32_t(nact));
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
-      mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
       mbar_init(s_full(s), 1); mbar_init(p_full(s), ATT_BM);
+      mbar_init(s_free(s), ATT_BM); mbar_init(pv_done(s), 1);
     }
     fence_mbar_init();
   }
@@ -101,6 +110,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
   auto tS = [&](int w) { return tmem_base + uint32_t(w) * 128u; };
   auto tO = [&](int w) { return tmem_base + uint32_t(p.nwg) * 128u + uint32_t(w) * uint32_t(p.dpad); };
+  // P: 128 rows x 128 16-bit values = 64 columns; its own region when TMEM has room, else the first half of S
+  auto tP = [&](int w) {
+    return p.p_alias ? tS(w) : tmem_base + uint32_t(p.nwg) * (128u + uint32_t(p.dpad)) + uint32_t(w) * 64u;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -123,10 +136,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           tma_load_3d(sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapV, v_full(st), pn * 64, j * ATT_BN, bh);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      auto issue_qk = [&](int w, int kstage) {
+  } else if (warp == 1 || warp == 10) {
+    // ===================== MMA issuers (one thread per query tile) =====================
+    const int w = (warp == 1) ? 0 : 1;
+    if (lane == 0 && w < nact) {
+      auto issue_qk = [&](int kstage) {
         const uint32_t qb = sQ + uint32_t(w) * tile_bytes, kb = sK + uint32_t(kstage) * tile_bytes;
         const int ksteps = p.dpad / 16;
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -134,41 +148,42 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           umma_bf16(tS(w), make_sdesc_sw128(qb + off, 16, 1024), make_sdesc_sw128(kb + off, 16, 1024), p.idesc_qk, ks != 0);
         }
       };
-      auto issue_pv = [&](int w, int vstage, bool accumulate) {
-        const uint32_t pb = sP + uint32_t(w) * 2u * PANEL_BYTES, vb = sV + uint32_t(vstage) * tile_bytes;
+      auto issue_pv = [&](int vstage, bool accumulate) {
+        const uint32_t vb = sV + uint32_t(vstage) * tile_bytes;
         for (int ks = 0; ks < ATT_BN / 16; ++ks) {
-          const uint32_t aoff = uint32_t(ks >> 2) * PANEL_BYTES + uint32_t(ks & 3) * 32u;  // P: K-major
           const uint32_t boff = uint32_t(ks) * 2048u;                                       // V: 16 kv rows = 2 atoms
-          umma_bf16(tO(w), make_sdesc_sw128(pb + aoff, 16, 1024), make_sdesc_sw128(vb + boff, PANEL_BYTES, 1024),
-                    p.idesc_pv, (accumulate || ks != 0) ? 1u : 0u);
+          // A = P from TMEM: 16 K-values of a row = 8 columns (two 16-bit values per 32-bit cell)
+          umma_ts(tO(w), tP(w) + uint32_t(ks) * 8u, make_sdesc_sw128(vb + boff, PANEL_BYTES, 1024),
+                  p.idesc_pv, (accumulate || ks != 0) ? 1u : 0u);
         }
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full(0), 0);
-      tc_fence_after();
-      for (int w = 0; w < nact; ++w) {
-        issue_qk(w, 0);
+      auto stage_of = [&](int j) { return j % p.stages; };
+      auto phase_of = [&](int j) { return uint32_t((j / p.stages) & 1); };
+      auto do_qk = [&](int j) {     // Q*K^T of block j (j >= 1: once the scores of block j-1 are in registers)
+        if (j > 0) mbar_wait(s_free(w), uint32_t((j - 1) & 1));
+        mbar_wait(k_full(stage_of(j)), phase_of(j));
+        tc_fence_after();
+        issue_qk(stage_of(j));
         umma_commit(s_full(w));
-      }
-      umma_commit(k_empty(0));
+        umma_commit(k_empty(stage_of(j)));
+      };
+      auto do_pv = [&](int j) {
+        mbar_wait(p_full(w), uint32_t(j & 1));
+        mbar_wait(v_full(stage_of(j)), phase_of(j));
+        tc_fence_after();
+        issue_pv(stage_of(j), j > 0);
+        umma_commit(pv_done(w));
+        umma_commit(v_empty(stage_of(j)));
+      };
+      mbar_wait(q_full, 0);
+      do_qk(0);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j % p.stages;
-        const uint32_t ph = uint32_t((j / p.stages) & 1);
-        const bool more = (j + 1 < nblk);
-        const int st1 = (j + 1) % p.stages;
-        const uint32_t ph1 = uint32_t(((j + 1) / p.stages) & 1);
-        for (int w = 0; w < nact; ++w) {
-          mbar_wait(p_full(w), uint32_t(j & 1));   // softmax w: S consumed, P written, O rescaled
-          if (w == 0) mbar_wait(v_full(st), ph);
-          tc_fence_after();
-          issue_pv(w, st, j > 0);
-          if (w == nact - 1) umma_commit(v_empty(st));
-          if (more) {
-            if (w == 0) { mbar_wait(k_full(st1), ph1); tc_fence_after(); }
-            issue_qk(w, st1);
-          }
-          umma_commit(s_full(w));                   // S_w(j+1) ready / final O_w ready
-          if (more && w == nact - 1) umma_commit(k_empty(st1));
+        if (p.p_alias) {            // P overwrites S: the next Q*K^T may only follow this block's P*V
+          do_pv(j);
+          if (j + 1 < nblk) do_qk(j + 1);
+        } else {
+          if (j + 1 < nblk) do_qk(j + 1);
+          do_pv(j);
         }
       }
     }
@@ -179,9 +194,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
       const int r = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
       const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-      const uint32_t p_row = sP + uint32_t(w) * 2u * PANEL_BYTES + uint32_t(r) * 128u;
-      const uint32_t sw = uint32_t(r & 7);
-      const uint32_t tSw = tS(w) + lane_off, tOw = tO(w) + lane_off;
+      const uint32_t tSw = tS(w) + lane_off, tOw = tO(w) + lane_off, tPw = tP(w) + lane_off;
       float m_used = -INFINITY, l_run = 0.f;
 
       for (int j = 0; j < nblk; ++j) {
@@ -193,6 +206,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         tmem_ld32(tSw + 64u, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
         tmem_ld32(tSw + 96u, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_free(w));      // the scores are in registers: Q*K^T of block j+1 may overwrite S
         const int nvalid = p.nk - j * ATT_BN;
         if (nvalid < ATT_BN) {   // ragged last block: K rows beyond nk were zero filled -> mask
 #pragma unroll
@@ -213,6 +228,8 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         } else {
           const bool need = (m_blk - m_used) > RESCALE_TAU;
           if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(pv_done(w), uint32_t((j - 1) & 1));   // O holds every P*V up to block j-1
+            tc_fence_after();
             const float alpha = need ? exp2f(m_used - m_blk) : 1.f;
             if (need) m_used = m_blk;
             if (!USE_ONES) l_run *= alpha;
@@ -230,34 +247,27 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
         float rs = 0.f;
 #pragma unroll
-        for (int c = 0; c < ATT_BN; c += 32) {
-          uint32_t pk[16];
+        for (int c = 0; c < ATT_BN; c += 64) {
+          uint32_t pk[32];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+          for (int e = 0; e < 64; e += 2) {
             pk[e >> 1] = exp2_pack(__uint_as_float(s[c + e]), __uint_as_float(s[c + e + 1]), p.scale_log2, m_used);
             if (!USE_ONES) {
               const float2 b = unpack_act2(pk[e >> 1]);
               rs += b.x + b.y;
             }
           }
-          const uint32_t panel = uint32_t(c >> 6) * PANEL_BYTES;
-          const uint32_t chunk0 = uint32_t((c & 63) >> 3);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t addr = p_row + panel + (((chunk0 + uint32_t(g)) ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * g]), "r"(pk[4 * g + 1]),
-                         "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
-                         : "memory");
-          }
+          if (c == 0 && j > 0) mbar_wait(pv_done(w), uint32_t((j - 1) & 1));   // P*V of block j-1 has finished reading P
+          tmem_st32(tPw + uint32_t(c >> 1), pk);
         }
+        tmem_st_wait();
         if (!USE_ONES) l_run += rs;
-        fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core's async proxy
         tc_fence_before();
         mbar_arrive(p_full(w));
       }
 
       // ---- epilogue: O / l -> out[b][q][head*d + :]
-      mbar_wait(s_full(w), uint32_t(nblk & 1));
+      mbar_wait(pv_done(w), uint32_t((nblk - 1) & 1));
       tc_fence_after();
       const int q = q_first + w * ATT_BM + r;
       const int b = bh / p.heads, head = bh - b * p.heads;
@@ -335,14 +345,15 @@ extern "C" int cb_attention(const void* q, const void* k, const void* v, void* o
   AttnParams p{};
   p.nq = (int)nq; p.nk = (int)nk; p.d = d; p.dpad = dpad; p.np = dpad / 64; p.heads = (int)heads;
   p.nwg = dpad <= 128 ? 2 : 1;           // TMEM: nwg * (128 + dpad) columns <= 512
-  p.stages = dpad <= 64 ? 2 : 1;         // smem: (nwg + 2*stages) * np panels + nwg * 2 panels
+  p.stages = dpad <= 64 ? 4 : (dpad <= 128 ? 2 : 1);   // smem: (nwg + 2*stages) * np panels of 16 KB
+  p.p_alias = (p.nwg * (128 + dpad + 64) > 512) ? 1 : 0;   // no room for a separate P region: P overwrites S
   p.use_ones = dpad > d;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.idesc_qk = make_idesc_f16(128, 128, 0, 0);
   p.idesc_pv = make_idesc_f16(128, dpad, 0, 1);   // B = V is MN-major
   p.tmem_cols = 512u;
   p.out = (act_t*)out;
-  const size_t smem = (size_t)(p.nwg + 2 * p.stages) * p.np * PANEL_BYTES + (size_t)p.nwg * 2 * PANEL_BYTES + 128;
+  const size_t smem = (size_t)(p.nwg + 2 * p.stages) * p.np * PANEL_BYTES + 256;
   CB_REQUIRE(smem <= 227 * 1024, "cb_attention: needs %zu bytes of shared memory", smem);
   static thread_local bool configured = false;
   if (!configured) {

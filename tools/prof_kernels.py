@@ -88,7 +88,8 @@ def bench_igemm(B, iters, warm, filt=""):
         bias = torch.zeros(cout, device="cuda")
         tp = ops.TAPS_3X3 if taps == 9 else ops.TAPS_1X1
         out = torch.empty(n * h * w, cout, dtype=ops.ACT, device="cuda")
-        ms = timeit(lambda: ops.igemm(x, wt, cout, taps=tp, bias=bias, out=out), iters, warm)
+        res = act(n * h * w, cout) if "+res" in name else None
+        ms = timeit(lambda: ops.igemm(x, wt, cout, taps=tp, bias=bias, out=out, residual=res), iters, warm)
         fl = 2.0 * n * h * w * taps * cin * cout
         print(f"{name:28s} M={n * h * w:7d} K={taps * cin:6d} N={cout:5d}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  "
               f"{fl / ms / 1e9 / tf_peak:6.1%} of burst peak")
