@@ -40,7 +40,7 @@ class IGemmDesc(C.Structure):
         ("out_scale", C.c_float),
         ("heads_d", C.c_int), ("heads_dpad", C.c_int), ("heads_h", C.c_int), ("heads_tokens", C.c_int),
         ("heads_which_stride", C.c_int64),
-        ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int),
+        ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int), ("cta_pair", C.c_int),
     ]
 
 

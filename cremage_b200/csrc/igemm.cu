@@ -40,6 +40,7 @@ struct IGemmKParams {
   int TW, TH, TN;        // tile decomposition, TW*TH*TN == 128
   int tiles_w, tiles_h;  // tiles along w / h
   int m_tiles, n_tiles;  // tile grid
+  int two, m_pairs;      // CTA-pair mode (cta_group::2): a cluster of 2 CTAs owns M tiles 2*mp, 2*mp+1 of one N tile
   int resident_b;        // 1: B of this CTA's N tile stays in smem, CTA walks M tiles of that N tile
   int m_step;            // resident mode: stride between the M tiles of one CTA ( = gridDim.x / n_tiles )
   // K loop
@@ -74,6 +75,13 @@ struct TileSched {
   const IGemmKParams& p;
   __device__ explicit TileSched(const IGemmKParams& pp) : p(pp) {}
   __device__ __forceinline__ bool get(int i, int& mt, int& nt) const {
+    if (p.two) {
+      const long long t = (long long)(blockIdx.x >> 1) + (long long)i * (gridDim.x >> 1);
+      if (t >= (long long)p.m_pairs * p.n_tiles) return false;
+      nt = int(t % p.n_tiles);
+      mt = 2 * int(t / p.n_tiles) + int(blockIdx.x & 1);   // may be == m_tiles (odd count): an all-out-of-bounds tile
+      return true;
+    }
     if (p.resident_b) {
       nt = int(blockIdx.x) % p.n_tiles;
       mt = int(blockIdx.x) / p.n_tiles + i * p.m_step;
@@ -261,7 +269,7 @@ __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32
   }
 }
 
-template <int EPI, bool STAGED>
+template <int EPI, bool STAGED, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
              const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
@@ -270,8 +278,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   // carve (1024-aligned): [resident B: num_k x bn*128] [ring: stages x (A 16K [+ B bn*128])]
   //                       [staging: EPI_WARPS x npan x 2K] [barriers] [bias x2]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_chunk_bytes = uint32_t(p.bn) * 128u;
+  const uint32_t b_chunk_bytes = uint32_t(TWO ? (p.bn >> 1) : p.bn) * 128u;   // a pair CTA stages half of the B tile
   const uint32_t res_bytes = p.resident_b ? uint32_t(p.num_k) * b_chunk_bytes : 0u;
+  const uint32_t pair_rank = TWO ? (blockIdx.x & 1u) : 0u;
   const uint32_t stage_bytes = A_STAGE_BYTES + (p.resident_b ? 0u : b_chunk_bytes);
   const uint32_t ring_base = smem_base + res_bytes;
   const uint32_t stg_base = ring_base + uint32_t(p.stages) * stage_bytes;
@@ -306,18 +315,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 32 * EPI_WARPS);
+      mbar_init(acc_empty(b), EPI_WARPS * (TWO ? 2 : 1));   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(bres_bar, 1);
     for (int e = 0; e < EPI_WARPS; ++e) mbar_init(resid_bar(e), 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (TWO) { tmem_alloc_pair(tmem_slot, p.tmem_cols); tmem_relinquish_pair(); }
+    else     { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -345,19 +355,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         for (int kt = 0; kt < p.num_k; ++kt) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = ring_base + uint32_t(stage) * stage_bytes;
-          mbar_expect_tx(full_bar(stage), stage_bytes);
           const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], cn = n0 + p.tap_dn[tap];
-          if (ch < p.chunks0) tma_load_4d(sa, &mapA0, full_bar(stage), ch * BK, cw, chh, cn);
-          else                tma_load_4d(sa, &mapA1, full_bar(stage), (ch - p.chunks0) * BK, cw, chh, cn);
-          if (!p.resident_b) tma_load_2d(sa + A_STAGE_BYTES, &mapB, full_bar(stage), kt * BK, nt * p.bn);
+          if (TWO) {
+            // both CTAs load (own A rows, own half of B); every byte is counted on the LEADER's full barrier
+            if (pair_rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
+            if (ch < p.chunks0) tma_load_4d_pair(sa, &mapA0, full_bar(stage), ch * BK, cw, chh, cn);
+            else                tma_load_4d_pair(sa, &mapA1, full_bar(stage), (ch - p.chunks0) * BK, cw, chh, cn);
+            tma_load_2d_pair(sa + A_STAGE_BYTES, &mapB, full_bar(stage), kt * BK, nt * p.bn + int(pair_rank) * (p.bn >> 1));
+          } else {
+            mbar_expect_tx(full_bar(stage), stage_bytes);
+            if (ch < p.chunks0) tma_load_4d(sa, &mapA0, full_bar(stage), ch * BK, cw, chh, cn);
+            else                tma_load_4d(sa, &mapA1, full_bar(stage), (ch - p.chunks0) * BK, cw, chh, cn);
+            if (!p.resident_b) tma_load_2d(sa + A_STAGE_BYTES, &mapB, full_bar(stage), kt * BK, nt * p.bn);
+          }
           if (++ch == cpt) { ch = 0; ++tap; }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (pair mode: the leader CTA's thread drives both tensor cores) =====================
+    if (lane == 0 && pair_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int mt, nt;
@@ -379,12 +397,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
-            umma_bf16(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), p.idesc, (kt | k) != 0);
+            if (TWO) umma_bf16_pair(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), p.idesc, (kt | k) != 0);
+            else     umma_bf16(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), p.idesc, (kt | k) != 0);
           }
-          umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (TWO) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(acc_full(buf));  // accumulator complete
+        if (TWO) umma_commit_pair(acc_full(buf)); else umma_commit(acc_full(buf));  // accumulator complete
       }
     }
   } else {
@@ -467,16 +487,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         epilogue_tile_direct<EPI>(p, trow, sb, nt, n, row_ok, row, hh);
       }
       tc_fence_before();
-      mbar_arrive(acc_empty(buf));   // 256 arrivals: every epilogue thread has drained its TMEM lanes
+      __syncwarp();                  // every lane of this warp has drained its TMEM lanes
+      if (lane == 0) {
+        if (TWO) mbar_arrive_leader(acc_empty(buf)); else mbar_arrive(acc_empty(buf));
+      }
     }
     if (STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all();   // no CTA of a pair leaves while its peer may still read its smem / signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (TWO) tmem_dealloc_pair(tmem_base, p.tmem_cols); else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -532,7 +556,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     }
     uint64_t bdims[2] = {(uint64_t)ktot, (uint64_t)d->wgt_rows};
     uint64_t bstr[2] = {1, (uint64_t)ktot};
-    uint32_t bbox[2] = {BK, (uint32_t)d->bn};
+    uint32_t bbox[2] = {BK, (uint32_t)(d->cta_pair ? d->bn / 2 : d->bn)};   // a pair CTA loads half of the N tile
     CB_REQUIRE(d->wgt_rows > 0, "cb_igemm: wgt_rows must be > 0");
     rc = make_tmap_act(&mapB, d->wgt, 2, bdims, bstr, bbox);
     if (rc) return rc;
@@ -556,7 +580,11 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.taps = d->taps; p.chunks0 = chunks0; p.chunks1 = chunks1; p.num_k = num_k;
   for (int i = 0; i < 9; ++i) { p.tap_dw[i] = d->tap_dw[i]; p.tap_dh[i] = d->tap_dh[i]; p.tap_dn[i] = d->tap_dn[i]; }
   p.cout = (int)d->cout; p.bn = d->bn;
-  p.idesc = make_idesc_f16(BM, d->bn, 0, 0);
+  const bool two = d->cta_pair != 0;
+  if (two) CB_REQUIRE(d->stages <= 0 || d->stages >= 2, "cb_igemm: bad stage count");
+  p.two = two ? 1 : 0;
+  p.m_pairs = (p.m_tiles + 1) / 2;
+  p.idesc = make_idesc_f16(two ? 2 * BM : BM, d->bn, 0, 0);
   p.acc_stride = (uint32_t)pow2_cols(d->bn);
   p.tmem_cols = 2u * p.acc_stride;   // two accumulators: <= 512 columns
   p.mode = d->mode; p.act = d->act; p.out_f32 = d->out_f32;
@@ -615,11 +643,11 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
   //      that N tile gets several M tiles; otherwise stream A and B through the ring
   const size_t fixed = 1024 + 16 * 12 + 128 + 16 + sizeof(float) * 512 + 64;
-  const size_t b_chunk = (size_t)d->bn * 128;
+  const size_t b_chunk = (size_t)(two ? d->bn / 2 : d->bn) * 128;
   const size_t res_bytes = (size_t)num_k * b_chunk;
   int resident = 0;
   unsigned grid = 0;
-  if (d->stages <= 0 && p.n_tiles <= g_num_sms &&
+  if (!two && d->stages <= 0 && p.n_tiles <= g_num_sms &&
       res_bytes + 4 * (size_t)A_STAGE_BYTES + staging + fixed <= (size_t)SMEM_LIMIT) {
     const int ctas_per_nt = g_num_sms / p.n_tiles;
     if (ctas_per_nt >= 1 && p.m_tiles >= 3 * ctas_per_nt) {
@@ -639,29 +667,52 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.stages = stages;
   const size_t smem = (resident ? res_bytes : 0) + (size_t)stages * stage_bytes + staging + fixed;
   CB_REQUIRE(smem <= (size_t)SMEM_LIMIT, "cb_igemm: tile needs %zu bytes of shared memory", smem);
-  if (!resident) {
+  if (two) {
+    const long long total = (long long)p.m_pairs * p.n_tiles;
+    const long long clusters = total < g_num_sms / 2 ? total : g_num_sms / 2;
+    grid = (unsigned)(2 * clusters);
+  } else if (!resident) {
     const long long total = (long long)p.m_tiles * p.n_tiles;
     grid = (unsigned)(total < g_num_sms ? total : g_num_sms);
   }
 
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const IGemmKParams);
-  static const KernelFn kernels[2][EPI_COUNT] = {
-      {igemm_kernel<EPI_GENERIC, false>, igemm_kernel<EPI_PLAIN, false>, igemm_kernel<EPI_RES, false>,
-       igemm_kernel<EPI_ROWBIAS, false>, nullptr, igemm_kernel<EPI_HEADS, false>},
-      {nullptr, igemm_kernel<EPI_PLAIN, true>, igemm_kernel<EPI_RES, true>, igemm_kernel<EPI_ROWBIAS, true>,
-       igemm_kernel<EPI_GEGLU, true>, nullptr}};
+  // [pair][staged][epilogue]
+  static const KernelFn kernels[2][2][EPI_COUNT] = {
+      {{igemm_kernel<EPI_GENERIC, false, false>, igemm_kernel<EPI_PLAIN, false, false>, igemm_kernel<EPI_RES, false, false>,
+        igemm_kernel<EPI_ROWBIAS, false, false>, nullptr, igemm_kernel<EPI_HEADS, false, false>},
+       {nullptr, igemm_kernel<EPI_PLAIN, true, false>, igemm_kernel<EPI_RES, true, false>,
+        igemm_kernel<EPI_ROWBIAS, true, false>, igemm_kernel<EPI_GEGLU, true, false>, nullptr}},
+      {{igemm_kernel<EPI_GENERIC, false, true>, igemm_kernel<EPI_PLAIN, false, true>, igemm_kernel<EPI_RES, false, true>,
+        igemm_kernel<EPI_ROWBIAS, false, true>, nullptr, igemm_kernel<EPI_HEADS, false, true>},
+       {nullptr, igemm_kernel<EPI_PLAIN, true, true>, igemm_kernel<EPI_RES, true, true>,
+        igemm_kernel<EPI_ROWBIAS, true, true>, igemm_kernel<EPI_GEGLU, true, true>, nullptr}}};
   static thread_local bool configured = false;
   if (!configured) {
-    for (int st = 0; st < 2; ++st)
-      for (int i = 0; i < EPI_COUNT; ++i)
-        if (kernels[st][i])
-          CB_CHECK_CUDA(cudaFuncSetAttribute(kernels[st][i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    for (int tw = 0; tw < 2; ++tw)
+      for (int st = 0; st < 2; ++st)
+        for (int i = 0; i < EPI_COUNT; ++i)
+          if (kernels[tw][st][i])
+            CB_CHECK_CUDA(cudaFuncSetAttribute(kernels[tw][st][i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
-  const KernelFn kfn = kernels[staged ? 1 : 0][epi];
+  const KernelFn kfn = kernels[two ? 1 : 0][staged ? 1 : 0][epi];
   CB_REQUIRE(kfn != nullptr, "cb_igemm: internal: no kernel for epilogue %d staged %d", epi, (int)staged);
-  kfn<<<grid, NUM_THREADS, smem, stream>>>(mapA0, mapA1, mapB, mapO, mapR, p);
+  if (two) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(NUM_THREADS);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    CB_CHECK_CUDA(cudaLaunchKernelEx(&lc, kfn, mapA0, mapA1, mapB, mapO, mapR, p));
+  } else {
+    kfn<<<grid, NUM_THREADS, smem, stream>>>(mapA0, mapA1, mapB, mapO, mapR, p);
+  }
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

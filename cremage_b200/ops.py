@@ -158,6 +158,7 @@ def choose_tile(n: int, h: int, w: int) -> Tuple[int, int, int]:
 
 
 NUM_SMS = 148  # B200
+PAIR_DEFAULT = True
 
 
 def choose_bn(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
@@ -172,6 +173,25 @@ def choose_bn(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
         if best is None or cost < best[0]:
             best = (cost, bn)
     return best[1]
+
+
+def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
+    """N tile in CTA-pair mode (74 clusters, each a 256-row tile): wide tiles first -- the B half per CTA shrinks the
+    shared-memory fill per flop, which is what bounds the large-K convolutions."""
+    best = None
+    m_pairs = (m_tiles + 1) // 2
+    for bn in (256, 160, 128, 64, 32):
+        if bn % multiple:
+            continue
+        tiles = m_pairs * (-(-cout_cols // bn))
+        cost = (-(-tiles // (NUM_SMS // 2))) * (bn + 16)
+        if best is None or cost < best[0]:
+            best = (cost, bn)
+    return best[1]
+
+
+PAIR_MIN_K_CHUNKS = 18   # CTA pairs for K >= 1152 (the MMA-bound launches); below that the epilogue dominates
+PAIR_MIN_M_TILES = 8
 
 
 TAPS_1X1 = ([0], [0], [0])
@@ -200,7 +220,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
           mode: int = EPI_LINEAR, out: Optional[torch.Tensor] = None, out_f32: bool = False, out_ld: Optional[int] = None,
           out_scale: float = 1.0, heads: Optional[Tuple[int, int, int, int, int]] = None, bn: Optional[int] = None,
-          stages: int = 0, epilogue: int = 0) -> torch.Tensor:
+          stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
@@ -221,8 +241,11 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     tw, th, tn = choose_tile(n, h, w)
     m_tiles = (-(-w // tw)) * (-(-h // th)) * (-(-n // tn))
     ncols = 2 * cout if mode == EPI_GEGLU else cout
+    num_k = len(taps[0]) * (ceil64(c0) // 64 + ceil64(c1) // 64)
+    if pair is None:
+        pair = PAIR_DEFAULT and num_k >= PAIR_MIN_K_CHUNKS and m_tiles >= PAIR_MIN_M_TILES
     if bn is None:
-        bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
+        bn = (choose_bn_pair if pair else choose_bn)(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
     if out is None:
         ld = out_ld if out_ld is not None else cout
         out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
@@ -254,11 +277,11 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     d.out_scale = out_scale
     if heads is not None:
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
-    d.bn, d.stages, d.epilogue = bn, stages, epilogue
+    d.bn, d.stages, d.epilogue, d.cta_pair = bn, stages, epilogue, int(bool(pair))
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
             flops=2.0 * rows * len(dw) * (c0 + c1) * ncols,
-            tag=f"M={rows} K={len(dw) * (c0 + c1)} N={ncols} taps={len(dw)} bn={bn} epi={mode}"
+            tag=f"M={rows} K={len(dw) * (c0 + c1)} N={ncols} taps={len(dw)} bn={bn}{'x2' if pair else ''} epi={mode}"
                 f"{'+res' if residual is not None else ''}{'+rowb' if rowbias is not None else ''}"
                 f"{'+act' if act else ''}{'+f32' if out_f32 else ''}" if _PROF is not None else "")
     return out

@@ -189,3 +189,38 @@ def test_geglu_epilogue_shapes(m, dim):
     y = a.float() @ w.to(ACT).float().t() + b
     xh, gate = y.chunk(2, dim=-1)
     _close(out, xh * F.gelu(gate))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", [(2, 16, 16, 64, 128, 128), (3, 8, 8, 128, 64, 64), (1, 64, 64, 64, 160, 160),
+                                               (2, 32, 32, 192, 256, 256), (1, 12, 20, 64, 32, 32), (5, 4, 4, 64, 96, 32)])
+@pytest.mark.parametrize("epilogue", [1, 2])
+def test_cta_pair_conv_equals_single(n, h, w, cin, cout, bn, epilogue):
+    """CTA-pair mode (cta_group::2, 256-row tiles over a cluster of 2) vs the single-CTA kernel: same dot products in
+    the same order -> bit-identical; odd tile counts leave the pair's second tile fully out of bounds."""
+    ops = _ops()
+    x = _rand(n, cin, h, w, seed=5).to(ACT)
+    wt = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=6)
+    b = _rand(cout, seed=7)
+    res = _rand(n * h * w, cout, seed=9).to(ACT).cuda()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wp = ops.pack_weight(wt).cuda()
+    single = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b.cuda(), residual=res, pair=False, epilogue=epilogue)
+    paired = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b.cuda(), residual=res, pair=True, bn=bn, epilogue=epilogue)
+    torch.cuda.synchronize()
+    want = F.conv2d(x.float(), wt.to(ACT).float(), b, padding=1) + res.float().cpu().view(n, h, w, cout).permute(0, 3, 1, 2)
+    _close(paired.view(n, h, w, cout).permute(0, 3, 1, 2), want)
+    assert torch.equal(single, paired)
+
+
+@pytest.mark.parametrize("m,k,n", [(4096, 1280, 1280), (1000, 320, 320), (65536, 2560, 640)])
+def test_cta_pair_gemm(m, k, n):
+    ops = _ops()
+    a = _rand(m, k, seed=1).to(ACT).cuda()
+    w = _rand(n, k, scale=k ** -0.5, seed=2)
+    b = _rand(n, seed=3).cuda()
+    wp = ops.pack_weight(w).cuda()
+    o1 = ops.igemm(a, wp, n, bias=b, pair=False)
+    o2 = ops.igemm(a, wp, n, bias=b, pair=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    _close(o2[:2048], a[:2048].float().cpu() @ w.to(ACT).float().t() + b.cpu())
