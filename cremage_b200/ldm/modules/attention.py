@@ -18,7 +18,7 @@ import torch.nn as nn
 from ... import ops
 from ...engine import ACT, PackedModule, f32, head_pad, packw, qkv_workspace, require_cuda, zero_workspace
 
-GEGLU_BN = 128  # N tile of the fused GEGLU projection (x / gate rows interleaved per 64 output columns)
+GEGLU_BN = ops.GEGLU_BN  # N tile of the fused GEGLU projection (x / gate rows interleaved per 64 output columns)
 
 
 def _check_extras(lora_ranks, ipa_num_tokens):

@@ -190,8 +190,12 @@ def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
     return best[1]
 
 
-PAIR_MIN_K_CHUNKS = 18   # CTA pairs for K >= 1152 (the MMA-bound launches); below that the epilogue dominates
+import os as _os
+# CTA pairs for K >= 1152 (the MMA-bound launches); below that the epilogue dominates.  Env overrides are tuning knobs.
+PAIR_MIN_K_CHUNKS = int(_os.environ.get("CB_PAIR_MIN_K_CHUNKS", "18"))
 PAIR_MIN_M_TILES = 8
+GEGLU_PAIR = int(_os.environ.get("CB_GEGLU_PAIR", "1"))
+GEGLU_BN = int(_os.environ.get("CB_GEGLU_BN", "256"))   # N tile of the fused GEGLU projection (x | gate halves)
 
 
 TAPS_1X1 = ([0], [0], [0])
@@ -244,6 +248,8 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     num_k = len(taps[0]) * (ceil64(c0) // 64 + ceil64(c1) // 64)
     if pair is None:
         pair = PAIR_DEFAULT and num_k >= PAIR_MIN_K_CHUNKS and m_tiles >= PAIR_MIN_M_TILES
+        if mode == EPI_GEGLU:
+            pair = bool(GEGLU_PAIR) and m_tiles >= PAIR_MIN_M_TILES
     if bn is None:
         bn = (choose_bn_pair if pair else choose_bn)(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
     if out is None:

@@ -101,9 +101,9 @@ def bench_igemm(B, iters, warm, filt=""):
         x = act(m, dim)
         w = torch.randn(8 * dim, dim, device="cuda") * dim ** -0.5
         b = torch.zeros(8 * dim, device="cuda")
-        wq, bq = ops.pack_geglu(w, b, 128)
+        wq, bq = ops.pack_geglu(w, b, ops.GEGLU_BN)
         wq = ops.pack_weight(wq)
-        ms = timeit(lambda: ops.igemm(x, wq, 4 * dim, bias=bq, mode=ops.EPI_GEGLU, bn=128), iters, warm)
+        ms = timeit(lambda: ops.igemm(x, wq, 4 * dim, bias=bq, mode=ops.EPI_GEGLU, bn=ops.GEGLU_BN), iters, warm)
         fl = 2.0 * m * dim * 8 * dim
         print(f"{name:28s} M={m:7d} K={dim:6d} N={8 * dim:5d}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  "
               f"{fl / ms / 1e9 / tf_peak:6.1%} of burst peak")
