@@ -40,7 +40,7 @@ class IGemmDesc(C.Structure):
         ("out_scale", C.c_float),
         ("heads_d", C.c_int), ("heads_dpad", C.c_int), ("heads_h", C.c_int), ("heads_tokens", C.c_int),
         ("heads_which_stride", C.c_int64),
-        ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int), ("cta_pair", C.c_int),
+        ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int), ("cta_pair", C.c_int), ("nsub", C.c_int),
     ]
 
 
@@ -79,7 +79,8 @@ _RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64, "cb_grou
 
 
 def lib_path() -> Path:
-    return _build.lib_path(DTYPE)
+    override = os.environ.get("CREMAGE_B200_LIB")   # A/B comparison of library builds (tools/)
+    return Path(override) if override else _build.lib_path(DTYPE)
 
 
 def load() -> C.CDLL:

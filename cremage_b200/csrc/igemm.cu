@@ -21,6 +21,8 @@
 //   kernel): the residual panel of every chunk is prefetched by TMA into a 64B-swizzled shared-memory panel
 //   while the tile's MMAs run, the thread adds it in place and the panel leaves by TMA store (bulk, asynchronous,
 //   full-sector writes; rows / columns outside the tensor are clipped by the tensor map).
+#include <type_traits>
+
 #include "common.cuh"
 #include "cremage_b200.h"
 
@@ -41,6 +43,8 @@ struct IGemmKParams {
   int tiles_w, tiles_h;  // tiles along w / h
   int m_tiles, n_tiles;  // tile grid
   int two, m_pairs;      // CTA-pair mode (cta_group::2): a cluster of 2 CTAs owns M tiles 2*mp, 2*mp+1 of one N tile
+  int nsub, n_groups;    // N sub-tiles that share one A stage (1 or 2), groups of sub-tiles = ceil(n_tiles / nsub)
+  int nacc;              // TMEM accumulator ring: 2 slots (nsub 1) or 3 slots (nsub 2: 3 x bn <= 512 columns)
   int resident_b;        // 1: B of this CTA's N tile stays in smem, CTA walks M tiles of that N tile
   int m_step;            // resident mode: stride between the M tiles of one CTA ( = gridDim.x / n_tiles )
   // K loop
@@ -75,11 +79,12 @@ struct TileSched {
   const IGemmKParams& p;
   __device__ explicit TileSched(const IGemmKParams& pp) : p(pp) {}
   __device__ __forceinline__ bool get(int i, int& mt, int& nt) const {
+    // `nt` is the N GROUP index: the group's sub-tiles are n-tiles nt*nsub .. nt*nsub + nsub-1 (see subs())
     if (p.two) {
       const long long t = (long long)(blockIdx.x >> 1) + (long long)i * (gridDim.x >> 1);
-      if (t >= (long long)p.m_pairs * p.n_tiles) return false;
-      nt = int(t % p.n_tiles);
-      mt = 2 * int(t / p.n_tiles) + int(blockIdx.x & 1);   // may be == m_tiles (odd count): an all-out-of-bounds tile
+      if (t >= (long long)p.m_pairs * p.n_groups) return false;
+      nt = int(t % p.n_groups);
+      mt = 2 * int(t / p.n_groups) + int(blockIdx.x & 1);   // may be == m_tiles (odd count): an all-out-of-bounds tile
       return true;
     }
     if (p.resident_b) {
@@ -88,10 +93,16 @@ struct TileSched {
       return mt < p.m_tiles;
     }
     const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
-    if (t >= (long long)p.m_tiles * p.n_tiles) return false;
-    nt = int(t % p.n_tiles);
-    mt = int(t / p.n_tiles);
+    if (t >= (long long)p.m_tiles * p.n_groups) return false;
+    nt = int(t % p.n_groups);
+    mt = int(t / p.n_groups);
     return true;
+  }
+  template <int NSUB>
+  __device__ __forceinline__ int subs(int ng) const {   // sub-tiles of group ng that exist
+    if (NSUB == 1) return 1;
+    const int left = p.n_tiles - ng * NSUB;
+    return left < NSUB ? left : NSUB;
   }
 };
 
@@ -269,11 +280,15 @@ __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32
   }
 }
 
-template <int EPI, bool STAGED, bool TWO>
+// DUAL (pair mode only): two N sub-tiles share every A stage, three accumulator slots in TMEM
+template <int EPI, bool STAGED, bool TWO, bool DUAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
              const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
              const __grid_constant__ CUtensorMap mapR, const IGemmKParams p) {
+  static_assert(!DUAL || TWO, "sub-tile groups exist in pair mode only");
+  constexpr int NSUB = DUAL ? 2 : 1;
+  constexpr int NACC = DUAL ? 3 : 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve (1024-aligned): [resident B: num_k x bn*128] [ring: stages x (A 16K [+ B bn*128])]
   //                       [staging: EPI_WARPS x npan x 2K] [barriers] [bias x2]
@@ -281,19 +296,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const uint32_t b_chunk_bytes = uint32_t(TWO ? (p.bn >> 1) : p.bn) * 128u;   // a pair CTA stages half of the B tile
   const uint32_t res_bytes = p.resident_b ? uint32_t(p.num_k) * b_chunk_bytes : 0u;
   const uint32_t pair_rank = TWO ? (blockIdx.x & 1u) : 0u;
-  const uint32_t stage_bytes = A_STAGE_BYTES + (p.resident_b ? 0u : b_chunk_bytes);
+  const uint32_t stage_bytes = A_STAGE_BYTES + (p.resident_b ? 0u : uint32_t(NSUB) * b_chunk_bytes);
   const uint32_t ring_base = smem_base + res_bytes;
   const uint32_t stg_base = ring_base + uint32_t(p.stages) * stage_bytes;
   const uint32_t bar_base = stg_base + (STAGED ? uint32_t(EPI_WARPS * p.npan) * PANEL_BYTES : 0u);
   auto full_bar = [&](int s) { return bar_base + 8u * uint32_t(s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * uint32_t(p.stages + s); };
   const uint32_t misc = bar_base + 16u * uint32_t(p.stages);
-  auto acc_full = [&](int b) { return misc + 8u * uint32_t(b); };
-  auto acc_empty = [&](int b) { return misc + 16u + 8u * uint32_t(b); };
-  const uint32_t bres_bar = misc + 32u;
-  const uint32_t tmem_slot = misc + 40u;
-  auto resid_bar = [&](int ew) { return misc + 48u + 8u * uint32_t(ew); };
-  const uint32_t bias_smem = (misc + 48u + 8u * EPI_WARPS + 15u) & ~15u;  // float[2][256]: the tile's bias slice, double buffered
+  auto acc_full = [&](int b) { return misc + 8u * uint32_t(b); };            // [3]
+  auto acc_empty = [&](int b) { return misc + 24u + 8u * uint32_t(b); };      // [3]
+  const uint32_t bres_bar = misc + 48u;
+  const uint32_t tmem_slot = misc + 56u;
+  auto resid_bar = [&](int ew) { return misc + 64u + 8u * uint32_t(ew); };
+  const uint32_t bias_smem = (misc + 64u + 8u * EPI_WARPS + 15u) & ~15u;  // float[3][256]: a sub-tile's bias slice per accumulator slot
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -313,7 +328,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 3; ++b) {
       mbar_init(acc_full(b), 1);
       mbar_init(acc_empty(b), EPI_WARPS * (TWO ? 2 : 1));   // one arrival per epilogue warp (of both CTAs of a pair)
     }
@@ -351,6 +366,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
+        const int subs = sched.subs<NSUB>(nt);
+        const uint32_t tx_bytes = A_STAGE_BYTES + (p.resident_b ? 0u : uint32_t(subs) * b_chunk_bytes);
+        const int brow0 = nt * NSUB * p.bn;   // first weight row of the group
         int tap = 0, ch = 0;
         for (int kt = 0; kt < p.num_k; ++kt) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -358,15 +376,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], cn = n0 + p.tap_dn[tap];
           if (TWO) {
             // both CTAs load (own A rows, own half of B); every byte is counted on the LEADER's full barrier
-            if (pair_rank == 0) mbar_expect_tx(full_bar(stage), 2u * stage_bytes);
+            if (pair_rank == 0) mbar_expect_tx(full_bar(stage), 2u * tx_bytes);
             if (ch < p.chunks0) tma_load_4d_pair(sa, &mapA0, full_bar(stage), ch * BK, cw, chh, cn);
             else                tma_load_4d_pair(sa, &mapA1, full_bar(stage), (ch - p.chunks0) * BK, cw, chh, cn);
-            tma_load_2d_pair(sa + A_STAGE_BYTES, &mapB, full_bar(stage), kt * BK, nt * p.bn + int(pair_rank) * (p.bn >> 1));
+            for (int h = 0; h < subs; ++h)
+              tma_load_2d_pair(sa + A_STAGE_BYTES + uint32_t(h) * b_chunk_bytes, &mapB, full_bar(stage), kt * BK,
+                               brow0 + h * p.bn + int(pair_rank) * (p.bn >> 1));
           } else {
-            mbar_expect_tx(full_bar(stage), stage_bytes);
+            mbar_expect_tx(full_bar(stage), tx_bytes);
             if (ch < p.chunks0) tma_load_4d(sa, &mapA0, full_bar(stage), ch * BK, cw, chh, cn);
             else                tma_load_4d(sa, &mapA1, full_bar(stage), (ch - p.chunks0) * BK, cw, chh, cn);
-            if (!p.resident_b) tma_load_2d(sa + A_STAGE_BYTES, &mapB, full_bar(stage), kt * BK, nt * p.bn);
+            if (!p.resident_b)
+              for (int h = 0; h < subs; ++h)
+                tma_load_2d(sa + A_STAGE_BYTES + uint32_t(h) * b_chunk_bytes, &mapB, full_bar(stage), kt * BK, brow0 + h * p.bn);
           }
           if (++ch == cpt) { ch = 0; ++tap; }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -380,31 +402,49 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       uint32_t phase = 0;
       int mt, nt;
       bool b_ready = !p.resident_b;
+      int acc_cnt = 0;   // accumulator ring position (sub-tiles issued so far)
       for (int i = 0; sched.get(i, mt, nt); ++i) {
-        const int buf = i & 1;
-        const uint32_t use = uint32_t(i >> 1);
-        mbar_wait(acc_empty(buf), (use & 1u) ^ 1u);   // epilogue drained this accumulator (first two uses pass)
+        const bool dual = DUAL && sched.subs<NSUB>(nt) > 1;
+        // (scalars, not arrays: a dynamically indexed array would live in local memory on the issue path)
+        const int slot0 = acc_cnt % NACC, slot1 = (acc_cnt + 1) % NACC;
+        mbar_wait(acc_empty(slot0), (uint32_t(acc_cnt / NACC) & 1u) ^ 1u);   // epilogue drained the slot (first round passes)
+        if (DUAL && dual) mbar_wait(acc_empty(slot1), (uint32_t((acc_cnt + 1) / NACC) & 1u) ^ 1u);
+        const uint32_t tacc0 = tmem_base + uint32_t(slot0) * p.acc_stride;
+        const uint32_t tacc1 = tmem_base + uint32_t(slot1) * p.acc_stride;
         tc_fence_after();
         if (!b_ready) { mbar_wait(bres_bar, 0); b_ready = true; }
-        const uint32_t tacc = tmem_base + uint32_t(buf) * p.acc_stride;
-        for (int kt = 0; kt < p.num_k; ++kt) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = ring_base + uint32_t(stage) * stage_bytes;
-          const uint32_t sb = p.resident_b ? (smem_base + uint32_t(kt) * b_chunk_bytes) : (sa + A_STAGE_BYTES);
-          const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = make_sdesc_sw128(sb, 16, 1024);
+        // K loop; the sub-tile count is hoisted out of the issue loop (a branch per MMA costs ~20 % on this thread)
+        auto k_loop = [&](auto both_tag) {
+          constexpr bool BOTH = decltype(both_tag)::value;
+          for (int kt = 0; kt < p.num_k; ++kt) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = ring_base + uint32_t(stage) * stage_bytes;
+            const uint32_t sb = p.resident_b ? (smem_base + uint32_t(kt) * b_chunk_bytes) : (sa + A_STAGE_BYTES);
+            const uint64_t adesc = make_sdesc_sw128(sa, 16, 1024);
+            const uint64_t bdesc0 = make_sdesc_sw128(sb, 16, 1024);
+            const uint64_t bdesc1 = make_sdesc_sw128(sb + b_chunk_bytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
-            if (TWO) umma_bf16_pair(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), p.idesc, (kt | k) != 0);
-            else     umma_bf16(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), p.idesc, (kt | k) != 0);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
+              const uint32_t acc = (kt | k) != 0;
+              if (TWO) {
+                umma_bf16_pair(tacc0, adesc + uint64_t(2 * k), bdesc0 + uint64_t(2 * k), p.idesc, acc);
+                if (BOTH) umma_bf16_pair(tacc1, adesc + uint64_t(2 * k), bdesc1 + uint64_t(2 * k), p.idesc, acc);   // reuses the A stage
+              } else {
+                umma_bf16(tacc0, adesc + uint64_t(2 * k), bdesc0 + uint64_t(2 * k), p.idesc, acc);
+              }
+            }
+            // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+            if (TWO) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
-          if (TWO) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-        }
-        if (TWO) umma_commit_pair(acc_full(buf)); else umma_commit(acc_full(buf));  // accumulator complete
+        };
+        if (DUAL && dual) k_loop(std::true_type{}); else k_loop(std::false_type{});
+        // accumulators complete
+        if (TWO) umma_commit_pair(acc_full(slot0)); else umma_commit(acc_full(slot0));
+        if (DUAL && dual) umma_commit_pair(acc_full(slot1));   // (cta_group::2 instructions only in the pair instantiations)
+        acc_cnt += (DUAL && dual) ? 2 : 1;
       }
     }
   } else {
@@ -424,10 +464,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
     constexpr bool GEGLU = (EPI == EPI_GEGLU);
     const int ocols = GEGLU ? (p.bn >> 1) : p.bn;   // output columns per tile
-    int mt, nt;
-    for (int i = 0; sched.get(i, mt, nt); ++i) {
-      const int buf = i & 1;
-      const uint32_t use = uint32_t(i >> 1);
+    int mt, ng;
+    int acc_cnt = 0;
+    for (int i = 0; sched.get(i, mt, ng); ++i)
+    for (int sub = 0, subs = sched.subs<NSUB>(ng); sub < subs; ++sub, ++acc_cnt) {
+      const int nt = ng * NSUB + sub;
+      const int buf = acc_cnt % NACC;
+      const uint32_t use = uint32_t(acc_cnt / NACC);
       const int tw = mt % p.tiles_w;
       const int th = (mt / p.tiles_w) % p.tiles_h;
       const int tn = mt / (p.tiles_w * p.tiles_h);
@@ -585,8 +628,13 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.two = two ? 1 : 0;
   p.m_pairs = (p.m_tiles + 1) / 2;
   p.idesc = make_idesc_f16(two ? 2 * BM : BM, d->bn, 0, 0);
-  p.acc_stride = (uint32_t)pow2_cols(d->bn);
-  p.tmem_cols = 2u * p.acc_stride;   // two accumulators: <= 512 columns
+  // N sub-tile groups: in pair mode two N tiles share every A stage when three accumulators fit TMEM (bn <= 160);
+  // the shared-memory fill per flop -- what bounds the K >= 1152 launches -- drops from (A + B/2) to (A/2 + B/2) per tile
+  p.nsub = (two && d->nsub != 1 && p.n_tiles >= 2 && 3 * d->bn <= 512) ? 2 : 1;
+  p.nacc = p.nsub == 2 ? 3 : 2;
+  p.n_groups = (p.n_tiles + p.nsub - 1) / p.nsub;
+  p.acc_stride = p.nsub == 2 ? (uint32_t)d->bn : (uint32_t)pow2_cols(d->bn);
+  p.tmem_cols = (uint32_t)pow2_cols(int(p.nacc * p.acc_stride));   // <= 512 columns
   p.mode = d->mode; p.act = d->act; p.out_f32 = d->out_f32;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_ld = d->rowbias_ld;
   p.bias_len = int(d->mode == CB_EPI_GEGLU ? 2 * d->cout : d->cout);
@@ -642,7 +690,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
 
   // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
   //      that N tile gets several M tiles; otherwise stream A and B through the ring
-  const size_t fixed = 1024 + 16 * 12 + 128 + 16 + sizeof(float) * 512 + 64;
+  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 768 + 64;
   const size_t b_chunk = (size_t)(two ? d->bn / 2 : d->bn) * 128;
   const size_t res_bytes = (size_t)num_k * b_chunk;
   int resident = 0;
@@ -657,7 +705,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     }
   }
   p.resident_b = resident;
-  const size_t stage_bytes = A_STAGE_BYTES + (resident ? 0 : b_chunk);
+  const size_t stage_bytes = A_STAGE_BYTES + (resident ? 0 : (size_t)p.nsub * b_chunk);
   int stages = d->stages;
   if (stages <= 0) {
     stages = int(((size_t)SMEM_LIMIT - fixed - staging - (resident ? res_bytes : 0)) / stage_bytes);
@@ -668,36 +716,43 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   const size_t smem = (resident ? res_bytes : 0) + (size_t)stages * stage_bytes + staging + fixed;
   CB_REQUIRE(smem <= (size_t)SMEM_LIMIT, "cb_igemm: tile needs %zu bytes of shared memory", smem);
   if (two) {
-    const long long total = (long long)p.m_pairs * p.n_tiles;
+    const long long total = (long long)p.m_pairs * p.n_groups;
     const long long clusters = total < g_num_sms / 2 ? total : g_num_sms / 2;
     grid = (unsigned)(2 * clusters);
   } else if (!resident) {
-    const long long total = (long long)p.m_tiles * p.n_tiles;
+    const long long total = (long long)p.m_tiles * p.n_groups;
     grid = (unsigned)(total < g_num_sms ? total : g_num_sms);
   }
 
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const IGemmKParams);
-  // [pair][staged][epilogue]
-  static const KernelFn kernels[2][2][EPI_COUNT] = {
-      {{igemm_kernel<EPI_GENERIC, false, false>, igemm_kernel<EPI_PLAIN, false, false>, igemm_kernel<EPI_RES, false, false>,
-        igemm_kernel<EPI_ROWBIAS, false, false>, nullptr, igemm_kernel<EPI_HEADS, false, false>},
-       {nullptr, igemm_kernel<EPI_PLAIN, true, false>, igemm_kernel<EPI_RES, true, false>,
-        igemm_kernel<EPI_ROWBIAS, true, false>, igemm_kernel<EPI_GEGLU, true, false>, nullptr}},
-      {{igemm_kernel<EPI_GENERIC, false, true>, igemm_kernel<EPI_PLAIN, false, true>, igemm_kernel<EPI_RES, false, true>,
-        igemm_kernel<EPI_ROWBIAS, false, true>, nullptr, igemm_kernel<EPI_HEADS, false, true>},
-       {nullptr, igemm_kernel<EPI_PLAIN, true, true>, igemm_kernel<EPI_RES, true, true>,
-        igemm_kernel<EPI_ROWBIAS, true, true>, igemm_kernel<EPI_GEGLU, true, true>, nullptr}}};
+  // [single | pair | pair with N sub-tile groups][staged][epilogue]
+  static const KernelFn kernels[3][2][EPI_COUNT] = {
+      {{igemm_kernel<EPI_GENERIC, false, false, false>, igemm_kernel<EPI_PLAIN, false, false, false>,
+        igemm_kernel<EPI_RES, false, false, false>, igemm_kernel<EPI_ROWBIAS, false, false, false>, nullptr,
+        igemm_kernel<EPI_HEADS, false, false, false>},
+       {nullptr, igemm_kernel<EPI_PLAIN, true, false, false>, igemm_kernel<EPI_RES, true, false, false>,
+        igemm_kernel<EPI_ROWBIAS, true, false, false>, igemm_kernel<EPI_GEGLU, true, false, false>, nullptr}},
+      {{igemm_kernel<EPI_GENERIC, false, true, false>, igemm_kernel<EPI_PLAIN, false, true, false>,
+        igemm_kernel<EPI_RES, false, true, false>, igemm_kernel<EPI_ROWBIAS, false, true, false>, nullptr,
+        igemm_kernel<EPI_HEADS, false, true, false>},
+       {nullptr, igemm_kernel<EPI_PLAIN, true, true, false>, igemm_kernel<EPI_RES, true, true, false>,
+        igemm_kernel<EPI_ROWBIAS, true, true, false>, igemm_kernel<EPI_GEGLU, true, true, false>, nullptr}},
+      {{igemm_kernel<EPI_GENERIC, false, true, true>, igemm_kernel<EPI_PLAIN, false, true, true>,
+        igemm_kernel<EPI_RES, false, true, true>, igemm_kernel<EPI_ROWBIAS, false, true, true>, nullptr,
+        igemm_kernel<EPI_HEADS, false, true, true>},
+       {nullptr, igemm_kernel<EPI_PLAIN, true, true, true>, igemm_kernel<EPI_RES, true, true, true>,
+        igemm_kernel<EPI_ROWBIAS, true, true, true>, igemm_kernel<EPI_GEGLU, true, true, true>, nullptr}}};
   static thread_local bool configured = false;
   if (!configured) {
-    for (int tw = 0; tw < 2; ++tw)
+    for (int tw = 0; tw < 3; ++tw)
       for (int st = 0; st < 2; ++st)
         for (int i = 0; i < EPI_COUNT; ++i)
           if (kernels[tw][st][i])
             CB_CHECK_CUDA(cudaFuncSetAttribute(kernels[tw][st][i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     configured = true;
   }
-  const KernelFn kfn = kernels[two ? 1 : 0][staged ? 1 : 0][epi];
+  const KernelFn kfn = kernels[two ? (p.nsub == 2 ? 2 : 1) : 0][staged ? 1 : 0][epi];
   CB_REQUIRE(kfn != nullptr, "cb_igemm: internal: no kernel for epilogue %d staged %d", epi, (int)staged);
   if (two) {
     cudaLaunchConfig_t lc{};

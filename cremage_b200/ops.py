@@ -175,19 +175,27 @@ def choose_bn(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
     return best[1]
 
 
-def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
-    """N tile in CTA-pair mode (74 clusters, each a 256-row tile): wide tiles first -- the B half per CTA shrinks the
-    shared-memory fill per flop, which is what bounds the large-K convolutions."""
+def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32) -> Tuple[int, int]:
+    """(bn, nsub) in CTA-pair mode (74 clusters, each a 256-row tile).  nsub = 2: two N tiles share every A stage
+    (cb_igemm's sub-tile groups, 3 * bn <= 512).  Cost of a round ~ MMA columns of the tile group; tiles narrower
+    than 256 columns are shared-memory-fill bound (x1.25), and below 128 columns the single issuing thread cannot keep
+    the tensor core fed, so narrower tiles cost as much as 128."""
     best = None
     m_pairs = (m_tiles + 1) // 2
     for bn in (256, 160, 128, 64, 32):
         if bn % multiple:
             continue
-        tiles = m_pairs * (-(-cout_cols // bn))
-        cost = (-(-tiles // (NUM_SMS // 2))) * (bn + 16)
-        if best is None or cost < best[0]:
-            best = (cost, bn)
-    return best[1]
+        n_tiles = -(-cout_cols // bn)
+        for nsub in (2, 1):
+            if nsub == 2 and not (3 * bn <= 512 and n_tiles >= 2):
+                continue
+            groups = -(-n_tiles // nsub)
+            width = nsub * bn
+            per = (nsub * max(bn, 128) + 16) * (1.0 if width >= 256 else 1.25)
+            cost = (-(-(m_pairs * groups) // (NUM_SMS // 2))) * per
+            if best is None or cost < best[0]:
+                best = (cost, bn, nsub)
+    return best[1], best[2]
 
 
 import os as _os
@@ -224,7 +232,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
           mode: int = EPI_LINEAR, out: Optional[torch.Tensor] = None, out_f32: bool = False, out_ld: Optional[int] = None,
           out_scale: float = 1.0, heads: Optional[Tuple[int, int, int, int, int]] = None, bn: Optional[int] = None,
-          stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None) -> torch.Tensor:
+          stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None, nsub: int = 0) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
@@ -251,7 +259,12 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         if mode == EPI_GEGLU:
             pair = bool(GEGLU_PAIR) and m_tiles >= PAIR_MIN_M_TILES
     if bn is None:
-        bn = (choose_bn_pair if pair else choose_bn)(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
+        if pair:
+            bn, auto_nsub = choose_bn_pair(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
+            if nsub == 0:
+                nsub = auto_nsub
+        else:
+            bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
     if out is None:
         ld = out_ld if out_ld is not None else cout
         out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
@@ -283,7 +296,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     d.out_scale = out_scale
     if heads is not None:
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
-    d.bn, d.stages, d.epilogue, d.cta_pair = bn, stages, epilogue, int(bool(pair))
+    d.bn, d.stages, d.epilogue, d.cta_pair, d.nsub = bn, stages, epilogue, int(bool(pair)), nsub
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
             flops=2.0 * rows * len(dw) * (c0 + c1) * ncols,

@@ -86,6 +86,7 @@ typedef struct cb_igemm_desc {
   int stages;            /* smem pipeline depth, 0 = auto */
   int epilogue;          /* CB_EPILOGUE_* (tuning / test knob; results are identical) */
   int cta_pair;          /* 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2, cluster of 2); bn % 32 == 0 */
+  int nsub;              /* pair mode: 0 = auto (two N tiles share each A stage when 3 * bn <= 512), 1 = never */
 } cb_igemm_desc;
 
 int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);

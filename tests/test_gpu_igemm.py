@@ -224,3 +224,24 @@ def test_cta_pair_gemm(m, k, n):
     torch.cuda.synchronize()
     assert torch.equal(o1, o2)
     _close(o2[:2048], a[:2048].float().cpu() @ w.to(ACT).float().t() + b.cpu())
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", [(2, 16, 16, 64, 320, 160), (1, 32, 32, 128, 224, 32), (3, 8, 8, 64, 96, 32),
+                                               (1, 64, 64, 64, 640, 160), (2, 16, 16, 64, 160, 32)])
+def test_cta_pair_dual_n_subtiles_equal_single(n, h, w, cin, cout, bn):
+    """Pair mode with two N sub-tiles per A stage (3-slot TMEM accumulator ring), odd sub-tile counts included."""
+    ops = _ops()
+    x = _rand(n, cin, h, w, seed=5).to(ACT)
+    wt = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=6)
+    b = _rand(cout, seed=7).cuda()
+    emb = _rand(n, cout, seed=8).cuda()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wp = ops.pack_weight(wt).cuda()
+    single = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, rowbias=emb, pair=False)
+    dual = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, rowbias=emb, pair=True, bn=bn)
+    nodual = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, rowbias=emb, pair=True, bn=bn, nsub=1)
+    staged = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, rowbias=emb, pair=True, bn=bn, epilogue=ops.EPILOGUE_STAGED)
+    torch.cuda.synchronize()
+    assert torch.equal(single, dual) and torch.equal(single, nodual) and torch.equal(single, staged)
+    want = F.conv2d(x.float(), wt.to(ACT).float(), b.cpu(), padding=1) + emb.cpu()[:, :, None, None]
+    _close(dual.view(n, h, w, cout).permute(0, 3, 1, 2), want)
