@@ -21,83 +21,151 @@ __global__ void cfg_scale_input_kernel(const float4* __restrict__ x, long long n
   }
 }
 
+// ---- vector access: V = 4 (16-byte loads / stores; every pointer 16-byte aligned and total % 4 == 0) or V = 1 ----
+template <int V> struct Vf { float v[V]; };
+template <int V> CB_DEVINL Vf<V> ldv(const float* __restrict__ p, long long i) {
+  Vf<V> r;
+  if (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+    r.v[0] = t.x; r.v[1 % V] = t.y; r.v[2 % V] = t.z; r.v[3 % V] = t.w;
+  } else {
+    r.v[0] = __ldg(p + i);
+  }
+  return r;
+}
+template <int V> CB_DEVINL void stv(float* __restrict__ p, long long i, const Vf<V>& r) {
+  if (V == 4) reinterpret_cast<float4*>(p)[i] = make_float4(r.v[0], r.v[1 % V], r.v[2 % V], r.v[3 % V]);
+  else p[i] = r.v[0];
+}
+#define CB_VEC_LOOP(i, nvec) \
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (nvec); i += (long long)gridDim.x * blockDim.x)
+
 // out = a * x + b * y (y may be null)
-__global__ void axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float b, long long total,
+template <int V>
+__global__ void axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float b, long long nvec,
                              float* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    out[i] = y ? (a * x[i] + b * y[i]) : a * x[i];
+  CB_VEC_LOOP(i, nvec) {
+    const Vf<V> xv = ldv<V>(x, i);
+    Vf<V> o;
+    if (y) {
+      const Vf<V> yv = ldv<V>(y, i);
+#pragma unroll
+      for (int e = 0; e < V; ++e) o.v[e] = a * xv.v[e] + b * yv.v[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) o.v[e] = a * xv.v[e];
+    }
+    stv<V>(out, i, o);
+  }
 }
 
 // out = u + s * (c - u)
-__global__ void cfg_mix_kernel(const float* __restrict__ u, const float* __restrict__ c, float s, long long total,
+template <int V>
+__global__ void cfg_mix_kernel(const float* __restrict__ u, const float* __restrict__ c, float s, long long nvec,
                                float* __restrict__ out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const float uu = u[i];
-    out[i] = uu + s * (c[i] - uu);
+  CB_VEC_LOOP(i, nvec) {
+    const Vf<V> uv = ldv<V>(u, i), cv = ldv<V>(c, i);
+    Vf<V> o;
+#pragma unroll
+    for (int e = 0; e < V; ++e) o.v[e] = uv.v[e] + s * (cv.v[e] - uv.v[e]);
+    stv<V>(out, i, o);
   }
 }
 
 // guided denoised prediction from the two eps halves, or pass-through when `a` already is the denoised tensor
-__device__ __forceinline__ float guided_denoised(float xv, const float* a, const float* b, long long i, float cfg,
-                                                 float sigma, int is_denoised) {
-  if (is_denoised) return a[i];
+__device__ __forceinline__ float guided_denoised(float xv, float a, float b, float cfg, float sigma, int is_denoised) {
+  if (is_denoised) return a;
   // CompVisDenoiser on each half: denoised = input + eps * c_out, c_out = -sigma
-  const float du = xv + a[i] * (-sigma);
-  const float dc = xv + b[i] * (-sigma);
+  const float du = xv + a * (-sigma);
+  const float dc = xv + b * (-sigma);
   return du + cfg * (dc - du);
 }
 
 struct EulerA { float cfg, sigma, sigma_down, sigma_up; int is_denoised; };
+template <int V>
 __global__ void step_euler_ancestral_kernel(const float* __restrict__ x, const float* __restrict__ eu,
                                             const float* __restrict__ ec, const float* __restrict__ noise,
-                                            long long total, EulerA a, float* __restrict__ x_out,
+                                            long long nvec, EulerA a, float* __restrict__ x_out,
                                             float* __restrict__ den_out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const float xv = x[i];
-    const float den = guided_denoised(xv, eu, ec, i, a.cfg, a.sigma, a.is_denoised);
-    const float d = (xv - den) / a.sigma;
-    float xn = xv + d * (a.sigma_down - a.sigma);
-    if (noise) xn = xn + noise[i] * a.sigma_up;
-    x_out[i] = xn;
-    if (den_out) den_out[i] = den;
+  CB_VEC_LOOP(i, nvec) {
+    const Vf<V> xv = ldv<V>(x, i), av = ldv<V>(eu, i);
+    Vf<V> bv = av, nz = av, xn, dn;
+    if (!a.is_denoised) bv = ldv<V>(ec, i);
+    if (noise) nz = ldv<V>(noise, i);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float den = guided_denoised(xv.v[e], av.v[e], bv.v[e], a.cfg, a.sigma, a.is_denoised);
+      const float d = (xv.v[e] - den) / a.sigma;
+      float r = xv.v[e] + d * (a.sigma_down - a.sigma);
+      if (noise) r = r + nz.v[e] * a.sigma_up;
+      xn.v[e] = r;
+      dn.v[e] = den;
+    }
+    stv<V>(x_out, i, xn);
+    if (den_out) stv<V>(den_out, i, dn);
   }
 }
 
 struct Dpm2m { float cfg, sigma, ratio, em1, c_new, c_old; int is_denoised; };
+template <int V>
 __global__ void step_dpmpp_2m_kernel(const float* __restrict__ x, const float* __restrict__ eu,
-                                     const float* __restrict__ ec, const float* __restrict__ old_den, long long total,
+                                     const float* __restrict__ ec, const float* __restrict__ old_den, long long nvec,
                                      Dpm2m a, float* __restrict__ x_out, float* __restrict__ den_out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const float xv = x[i];
-    const float den = guided_denoised(xv, eu, ec, i, a.cfg, a.sigma, a.is_denoised);
-    float dd = den;
-    if (old_den) dd = a.c_new * den - a.c_old * old_den[i];
-    x_out[i] = a.ratio * xv - a.em1 * dd;
-    if (den_out) den_out[i] = den;
+  CB_VEC_LOOP(i, nvec) {
+    const Vf<V> xv = ldv<V>(x, i), av = ldv<V>(eu, i);
+    Vf<V> bv = av, ov = av, xn, dn;
+    if (!a.is_denoised) bv = ldv<V>(ec, i);
+    if (old_den) ov = ldv<V>(old_den, i);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float den = guided_denoised(xv.v[e], av.v[e], bv.v[e], a.cfg, a.sigma, a.is_denoised);
+      float dd = den;
+      if (old_den) dd = a.c_new * den - a.c_old * ov.v[e];
+      xn.v[e] = a.ratio * xv.v[e] - a.em1 * dd;
+      dn.v[e] = den;
+    }
+    stv<V>(x_out, i, xn);
+    if (den_out) stv<V>(den_out, i, dn);
   }
 }
 
 struct Ddim { float cfg, sqrt_at, sqrt_1mat, sqrt_aprev, dir_coef, sigma_t; };
+template <int V>
 __global__ void step_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eu, const float* __restrict__ ec,
-                                 const float* __restrict__ noise, long long total, Ddim a, float* __restrict__ x_out,
+                                 const float* __restrict__ noise, long long nvec, Ddim a, float* __restrict__ x_out,
                                  float* __restrict__ x0_out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const float xv = x[i];
-    const float u = eu[i];
-    const float e = u + a.cfg * (ec[i] - u);
-    const float pred_x0 = (xv - a.sqrt_1mat * e) / a.sqrt_at;
-    const float dir = a.dir_coef * e;
-    float xn = a.sqrt_aprev * pred_x0 + dir;
-    // the reference adds sigma_t * noise unconditionally (identically zero when eta == 0)
-    xn = xn + (noise ? a.sigma_t * noise[i] : 0.f);
-    x_out[i] = xn;
-    if (x0_out) x0_out[i] = pred_x0;
+  CB_VEC_LOOP(i, nvec) {
+    const Vf<V> xv = ldv<V>(x, i), uv = ldv<V>(eu, i), cv = ldv<V>(ec, i);
+    Vf<V> nz = uv, xn, x0;
+    if (noise) nz = ldv<V>(noise, i);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float ee = uv.v[e] + a.cfg * (cv.v[e] - uv.v[e]);
+      const float pred_x0 = (xv.v[e] - a.sqrt_1mat * ee) / a.sqrt_at;
+      const float dir = a.dir_coef * ee;
+      float r = a.sqrt_aprev * pred_x0 + dir;
+      // the reference adds sigma_t * noise unconditionally (identically zero when eta == 0)
+      r = r + (noise ? a.sigma_t * nz.v[e] : 0.f);
+      xn.v[e] = r;
+      x0.v[e] = pred_x0;
+    }
+    stv<V>(x_out, i, xn);
+    if (x0_out) stv<V>(x0_out, i, x0);
   }
+}
+
+// 16-byte vector path when every pointer allows it
+template <typename... P>
+static bool vec4_ok(long long total, P... ptrs) {
+  const void* arr[] = {static_cast<const void*>(ptrs)...};
+  uintptr_t bits = 0;
+  for (const void* q : arr) bits |= reinterpret_cast<uintptr_t>(q);   // null pointers contribute nothing
+  return total % 4 == 0 && (bits & 15u) == 0;
 }
 
 static unsigned ew_grid(long long total) {
   long long g = (total + 255) / 256;
-  if (g > 148LL * 8) g = 148LL * 8;
+  if (g > 148LL * 16) g = 148LL * 16;
   if (g < 1) g = 1;
   return (unsigned)g;
 }
@@ -120,7 +188,8 @@ extern "C" int cb_cfg_scale_input(const float* x, int64_t per_batch, int64_t b, 
 extern "C" int cb_axpby_f32(const float* x, float a, const float* y, float b, int64_t count, float* out,
                             cudaStream_t stream) {
   CB_REQUIRE(x && out && count > 0, "cb_axpby_f32: bad arguments");
-  axpby_kernel<<<ew_grid(count), 256, 0, stream>>>(x, a, y, b, count, out);
+  if (vec4_ok(count, x, y, out)) axpby_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(x, a, y, b, count / 4, out);
+  else axpby_kernel<1><<<ew_grid(count), 256, 0, stream>>>(x, a, y, b, count, out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -129,7 +198,8 @@ extern "C" int cb_axpby_f32(const float* x, float a, const float* y, float b, in
 extern "C" int cb_cfg_mix_f32(const float* uncond, const float* cond, float scale, int64_t count, float* out,
                               cudaStream_t stream) {
   CB_REQUIRE(uncond && cond && out && count > 0, "cb_cfg_mix_f32: bad arguments");
-  cfg_mix_kernel<<<ew_grid(count), 256, 0, stream>>>(uncond, cond, scale, count, out);
+  if (vec4_ok(count, uncond, cond, out)) cfg_mix_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(uncond, cond, scale, count / 4, out);
+  else cfg_mix_kernel<1><<<ew_grid(count), 256, 0, stream>>>(uncond, cond, scale, count, out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -141,7 +211,10 @@ extern "C" int cb_step_euler_ancestral(const float* x, const float* eps_u, const
                                        cudaStream_t stream) {
   CB_REQUIRE(x && eps_u && x_out && count > 0 && (is_denoised || eps_c), "cb_step_euler_ancestral: bad arguments");
   EulerA a{cfg_scale, sigma, sigma_down, sigma_up, is_denoised};
-  step_euler_ancestral_kernel<<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, noise, count, a, x_out, denoised_out);
+  if (vec4_ok(count, x, eps_u, eps_c, noise, x_out, denoised_out))
+    step_euler_ancestral_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(x, eps_u, eps_c, noise, count / 4, a, x_out, denoised_out);
+  else
+    step_euler_ancestral_kernel<1><<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, noise, count, a, x_out, denoised_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -153,7 +226,10 @@ extern "C" int cb_step_dpmpp_2m(const float* x, const float* eps_u, const float*
                                 cudaStream_t stream) {
   CB_REQUIRE(x && eps_u && x_out && count > 0 && (is_denoised || eps_c), "cb_step_dpmpp_2m: bad arguments");
   Dpm2m a{cfg_scale, sigma, ratio, em1, c_new, c_old, is_denoised};
-  step_dpmpp_2m_kernel<<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, old_denoised, count, a, x_out, denoised_out);
+  if (vec4_ok(count, x, eps_u, eps_c, old_denoised, x_out, denoised_out))
+    step_dpmpp_2m_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(x, eps_u, eps_c, old_denoised, count / 4, a, x_out, denoised_out);
+  else
+    step_dpmpp_2m_kernel<1><<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, old_denoised, count, a, x_out, denoised_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -164,7 +240,10 @@ extern "C" int cb_step_ddim(const float* x, const float* eps_u, const float* eps
                             float sigma_t, float* x_out, float* pred_x0_out, cudaStream_t stream) {
   CB_REQUIRE(x && eps_u && eps_c && x_out && count > 0, "cb_step_ddim: bad arguments");
   Ddim a{cfg_scale, sqrt_at, sqrt_one_minus_at, sqrt_aprev, dir_coef, sigma_t};
-  step_ddim_kernel<<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, noise, count, a, x_out, pred_x0_out);
+  if (vec4_ok(count, x, eps_u, eps_c, noise, x_out, pred_x0_out))
+    step_ddim_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(x, eps_u, eps_c, noise, count / 4, a, x_out, pred_x0_out);
+  else
+    step_ddim_kernel<1><<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, noise, count, a, x_out, pred_x0_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

@@ -129,6 +129,30 @@ def bench_norm(B, iters, warm):
         print(f"{name:22s} elems={rows * c / 1e6:8.1f} M: {ms * 1e3:9.1f} us  {by / ms / 1e6:8.1f} GB/s  {by / ms / 1e6 / bw_peak:6.1%} of HBM peak")
 
 
+def bench_sampler(iters, warm):
+    """Per-step latent update kernels (fused CFG mix + update) at sizes where bandwidth, not launch latency, decides:
+    algorithmic bytes = 4 B x (streams read + written) per element."""
+    _, bw_peak = peaks()
+    print("== sampler step kernels (fp32 latents) ==")
+    for logn in (14 + 3, 22, 24, 26):   # 2^17 = batch 8 of 4x64x64; the large ones measure bandwidth
+        b = 8
+        per = (1 << logn) // b
+        x = torch.randn(b, per, device="cuda")
+        eps2 = torch.randn(2 * b, per, device="cuda")
+        noise = torch.randn(b, per, device="cuda")
+        old = torch.randn(b, per, device="cuda")
+        cases = [
+            ("euler_ancestral (x, eps_u, eps_c, noise -> x)", 5, lambda: ops.step_euler_ancestral(x, eps2, noise, 7.5, 5.0, 3.0, 2.0)),
+            ("dpmpp_2m (x, eps_u, eps_c, old -> x, denoised)", 6, lambda: ops.step_dpmpp_2m(x, eps2, old, 7.5, 5.0, 0.7, -0.3, 1.5, 0.5)),
+            ("ddim (x, eps_u, eps_c -> x, pred_x0)", 5, lambda: ops.step_ddim(x, eps2, None, 7.5, 0.9, 0.43, 0.95, 0.3, 0.0)),
+            ("cfg_mix (u, c -> out)", 3, lambda: ops.cfg_mix(eps2[:b], eps2[b:], 7.5)),
+        ]
+        for name, streams, fn in cases:
+            ms = timeit(fn, iters, warm)
+            by = 4.0 * streams * (1 << logn)
+            print(f"{name:52s} elems=2^{logn}: {ms * 1e3:9.1f} us  {by / ms / 1e6:8.1f} GB/s  {by / ms / 1e6 / bw_peak:6.1%} of HBM peak")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="all")
@@ -143,3 +167,5 @@ if __name__ == "__main__":
         bench_igemm(a.batch, a.iters, a.warm, a.filter)
     if a.only in ("all", "norm"):
         bench_norm(a.batch, a.iters, a.warm)
+    if a.only in ("all", "sampler"):
+        bench_sampler(a.iters, a.warm)
