@@ -66,6 +66,7 @@ SIGNATURES = {
     "cb_timestep_embedding": [_vp, _i64, _int, _vp, _vp, _vp],
     "cb_conv3x3_small_cin": [_vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _i64, _vp, _vp],
     "cb_silu_add": [_vp, _vp, _i64, _vp, _vp],
+    "cb_diag_gaussian": [_vp, _vp, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp],
     "cb_cfg_scale_input": [_vp, _i64, _i64, _f32, _vp, _vp],
     "cb_axpby_f32": [_vp, _f32, _vp, _f32, _i64, _vp, _vp],
     "cb_cfg_mix_f32": [_vp, _vp, _f32, _i64, _vp, _vp],

@@ -183,6 +183,24 @@ __global__ void silu_add_kernel(const act_t* __restrict__ x, const act_t* __rest
   out[i] = to_act(silu_f(v));
 }
 
+// DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-37) from the encoder's moments
+// [n][2c][hw] fp32 NCHW: mean = first c channels, logvar = clamp(last c, -30, 20), std = exp(0.5 logvar),
+// sample = mean + std * noise  (noise = the caller's torch.randn draw; null -> sample = mean, the mode)
+__global__ void diag_gaussian_kernel(const float* __restrict__ moments, const float* __restrict__ noise, long long n,
+                                     long long c, long long hw, float scale, float* __restrict__ mean_out,
+                                     float* __restrict__ std_out, float* __restrict__ sample_out) {
+  const long long total = n * c * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / (c * hw), rem = i - img * (c * hw);
+    const float mean = moments[img * 2 * c * hw + rem];
+    const float logvar = fminf(fmaxf(moments[img * 2 * c * hw + c * hw + rem], -30.f), 20.f);
+    const float sd = expf(0.5f * logvar);
+    if (mean_out) mean_out[i] = mean;
+    if (std_out) std_out[i] = sd;
+    if (sample_out) sample_out[i] = scale * (noise ? mean + sd * noise[i] : mean);
+  }
+}
+
 // bilinear upsample by an integer factor, align_corners=False (F.interpolate semantics: src = (dst + 0.5) / scale - 0.5,
 // clamped at 0; neighbours clamped at the last index), fp32 planes [planes][h][w] -> [planes][h*f][w*f]
 __global__ void bilinear_upsample_kernel(const float* __restrict__ src, long long planes, int h, int w, int f,
@@ -332,6 +350,16 @@ extern "C" int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64
 extern "C" int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream) {
   CB_REQUIRE(x && out && count > 0, "cb_silu_add: bad arguments");
   silu_add_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>((const act_t*)x, (const act_t*)add, count, (act_t*)out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_diag_gaussian(const float* moments, const float* noise, int64_t n, int64_t c, int64_t hw, float scale,
+                                float* mean_out, float* std_out, float* sample_out, cudaStream_t stream) {
+  CB_REQUIRE(moments && n > 0 && c > 0 && hw > 0 && (mean_out || std_out || sample_out), "cb_diag_gaussian: bad arguments");
+  diag_gaussian_kernel<<<grid_for(n * c * hw, 256), 256, 0, stream>>>(moments, noise, n, c, hw, scale == 0.f ? 1.f : scale,
+                                                                     mean_out, std_out, sample_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

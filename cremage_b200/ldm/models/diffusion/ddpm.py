@@ -80,5 +80,18 @@ class LatentDiffusion(nn.Module):
             raise RuntimeError("LatentDiffusion was built without a first stage model")
         return self.first_stage_model.decode_first_stage(z, self.scale_factor, to_uint8=to_uint8)
 
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        """ddpm.py:861-899 (live branch :899: self.first_stage_model.encode(x)): the first stage's posterior."""
+        if self.first_stage_model is None:
+            raise RuntimeError("LatentDiffusion was built without a first stage model")
+        return self.first_stage_model.encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior, noise=None):
+        """ddpm.py:575-582: scale_factor * posterior.sample() (a tensor passes through scaled)."""
+        if isinstance(encoder_posterior, torch.Tensor):
+            return self.scale_factor * encoder_posterior
+        return encoder_posterior.sample(noise=noise, scale=self.scale_factor)
+
     def get_learned_conditioning(self, c):
         raise NotImplementedError("cremage_b200: the text encoder is outside the hot-path scope; pass context tensors")

@@ -12,7 +12,9 @@ import numpy as np
 import torch
 
 from ....k_diffusion.external import CompVisDenoiser
-from ....k_diffusion.sampling import get_sigmas_karras, sample_dpmpp_2m, sample_euler, sample_euler_ancestral
+from ....k_diffusion.sampling import (get_sigmas_karras, sample_dpm_2, sample_dpm_2_ancestral, sample_dpmpp_2m,
+                                         sample_dpmpp_2s_ancestral, sample_euler, sample_euler_ancestral, sample_heun,
+                                         sample_lms)
 from .ldm_wrapper_for_k_diffusion import LDMWrapperForKDiffusion
 
 
@@ -120,3 +122,53 @@ class Dpmpp2mSampler(KDiffusionSamplerBase):
     @torch.no_grad()
     def do_sample(self):
         return sample_dpmpp_2m(self.ldm_wrapper_model, self.x, self.sigmas), None
+
+
+class HeunSampler(KDiffusionSamplerBase):
+    @torch.no_grad()
+    def compute_sigmas(self, n):
+        return self.compviz_wrapper_model.get_sigmas(n).to(self.device)
+
+    @torch.no_grad()
+    def do_sample(self):
+        return sample_heun(self.ldm_wrapper_model, self.x, self.sigmas), None
+
+
+class Dpm2Sampler(KDiffusionSamplerBase):
+    @torch.no_grad()
+    def compute_sigmas(self, n):
+        return get_sigmas_karras(n, self.sigma_min, self.sigma_max, device=self.device)
+
+    @torch.no_grad()
+    def do_sample(self):
+        return sample_dpm_2(self.ldm_wrapper_model, self.x, self.sigmas), None
+
+
+class Dpm2AncestralSampler(KDiffusionSamplerBase):
+    @torch.no_grad()
+    def compute_sigmas(self, n):
+        return get_sigmas_karras(n, self.sigma_min, self.sigma_max, device=self.device)
+
+    @torch.no_grad()
+    def do_sample(self):
+        return sample_dpm_2_ancestral(self.ldm_wrapper_model, self.x, self.sigmas), None
+
+
+class LmsSampler(KDiffusionSamplerBase):
+    @torch.no_grad()
+    def compute_sigmas(self, n):
+        return self.compviz_wrapper_model.get_sigmas(n).to(self.device)
+
+    @torch.no_grad()
+    def do_sample(self):
+        return sample_lms(self.ldm_wrapper_model, self.x, self.sigmas), None
+
+
+class Dpmpp2sAncestralSampler(KDiffusionSamplerBase):
+    @torch.no_grad()
+    def compute_sigmas(self, n):
+        return get_sigmas_karras(n, self.sigma_min, self.sigma_max, device=self.device)
+
+    @torch.no_grad()
+    def do_sample(self):
+        return sample_dpmpp_2s_ancestral(self.ldm_wrapper_model, self.x, self.sigmas), None

@@ -1,6 +1,6 @@
-"""Drop-in mirror of the reference's VAE decoder (`ldm.modules.diffusionmodules.model`, HowToSD/cremage
-modules/ldm/modules/diffusionmodules/model.py): Decoder (:469), ResnetBlock (:89), AttnBlock (:157), Upsample (:49),
-Normalize (:45, GroupNorm eps 1e-6) and nonlinearity (:40, x*sigmoid(x)).  Same constructor arguments, parameter names
+"""Drop-in mirror of the reference's VAE decoder and encoder (`ldm.modules.diffusionmodules.model`, HowToSD/cremage
+modules/ldm/modules/diffusionmodules/model.py): Decoder (:469), Encoder (:375), ResnetBlock (:89), AttnBlock (:157),
+Upsample (:49), Downsample (:66), Normalize (:45, GroupNorm eps 1e-6) and nonlinearity (:40, x*sigmoid(x)).  Same constructor arguments, parameter names
 and forward signatures; the arithmetic runs on the sm_100a kernels (NHWC bf16, fp32 accumulate / statistics).
 """
 from __future__ import annotations
@@ -41,6 +41,37 @@ class Upsample(PackedModule):
 
     def forward(self, x):
         require_cuda(x, "Upsample.forward")
+        return ops.nhwc_to_nchw_f32(self._run(ops.nchw_to_nhwc(x))).to(x.dtype)
+
+
+class Downsample(PackedModule):
+    """model.py:66-86: F.pad(x, (0, 1, 0, 1)) then conv3x3 stride 2 padding 0 (asymmetric: the extra zero row / column
+    sits at the bottom / right).  Runs as the stride-2 implicit GEMM over the parity-split input with the asymmetric
+    tap table; the padding is TMA's out-of-bounds zero fill."""
+
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        self.with_conv = with_conv
+        self.in_channels = in_channels
+        if not with_conv:
+            raise NotImplementedError("cremage_b200: Downsample without conv (avg_pool2d) is not used by the SD VAE")
+        self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
+
+    def _pack(self, device):
+        return {"w": packw(self.conv.weight, device), "b": f32(self.conv.bias, device)}
+
+    def _run(self, x):
+        p = self.packed(x.device)
+        n, h, w, c = x.shape
+        if h % 2 or w % 2:
+            raise ValueError("cremage_b200: Downsample needs even spatial extents")
+        xs = ops.parity_split(x)
+        out = ops.igemm(xs.view(4 * n, h // 2, w // 2, c), p["w"], c, out_grid=(n, h // 2, w // 2),
+                        taps=ops.taps_3x3_stride2_asym(n), bias=p["b"])
+        return out.view(n, h // 2, w // 2, c)
+
+    def forward(self, x):
+        require_cuda(x, "Downsample.forward")
         return ops.nhwc_to_nchw_f32(self._run(ops.nchw_to_nhwc(x))).to(x.dtype)
 
 
@@ -240,3 +271,99 @@ class Decoder(PackedModule):
         self.last_z_shape = z.shape
         o = self._run(ops.nchw_to_nhwc(z.float(), c_pad=8))
         return ops.nhwc_to_nchw_f32(o, self.out_ch).to(z.dtype)
+
+
+class Encoder(PackedModule):
+    """model.py:375-466: conv_in, per level `num_res_blocks` ResnetBlocks (+ Downsample), mid (Res, Attn, Res),
+    GroupNorm + swish + conv_out to 2 * z_channels moments.  `_run` returns the moments as fp32 NHWC."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, use_linear_attn=False,
+                 attn_type="vanilla", **ignore_kwargs):
+        super().__init__()
+        if use_linear_attn:
+            raise NotImplementedError("cremage_b200: use_linear_attn is not implemented")
+        if in_channels > 8:
+            raise NotImplementedError("cremage_b200: Encoder input channels above 8 are not implemented")
+        self.ch = ch
+        self.temb_ch = 0
+        self.num_resolutions = len(ch_mult)
+        self.num_res_blocks = num_res_blocks
+        self.resolution = resolution
+        self.in_channels = in_channels
+        self.conv_in = nn.Conv2d(in_channels, self.ch, kernel_size=3, stride=1, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.in_ch_mult = in_ch_mult
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block = nn.ModuleList()
+            attn = nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for i_block in range(self.num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=self.temb_ch,
+                                         dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(make_attn(block_in, attn_type=attn_type))
+            down = nn.Module()
+            down.block = block
+            down.attn = attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch,
+                                       dropout=dropout)
+        self.mid.attn_1 = make_attn(block_in, attn_type=attn_type)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=self.temb_ch,
+                                       dropout=dropout)
+        self.norm_out = Normalize(block_in)
+        self.out_channels = 2 * z_channels if double_z else z_channels
+        self.conv_out = nn.Conv2d(block_in, self.out_channels, kernel_size=3, stride=1, padding=1)
+
+    def _own_params(self):
+        return list(self.conv_in.parameters()) + list(self.norm_out.parameters()) + list(self.conv_out.parameters())
+
+    def _pack(self, device):
+        w_in = self.conv_in.weight.detach().to(device=device, dtype=torch.float32)
+        return {"inw": w_in.permute(2, 3, 1, 0).contiguous(), "inb": f32(self.conv_in.bias, device),
+                "og": f32(self.norm_out.weight, device), "ob": f32(self.norm_out.bias, device),
+                "ow": packw(self.conv_out.weight, device), "oc": f32(self.conv_out.bias, device)}
+
+    def _trunk(self, x_nhwc: torch.Tensor) -> torch.Tensor:
+        """image NHWC 16-bit [n, H, W, >= in_channels] -> normalised + swish features before conv_out."""
+        p = self.packed(x_nhwc.device)
+        h = ops.conv3x3_small_cin(x_nhwc, self.in_channels, p["inw"], p["inb"], self.ch)
+        for i_level in range(self.num_resolutions):
+            for i_block in range(self.num_res_blocks):
+                h = self.down[i_level].block[i_block]._run(h)
+                if len(self.down[i_level].attn) > 0:
+                    h = self.down[i_level].attn[i_block]._run(h)
+            if i_level != self.num_resolutions - 1:
+                h = self.down[i_level].downsample._run(h)
+        h = self.mid.block_1._run(h)
+        if isinstance(self.mid.attn_1, AttnBlock):
+            h = self.mid.attn_1._run(h)
+        h = self.mid.block_2._run(h)
+        return ops.groupnorm(h, p["og"], p["ob"], self.norm_out.eps, silu=True)
+
+    def _run(self, x_nhwc: torch.Tensor, out_w=None, out_b=None, out_c=None) -> torch.Tensor:
+        """-> fp32 NHWC [n, h, w, ld] moments; (out_w, out_b, out_c) override conv_out (AutoencoderKL folds quant_conv
+        into it: two linear maps with nothing in between)."""
+        p = self.packed(x_nhwc.device)
+        g = self._trunk(x_nhwc)
+        n, hh, ww, _ = g.shape
+        co = self.out_channels if out_c is None else out_c
+        ld = (co + 3) // 4 * 4
+        o = ops.igemm(g, p["ow"] if out_w is None else out_w, co, taps=ops.TAPS_3X3,
+                      bias=p["oc"] if out_b is None else out_b, out_f32=True, out_ld=ld)
+        return o.view(n, hh, ww, ld)
+
+    def forward(self, x):
+        require_cuda(x, "Encoder.forward")
+        o = self._run(ops.nchw_to_nhwc(x.float(), c_pad=8))
+        return ops.nhwc_to_nchw_f32(o, self.out_channels).to(x.dtype)

@@ -224,6 +224,22 @@ def taps_3x3_stride2(n: int):
     return dw, dh, dn
 
 
+def taps_3x3_stride2_asym(n: int):
+    """stride 2 after F.pad(x, (0, 1, 0, 1)) with padding 0 (the VAE encoder's Downsample, ldm/modules/
+    diffusionmodules/model.py:79-84) over the parity-split input: input row 2*oy+kh, the extra zero row / column at the
+    bottom / right is the TMA out-of-bounds fill of the parity plane."""
+    par = {0: (0, 0), 1: (1, 0), 2: (0, 1)}  # k -> (parity, shift)
+    dw, dh, dn = [], [], []
+    for kh in range(3):
+        for kw in range(3):
+            ph, sh = par[kh]
+            pw, sw = par[kw]
+            dw.append(sw)
+            dh.append(sh)
+            dn.append((2 * ph + pw) * n)
+    return dw, dh, dn
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # implicit GEMM
 # ------------------------------------------------------------------------------------------------------------------
@@ -438,6 +454,23 @@ def conv3x3_small_cin(x: torch.Tensor, cin: int, wgt: torch.Tensor, bias: Option
     out = torch.empty((n, h, w, cout), dtype=ACT, device=x.device)
     _launch("cb_conv3x3_small_cin", lambda: _lib.load().cb_conv3x3_small_cin(_p(x), n, h, w, cin, cin_ld, _p(wgt), _p(bias), cout, _p(out), _stream()))
     return out
+
+
+def diag_gaussian(moments: torch.Tensor, noise: Optional[torch.Tensor] = None, scale: float = 1.0,
+                  want_mean_std: bool = False):
+    """moments fp32 NCHW [n, 2c, h, w] -> sample = scale * (mean + std * noise) (noise None: the mode) [, mean, std]."""
+    _need_cuda(moments, noise)
+    assert moments.dtype == torch.float32 and moments.is_contiguous() and moments.shape[1] % 2 == 0
+    n, c2, h, w = moments.shape
+    c = c2 // 2
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (n, c, h, w)
+    sample = torch.empty((n, c, h, w), dtype=torch.float32, device=moments.device)
+    mean = torch.empty_like(sample) if want_mean_std else None
+    std = torch.empty_like(sample) if want_mean_std else None
+    _launch("cb_diag_gaussian", lambda: _lib.load().cb_diag_gaussian(_p(moments), _p(noise), n, c, h * w, scale, _p(mean), _p(std),
+                                                                     _p(sample), _stream()))
+    return (sample, mean, std) if want_mean_std else sample
 
 
 def silu_add(x: torch.Tensor, add: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -146,6 +146,12 @@ int cb_timestep_embedding(const float* t, int64_t n, int dim, const float* freqs
  * wgt fp32 [3][3][cin][cout], out NHWC bf16 */
 int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64_t w, int cin, int64_t cin_ld, const float* wgt,
                          const float* bias, int64_t cout, void* out, cudaStream_t stream);
+/* DiagonalGaussianDistribution of AutoencoderKL.encode (ldm/modules/distributions/distributions.py:24-37;
+ * ldm/models/autoencoder.py:324-331; LatentDiffusion.get_first_stage_encoding ddpm.py:585-594): moments fp32 NCHW
+ * [n][2c][hw] -> mean, std = exp(0.5 clamp(logvar, -30, 20)), sample = scale * (mean + std * noise); any output may
+ * be NULL, noise NULL = the mode; scale 0 = 1 */
+int cb_diag_gaussian(const float* moments, const float* noise, int64_t n, int64_t c, int64_t hw, float scale,
+                     float* mean_out, float* std_out, float* sample_out, cudaStream_t stream);
 /* y = silu(x) or y = silu(x + add) over bf16 vectors (SDXL label_emb path) */
 int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream);
 

@@ -643,3 +643,191 @@ def hires_fix_latent_ddim(eps_fn, alphas_cumprod: Tensor, samples: Tensor, cond:
     t_enc = int(strength * S)
     z_enc = ddim_stochastic_encode(alphas_cumprod, up, t_enc, S, noise)
     return ddim_decode(eps_fn, alphas_cumprod, z_enc, cond, uncond, cfg_scale, S, t_enc)
+
+
+# ======================================================================================================================
+# remaining k-diffusion samplers of the reference's front ends, s_churn = 0
+# ======================================================================================================================
+def sample_heun(model, x: Tensor, sigmas: Tensor) -> Tensor:
+    """k_diffusion/sampling.py:167-193."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        d = (x - denoised) / sigmas[i]
+        dt = sigmas[i + 1] - sigmas[i]
+        if sigmas[i + 1] == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            denoised_2 = model(x_2, sigmas[i + 1] * s_in)
+            d_2 = (x_2 - denoised_2) / sigmas[i + 1]
+            x = x + ((d + d_2) / 2) * dt
+    return x
+
+
+def sample_dpm_2(model, x: Tensor, sigmas: Tensor) -> Tensor:
+    """k_diffusion/sampling.py:196-224."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        d = (x - denoised) / sigmas[i]
+        if sigmas[i + 1] == 0:
+            x = x + d * (sigmas[i + 1] - sigmas[i])
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigmas[i + 1].log(), 0.5).exp()
+            x_2 = x + d * (sigma_mid - sigmas[i])
+            denoised_2 = model(x_2, sigma_mid * s_in)
+            d_2 = (x_2 - denoised_2) / sigma_mid
+            x = x + d_2 * (sigmas[i + 1] - sigmas[i])
+    return x
+
+
+def sample_dpm_2_ancestral(model, x: Tensor, sigmas: Tensor, noise: Sequence[Tensor], eta: float = 1.0,
+                           s_noise: float = 1.0) -> Tensor:
+    """k_diffusion/sampling.py:227-252; `noise[i]` is the injected noise_sampler output of step i."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        d = (x - denoised) / sigmas[i]
+        if sigma_down == 0:
+            x = x + d * (sigma_down - sigmas[i])
+        else:
+            sigma_mid = sigmas[i].log().lerp(sigma_down.log(), 0.5).exp()
+            x_2 = x + d * (sigma_mid - sigmas[i])
+            denoised_2 = model(x_2, sigma_mid * s_in)
+            d_2 = (x_2 - denoised_2) / sigma_mid
+            x = x + d_2 * (sigma_down - sigmas[i])
+            x = x + noise[i] * s_noise * sigma_up
+    return x
+
+
+def linear_multistep_coeff(order: int, t, i: int, j: int) -> float:
+    """k_diffusion/sampling.py:255-266 (scipy.integrate.quad, epsrel 1e-4)."""
+    from scipy import integrate
+
+    def fn(tau):
+        prod = 1.0
+        for k in range(order):
+            if j == k:
+                continue
+            prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+def sample_lms(model, x: Tensor, sigmas: Tensor, order: int = 4) -> Tensor:
+    """k_diffusion/sampling.py:269-286."""
+    s_in = x.new_ones([x.shape[0]])
+    sigmas_cpu = sigmas.detach().cpu().numpy()
+    ds: List[Tensor] = []
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        ds.append((x - denoised) / sigmas[i])
+        if len(ds) > order:
+            ds.pop(0)
+        cur_order = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur_order, sigmas_cpu, i, j) for j in range(cur_order)]
+        x = x + sum(coeff * d for coeff, d in zip(coeffs, reversed(ds)))
+    return x
+
+
+def sample_dpmpp_2s_ancestral(model, x: Tensor, sigmas: Tensor, noise: Sequence[Tensor], eta: float = 1.0,
+                              s_noise: float = 1.0) -> Tensor:
+    """k_diffusion/sampling.py:517-548."""
+    s_in = x.new_ones([x.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()
+    t_fn = lambda sigma: sigma.log().neg()
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=eta)
+        if sigma_down == 0:
+            x = x + ((x - denoised) / sigmas[i]) * (sigma_down - sigmas[i])
+        else:
+            t, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
+            r = 1 / 2
+            h = t_next - t
+            s = t + r * h
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * denoised
+            denoised_2 = model(x_2, sigma_fn(s) * s_in)
+            x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * denoised_2
+        if sigmas[i + 1] > 0:
+            x = x + noise[i] * s_noise * sigma_up
+    return x
+
+
+# ======================================================================================================================
+# VAE encoder (SURVEY 8f N2): the step before the path for img2img
+# ======================================================================================================================
+def encoder_param_shapes(cfg: DecoderConfig) -> Dict[str, Tuple[int, ...]]:
+    """Parameters of the reference VAE Encoder (ldm/modules/diffusionmodules/model.py:375-448) + quant_conv
+    (ldm/models/autoencoder.py:302), keys as under `first_stage_model.` in a checkpoint (attn_resolutions = [])."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def conv(p, i, o, k):
+        s[p + ".weight"] = (o, i, k, k)
+        s[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        s[p + ".weight"] = (c,)
+        s[p + ".bias"] = (c,)
+
+    def res(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cin, cout, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".nin_shortcut", cin, cout, 1)
+
+    nres = len(cfg.ch_mult)
+    in_ch_mult = (1,) + tuple(cfg.ch_mult)
+    conv("encoder.conv_in", 3, cfg.ch, 3)
+    block_in = cfg.ch
+    for i_level in range(nres):
+        block_in = cfg.ch * in_ch_mult[i_level]
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        for i_block in range(cfg.num_res_blocks):
+            res(f"encoder.down.{i_level}.block.{i_block}", block_in, block_out)
+            block_in = block_out
+        if i_level != nres - 1:
+            conv(f"encoder.down.{i_level}.downsample.conv", block_in, block_in, 3)
+    res("encoder.mid.block_1", block_in, block_in)
+    norm("encoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{n}", block_in, block_in, 1)
+    res("encoder.mid.block_2", block_in, block_in)
+    norm("encoder.norm_out", block_in)
+    conv("encoder.conv_out", block_in, 2 * cfg.z_channels, 3)
+    conv("quant_conv", 2 * cfg.z_channels, 2 * cfg.embed_dim, 1)
+    return s
+
+
+def encoder_forward(sd: SD, cfg: DecoderConfig, x: Tensor) -> Tensor:
+    """Encoder.forward, model.py:440-466; Downsample = pad (0,1,0,1) then conv3x3 stride 2 padding 0 (:79-84)."""
+    nres = len(cfg.ch_mult)
+    h = F.conv2d(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1)
+    for i_level in range(nres):
+        for i_block in range(cfg.num_res_blocks):
+            h = _vae_resnet(sd, f"encoder.down.{i_level}.block.{i_block}", h)
+        if i_level != nres - 1:
+            p = f"encoder.down.{i_level}.downsample.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1), mode="constant", value=0), sd[p + ".weight"], sd[p + ".bias"], stride=2)
+    h = _vae_resnet(sd, "encoder.mid.block_1", h)
+    h = _vae_attn(sd, "encoder.mid.attn_1", h)
+    h = _vae_resnet(sd, "encoder.mid.block_2", h)
+    h = F.group_norm(h, 32, sd["encoder.norm_out.weight"], sd["encoder.norm_out.bias"], 1e-6)
+    return F.conv2d(h * torch.sigmoid(h), sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1)
+
+
+def vae_encode_moments(sd: SD, cfg: DecoderConfig, x: Tensor) -> Tensor:
+    """AutoencoderKL.encode up to the posterior's parameters, autoencoder.py:324-331: quant_conv(encoder(x))."""
+    return F.conv2d(encoder_forward(sd, cfg, x), sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def gaussian_sample(moments: Tensor, noise: Tensor) -> Tensor:
+    """DiagonalGaussianDistribution, ldm/modules/distributions/distributions.py:24-37: mean + exp(0.5 * clamp(logvar,
+    -30, 20)) * noise (`noise` = the injected torch.randn draw)."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return mean + torch.exp(0.5 * logvar) * noise

@@ -41,12 +41,23 @@ def build_unet(cfg, sd, device="cuda"):
     return m.to(device).eval()
 
 
+ENCODER_SEED = 400
+
+
+def full_vae_weights(cfg, sd):
+    """Decoder-side weights `sd` completed with the (seeded) encoder-side tensors: the checkpoint layout of
+    `first_stage_model.*` (encoder.*, quant_conv, post_quant_conv, decoder.*)."""
+    out = dict(O.make_weights(O.encoder_param_shapes(cfg), seed=ENCODER_SEED))
+    out.update(sd)
+    return out
+
+
 def build_vae(cfg, sd, device="cuda"):
     from cremage_b200.ldm.models.autoencoder import AutoencoderKL
     with torch.device("meta"):
         m = AutoencoderKL(**vae_kwargs(cfg))
     m = m.to_empty(device="cpu")
-    m.load_state_dict(sd, strict=True)
+    m.load_state_dict(full_vae_weights(cfg, sd), strict=True)
     return m.to(device).eval()
 
 
