@@ -5,8 +5,11 @@ Same class names, constructor arguments, parameter (state-dict) names and forwar
   CrossAttention (:265; CrossAttentionOriginal :537 and MemoryEfficientCrossAttention :696 are aliases -- all three
   compute softmax(q k^T / sqrt(d)) v), GEGLU (:57) / GEGLU_with_lora (:66), FeedForward (:119),
   BasicTransformerBlock (:862), SpatialTransformer (:915).
-LoRA side branches and IP-adapter tokens are constructor-compatible but must be empty (they are no-ops in the
-reference when `lora_ranks=[]`, `ipa_num_tokens=0`); anything else raises instead of silently falling back.
+LoRA side branches (attention.py:79-96,148-168,306-376,966-1055) keep the reference's parameter names
+(`q_lora_downs.{i}.weight`, `q_lora_ups.{i}.weight`, `q_lora_alphas.{i}`, ...) and are MERGED into the packed base
+weight when the module packs:  W_eff = W + sum_i lora_weights[i] * (alpha_i / rank_i) * up_i @ down_i  -- the same
+linear map (every branch is `up(down(x))` added to the base projection of the same input), at zero run-time cost.
+IP-adapter tokens must be empty (`ipa_num_tokens=0`); anything else raises instead of silently falling back.
 """
 from __future__ import annotations
 
@@ -22,11 +25,51 @@ GEGLU_BN = ops.GEGLU_BN  # N tile of the fused GEGLU projection (x / gate rows i
 
 
 def _check_extras(lora_ranks, ipa_num_tokens):
-    if lora_ranks:
-        raise NotImplementedError("cremage_b200: LoRA side branches are not implemented; merge LoRA deltas into the "
-                                  "base weights before loading (lora_ranks must be empty)")
     if ipa_num_tokens:
         raise NotImplementedError("cremage_b200: IP-Adapter tokens are not implemented (ipa_num_tokens must be 0)")
+
+
+def zero_init_module(m):
+    with torch.no_grad():
+        for p_ in m.parameters():
+            p_.zero_()
+    return m
+
+
+class LoraBranches:
+    """Mixin: reference-named LoRA parameter containers + the load-time merge."""
+
+    def _init_lora(self, lora_ranks, lora_weights):
+        self.lora_ranks = list(lora_ranks) if lora_ranks else []
+        self.lora_weights = list(lora_weights) if lora_weights else [1.0] * len(self.lora_ranks)
+        if len(self.lora_weights) != len(self.lora_ranks):
+            raise ValueError("lora_weights and lora_ranks differ in length")
+
+    def _add_lora(self, prefix: str, dim_in: int, dim_out: int, conv: bool = False):
+        downs, ups, alphas = nn.ModuleList(), nn.ModuleList(), nn.ParameterList()
+        for rank in self.lora_ranks:
+            if conv:
+                downs.append(zero_init_module(nn.Conv2d(dim_in, rank, kernel_size=1, stride=1, padding=0, bias=False)))
+                ups.append(zero_init_module(nn.Conv2d(rank, dim_out, kernel_size=1, stride=1, padding=0, bias=False)))
+            else:
+                downs.append(zero_init_module(nn.Linear(dim_in, rank, bias=False)))
+                ups.append(zero_init_module(nn.Linear(rank, dim_out, bias=False)))
+            alphas.append(nn.Parameter(torch.tensor(float(rank))))
+        setattr(self, prefix + "_lora_downs", downs)
+        setattr(self, prefix + "_lora_ups", ups)
+        setattr(self, prefix + "_lora_alphas", alphas)
+
+    def _merged(self, base: torch.Tensor, prefix: str, device) -> torch.Tensor:
+        """fp32 [out, in] base weight + the LoRA deltas of branch `prefix`."""
+        w = base.detach().to(device=device, dtype=torch.float32).reshape(base.shape[0], -1).clone()
+        downs, ups = getattr(self, prefix + "_lora_downs"), getattr(self, prefix + "_lora_ups")
+        alphas = getattr(self, prefix + "_lora_alphas")
+        for i, rank in enumerate(self.lora_ranks):
+            up = ups[i].weight.detach().to(device=device, dtype=torch.float32).reshape(ups[i].weight.shape[0], -1)
+            down = downs[i].weight.detach().to(device=device, dtype=torch.float32).reshape(rank, -1)
+            scale = float(self.lora_weights[i]) * (alphas[i].detach().to(device=device, dtype=torch.float32) / float(rank))
+            w += scale * (up @ down)
+        return w
 
 
 def Normalize(in_channels):
@@ -34,38 +77,42 @@ def Normalize(in_channels):
     return nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
 
 
-class GEGLU(nn.Module):
+class GEGLU(nn.Module, LoraBranches):
     """Parameter container for `ff.net.0.proj` (attention.py:57-62,66-96); computed fused inside FeedForward."""
 
     def __init__(self, dim_in, dim_out, lora_ranks: List[int] = None, lora_weights: List[float] = None):
         super().__init__()
-        _check_extras(lora_ranks, 0)
+        self._init_lora(lora_ranks, lora_weights)
         self.proj = nn.Linear(dim_in, dim_out * 2)
+        self._add_lora("proj", dim_in, dim_out * 2)
 
 
 GEGLU_with_lora = GEGLU
 
 
-class FeedForward(PackedModule):
+class FeedForward(PackedModule, LoraBranches):
     """attention.py:119-168: Linear(d, 8d) -> x * gelu(gate) -> Linear(4d, d). Only the gated (glu=True) form is on
     the path (BasicTransformerBlock passes gated_ff=True)."""
 
     def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0., lora_ranks: List[int] = None,
                  lora_weights: List[float] = None):
         super().__init__()
-        _check_extras(lora_ranks, 0)
+        self._init_lora(lora_ranks, lora_weights)
         if not glu:
             raise NotImplementedError("cremage_b200: FeedForward without GEGLU is not on the SD path")
         inner_dim = int(dim * mult)
         dim_out = dim if dim_out is None else dim_out
         self.dim, self.inner_dim, self.dim_out = dim, inner_dim, dim_out
-        self.net = nn.ModuleList([GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out)])
+        self.net = nn.ModuleList([GEGLU(dim, inner_dim, lora_ranks=lora_ranks, lora_weights=lora_weights),
+                                  nn.Dropout(dropout), nn.Linear(inner_dim, dim_out)])
+        self._add_lora("net_2", inner_dim, dim_out)
 
     def _pack(self, device):
-        wq, bq = ops.pack_geglu(self.net[0].proj.weight.to(device).float(), self.net[0].proj.bias.to(device).float(),
-                                GEGLU_BN)
+        wq, bq = ops.pack_geglu(self.net[0]._merged(self.net[0].proj.weight, "proj", device),
+                                self.net[0].proj.bias.to(device).float(), GEGLU_BN)
         return {"w1": ops.pack_weight(wq), "b1": bq.contiguous(),
-                "w2": packw(self.net[2].weight, device), "b2": f32(self.net[2].bias, device)}
+                "w2": ops.pack_weight(self._merged(self.net[2].weight, "net_2", device)),
+                "b2": f32(self.net[2].bias, device)}
 
     def _run(self, x2d: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         p = self.packed(x2d.device)
@@ -79,7 +126,7 @@ class FeedForward(PackedModule):
         return y.view(*shp[:-1], self.dim_out).to(x.dtype)
 
 
-class CrossAttention(PackedModule):
+class CrossAttention(PackedModule, LoraBranches):
     """attention.py:265-534 / :537-693 / :696-861. q/k/v projections write the per-head padded layout straight from
     the GEMM epilogue; the core is one fused flash-style kernel; to_out fuses bias (+ the block residual)."""
 
@@ -87,6 +134,7 @@ class CrossAttention(PackedModule):
                  lora_weights: List[float] = None, ipa_scale=1.0, ipa_num_tokens=0):
         super().__init__()
         _check_extras(lora_ranks, ipa_num_tokens)
+        self._init_lora(lora_ranks, lora_weights)
         inner_dim = dim_head * heads
         self.is_self = context_dim is None
         context_dim = query_dim if context_dim is None else context_dim
@@ -99,13 +147,18 @@ class CrossAttention(PackedModule):
         self.to_k = nn.Linear(context_dim, inner_dim, bias=False)
         self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
         self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+        self._add_lora("q", query_dim, inner_dim)
+        self._add_lora("k", context_dim, inner_dim)
+        self._add_lora("v", context_dim, inner_dim)
+        self._add_lora("out", inner_dim, query_dim)
 
     def _pack(self, device):
-        p = {"wq": packw(self.to_q.weight, device),
-             "wkv": packw(torch.cat([self.to_k.weight, self.to_v.weight], 0), device),
-             "wo": packw(self.to_out[0].weight, device), "bo": f32(self.to_out[0].bias, device)}
+        wq, wk, wv = (self._merged(getattr(self, "to_" + n).weight, n, device) for n in ("q", "k", "v"))
+        p = {"wq": ops.pack_weight(wq), "wkv": ops.pack_weight(torch.cat([wk, wv], 0)),
+             "wo": ops.pack_weight(self._merged(self.to_out[0].weight, "out", device)),
+             "bo": f32(self.to_out[0].bias, device)}
         if self.context_dim == self.query_dim:
-            p["wqkv"] = packw(torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0), device)
+            p["wqkv"] = ops.pack_weight(torch.cat([wq, wk, wv], 0))
         return p
 
     def _run(self, x2d: torch.Tensor, batch: int, nq: int, ctx2d: Optional[torch.Tensor], nk: int,
@@ -161,11 +214,12 @@ class BasicTransformerBlock(PackedModule):
         super().__init__()
         _check_extras(lora_ranks, ipa_num_tokens)
         self.disable_self_attn = disable_self_attn
+        lk = dict(lora_ranks=lora_ranks, lora_weights=lora_weights)
         self.attn1 = CrossAttention(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout,
-                                    context_dim=context_dim if self.disable_self_attn else None)
-        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
+                                    context_dim=context_dim if self.disable_self_attn else None, **lk)
+        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff, **lk)
         self.attn2 = CrossAttention(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
-                                    dropout=dropout)
+                                    dropout=dropout, **lk)
         self.norm1 = nn.LayerNorm(dim)
         self.norm2 = nn.LayerNorm(dim)
         self.norm3 = nn.LayerNorm(dim)
@@ -203,7 +257,7 @@ class BasicTransformerBlock(PackedModule):
         return self._run(x2d, b, n, ctx2d, nk).view(b, n, c).to(x.dtype)
 
 
-class SpatialTransformer(PackedModule):
+class SpatialTransformer(PackedModule, LoraBranches):
     _HONOR_USE_LINEAR = False  # the ldm class ignores `use_linear`; the sgm mirror (SDXL) honours it
 
     """attention.py:915-1057. GroupNorm(eps 1e-6) -> 1x1 proj_in -> transformer blocks on [b, hw, c] -> 1x1 proj_out
@@ -215,6 +269,7 @@ class SpatialTransformer(PackedModule):
                  ipa_scale=1.0, ipa_num_tokens=0):
         super().__init__()
         _check_extras(lora_ranks, ipa_num_tokens)
+        self._init_lora(lora_ranks, lora_weights)
         if context_dim is not None and not isinstance(context_dim, (list, tuple)):
             context_dim = [context_dim]
         if context_dim is None:
@@ -230,7 +285,8 @@ class SpatialTransformer(PackedModule):
             self.proj_in = nn.Conv2d(in_channels, inner_dim, kernel_size=1, stride=1, padding=0)
         self.transformer_blocks = nn.ModuleList([
             BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim[d],
-                                  disable_self_attn=disable_self_attn, checkpoint=use_checkpoint)
+                                  disable_self_attn=disable_self_attn, checkpoint=use_checkpoint,
+                                  lora_ranks=self.lora_ranks, lora_weights=self.lora_weights)
             for d in range(depth)])
         if self.use_linear:
             self.proj_out = nn.Linear(inner_dim, in_channels)
@@ -239,15 +295,23 @@ class SpatialTransformer(PackedModule):
         with torch.no_grad():  # zero_module, attention.py:1002
             self.proj_out.weight.zero_()
             self.proj_out.bias.zero_()
+        self._add_lora("proj_in", in_channels, inner_dim, conv=not self.use_linear)
+        self._add_lora("proj_out", inner_dim, in_channels, conv=not self.use_linear)
 
     def _own_params(self):
-        return [self.norm.weight, self.norm.bias, self.proj_in.weight, self.proj_in.bias, self.proj_out.weight,
-                self.proj_out.bias]
+        ps = [self.norm.weight, self.norm.bias, self.proj_in.weight, self.proj_in.bias, self.proj_out.weight,
+              self.proj_out.bias]
+        for pre in ("proj_in", "proj_out"):
+            for kind in ("downs", "ups", "alphas"):
+                ps += list(getattr(self, f"{pre}_lora_{kind}").parameters())
+        return ps
 
     def _pack(self, device):
         return {"ng": f32(self.norm.weight, device), "nb": f32(self.norm.bias, device),
-                "wi": packw(self.proj_in.weight, device), "bi": f32(self.proj_in.bias, device),
-                "wo": packw(self.proj_out.weight, device), "bo": f32(self.proj_out.bias, device)}
+                "wi": ops.pack_weight(self._merged(self.proj_in.weight, "proj_in", device)),
+                "bi": f32(self.proj_in.bias, device),
+                "wo": ops.pack_weight(self._merged(self.proj_out.weight, "proj_out", device)),
+                "bo": f32(self.proj_out.bias, device)}
 
     def _run(self, x: torch.Tensor, ctx2d: Optional[torch.Tensor], nk: int) -> torch.Tensor:
         """x: NHWC bf16 [b, h, w, c] -> same shape."""

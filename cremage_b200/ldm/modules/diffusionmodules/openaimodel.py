@@ -259,8 +259,6 @@ class UNetModel(PackedModule):
             transformer_depth = len(channel_mult) * [transformer_depth]
         transformer_depth = list(transformer_depth)
         assert len(transformer_depth) == len(channel_mult), "transformer_depth must be an int or one entry per level"
-        if lora_ranks:
-            raise NotImplementedError("cremage_b200: merge LoRA weights before loading (lora_ranks must be empty)")
         if ipa_num_tokens:
             raise NotImplementedError("cremage_b200: IP-Adapter tokens are not implemented")
         if num_heads_upsample == -1:
@@ -301,7 +299,7 @@ class UNetModel(PackedModule):
         def make_st(ch, heads, dim_head, depth, disabled_sa=False):
             return self._ST_CLS(ch, heads, dim_head, depth=depth, context_dim=context_dim,
                                 disable_self_attn=disabled_sa, use_linear=use_linear_in_transformer,
-                                use_checkpoint=use_checkpoint)
+                                use_checkpoint=use_checkpoint, lora_ranks=lora_ranks, lora_weights=lora_weights)
 
         def head_cfg(ch, heads):
             if num_head_channels == -1:
@@ -484,9 +482,22 @@ class UNetModel(PackedModule):
     def packed(self, device):
         before = self._cb_packed
         p = super().packed(device)
-        if p is not before and self._graphed is not None:
+        # captured graphs hold the packed weight buffers of EVERY sub-module: any in-place parameter update anywhere in
+        # the tree (optimiser step, LoRA alpha edit, weight patching) must drop them, not only this module's own packs
+        params = self.__dict__.get("_cb_all_params")
+        if params is None:
+            params = list(self.parameters())
+            self.__dict__["_cb_all_params"] = params
+        versions = sum(q._version for q in params)
+        stale = versions != self.__dict__.get("_cb_all_versions")
+        self.__dict__["_cb_all_versions"] = versions
+        if (p is not before or stale) and self._graphed is not None:
             self._graphed.reset()  # parameters changed: captured graphs hold stale weight buffers
         return p
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_cb_all_params", None)   # .to() / .half() may replace Parameter objects
+        return super()._apply(fn, *args, **kwargs)
 
     def invalidate_packed(self):
         super().invalidate_packed()

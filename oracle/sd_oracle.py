@@ -831,3 +831,46 @@ def gaussian_sample(moments: Tensor, noise: Tensor) -> Tensor:
     mean, logvar = torch.chunk(moments, 2, dim=1)
     logvar = torch.clamp(logvar, -30.0, 20.0)
     return mean + torch.exp(0.5 * logvar) * noise
+
+
+# ======================================================================================================================
+# LoRA side branches of the UNet: ldm/modules/attention.py:79-96,148-168,306-376,966-1055
+# ======================================================================================================================
+LORA_BASE = {"q": "to_q", "k": "to_k", "v": "to_v", "out": "to_out.0", "proj": "proj", "net_2": "net.2",
+             "proj_in": "proj_in", "proj_out": "proj_out"}
+
+
+def make_lora_weights(shapes: Dict[str, Tuple[int, ...]], seed: int) -> SD:
+    """Deterministic non-trivial LoRA tensors for the keys `*_lora_downs.i.weight`, `*_lora_ups.i.weight`,
+    `*_lora_alphas.i` (the reference zero-initialises downs / ups, which would make the branches no-ops)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: SD = {}
+    for key in sorted(shapes):
+        shp = shapes[key]
+        if "_lora_alphas." in key:
+            sd[key] = torch.tensor(3.0) + torch.randn((), generator=g)
+        else:
+            fan_in = int(np.prod(shp[1:]))
+            sd[key] = torch.randn(shp, generator=g) * (0.7 / math.sqrt(fan_in))
+    return sd
+
+
+def lora_merge(sd: SD, lora_sd: SD, lora_ranks: Sequence[int], lora_weights: Sequence[float]) -> SD:
+    """Every branch computes  base(x) + sum_i up_i(down_i(x)) * lora_weights[i] * (alpha_i / rank_i)  on the SAME input as
+    the base projection (attention.py:344-348,1036-1041 ...), i.e. the linear map  W + sum_i s_i up_i @ down_i."""
+    out = dict(sd)
+    for key in lora_sd:
+        if "_lora_downs." not in key:
+            continue
+        head, rest = key.rsplit("_lora_downs.", 1)
+        i = int(rest.split(".")[0])
+        prefix, _, branch = head.rpartition(".")
+        # net_2 / proj_in / proj_out contain an underscore themselves: the branch is everything after the last dot
+        base_key = f"{prefix}.{LORA_BASE[branch]}.weight" if prefix else f"{LORA_BASE[branch]}.weight"
+        down = lora_sd[key].reshape(lora_sd[key].shape[0], -1)
+        up = lora_sd[f"{head}_lora_ups.{i}.weight"]
+        up = up.reshape(up.shape[0], -1)
+        scale = lora_weights[i] * (lora_sd[f"{head}_lora_alphas.{i}"] / lora_ranks[i])
+        w = out[base_key]
+        out[base_key] = w + (scale * (up @ down)).reshape(w.shape)
+    return out
