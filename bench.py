@@ -441,7 +441,7 @@ def run_ours(args):
         "model_tflops": round(value * gf_per_image / 1e3, 1),
         "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": pk["bf16_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4),
-                     "traffic": IGEMM_DRAM_TRAFFIC_NOTE if not sdxl else None,
+                     "traffic": IGEMM_DRAM_TRAFFIC_NOTE if (not sdxl and b == 8 and sampler != "hires") else None,
                      "kernel": "igemm_kernel (tcgen05 implicit GEMM: conv3x3 / conv1x1 / linear), all launches of one "
                                f"UNet forward at batch {2 * b}; share of UNet kernel time {ig['ms'] / total_ms:.3f}",
                      "peak_source": pk["source"] + " bf16_tflops_sustained"},

@@ -53,7 +53,7 @@ SIGNATURES = {
     "cb_act_dtype": [],
     "cb_launch_count": [],
     "cb_igemm": [C.POINTER(IGemmDesc), _vp],
-    "cb_attention": [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _int, _int, _f32, _vp],
+    "cb_attention": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _f32, _vp],
     "cb_softmax_rows": [_vp, _int, _i64, _vp, _i64, _i64, _i64, _f32, _vp],
     "cb_pointwise_nchw_to_nhwc": [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _vp, _vp],
     "cb_groupnorm_workspace_bytes": [_i64, _i64, _i64, _int],

@@ -16,10 +16,12 @@
 // Q*K^T of block j+1 while the warpgroup is still exponentiating block j; P*V of block j follows when P is written
 // (p_full) and signals pv_done, which the warpgroup only consults before it overwrites P or rescales O.  In steady state a warpgroup never waits for the
 // tensor core, and the two warpgroups keep the MUFU pipe (the bound for d = 40) busy back to back.
-// The softmax row sum costs nothing when dpad > d: column d of V holds 1.0 (contract of cb_attention), so the
-// tensor core accumulates sum_j P_ij into O[:, d].
-// Q/K/V arrive through 3-D TMA boxes from the per-head padded layout [bh][tokens][dpad] written by the QKV
-// projection epilogue (CB_EPI_HEADS).
+// The softmax row sum is a by-product of the tensor core when the padded head dim has a spare column (dpad > d): a
+// helper warp writes 1.0 into column d of every V tile once its TMA load has landed (the pad columns arrive as
+// zeros), so P*V accumulates sum_j P_ij into O[:, d] at no extra MMA.
+// Q/K/V are read IN PLACE from the projection GEMM's row-major output ([tokens, (q|k|v) x heads x d], any row stride)
+// through 4-D TMA boxes {d, tokens, heads, batch}: the box is 64 columns wide and the tensor map's inner extent is d,
+// so TMA zero-fills the pad columns (d = 40 -> 64) -- no per-head padded copy of Q/K/V exists.
 // Replaces the attention cores at ldm/modules/attention.py:418-423 (Doggettx), :646-657 (Original), :811 (xformers).
 #include "common.cuh"
 #include "cremage_b200.h"
@@ -29,7 +31,7 @@ namespace cb {
 constexpr int ATT_BM = 128;             // query rows per warpgroup tile
 constexpr int ATT_BN = 128;             // kv rows per iteration
 constexpr int PANEL_BYTES = 128 * 128;  // [128 rows][64 x 16-bit]
-constexpr int ATT_THREADS = 352;         // TMA warp, issuer warp (tile 0), 8 softmax warps, issuer warp (tile 1)
+constexpr int ATT_THREADS = 384;         // TMA warp, issuer (tile 0), 8 softmax warps, issuer (tile 1), V ones-column warp
 constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
@@ -76,11 +78,14 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   auto p_full = [&](int w) { return bars + 152u + 8u * uint32_t(w); };
   auto s_free = [&](int w) { return bars + 168u + 8u * uint32_t(w); };
   auto pv_done = [&](int w) { return bars + 184u + 8u * uint32_t(w); };
-  const uint32_t tmem_slot = bars + 200u;
+  auto v_ready = [&](int s) { return bars + 200u + 8u * uint32_t(s); };   // V tile landed AND its ones column written
+  const uint32_t tmem_slot = bars + 232u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.y;
+  const int b_idx = bh / p.heads, h_idx = bh - b_idx * p.heads;
+
   const int nblk = (p.nk + ATT_BN - 1) / ATT_BN;
   const int q_first = blockIdx.x * p.nwg * ATT_BM;                              // first query row of this CTA
   const int nact = (p.nwg == 2 && q_first + ATT_BM < p.nq) ? 2 : 1;            // active query tiles
@@ -94,6 +99,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_init(k_full(s), 1); mbar_init(k_empty(s), uint32_t(nact));
       mbar_init(v_full(s), 1); mbar_init(v_empty(s), uint32_t(nact));
     }
+    for (int s = 0; s < 4; ++s) mbar_init(v_ready(s), 32);
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full(s), 1); mbar_init(p_full(s), ATT_BM);
       mbar_init(s_free(s), ATT_BM); mbar_init(pv_done(s), 1);
@@ -121,19 +127,21 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_expect_tx(q_full, uint32_t(nact) * tile_bytes);
       for (int w = 0; w < nact; ++w)
         for (int pn = 0; pn < p.np; ++pn)
-          tma_load_3d(sQ + uint32_t(w) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapQ, q_full, pn * 64,
-                      q_first + w * ATT_BM, bh);
+          tma_load_4d(sQ + uint32_t(w) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapQ, q_full, pn * 64,
+                      q_first + w * ATT_BM, h_idx, b_idx);
       for (int j = 0; j < nblk; ++j) {
         const int st = j % p.stages;
         const uint32_t ph = uint32_t((j / p.stages) & 1);
         mbar_wait(k_empty(st), ph ^ 1u);
         mbar_expect_tx(k_full(st), tile_bytes);
         for (int pn = 0; pn < p.np; ++pn)
-          tma_load_3d(sK + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapK, k_full(st), pn * 64, j * ATT_BN, bh);
+          tma_load_4d(sK + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapK, k_full(st), pn * 64, j * ATT_BN,
+                      h_idx, b_idx);
         mbar_wait(v_empty(st), ph ^ 1u);
         mbar_expect_tx(v_full(st), tile_bytes);
         for (int pn = 0; pn < p.np; ++pn)
-          tma_load_3d(sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapV, v_full(st), pn * 64, j * ATT_BN, bh);
+          tma_load_4d(sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapV, v_full(st), pn * 64, j * ATT_BN,
+                      h_idx, b_idx);
       }
     }
   } else if (warp == 1 || warp == 10) {
@@ -169,7 +177,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       };
       auto do_pv = [&](int j) {
         mbar_wait(p_full(w), uint32_t(j & 1));
-        mbar_wait(v_full(stage_of(j)), phase_of(j));
+        mbar_wait(v_ready(stage_of(j)), phase_of(j));
         tc_fence_after();
         issue_pv(stage_of(j), j > 0);
         umma_commit(pv_done(w));
@@ -186,6 +194,28 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           do_pv(j);
         }
       }
+    }
+  } else if (warp == 11) {
+    // ===================== V ones-column warp =====================
+    // TMA zero-fills the pad columns of a V tile; column d becomes 1.0 so that P*V also yields the softmax row sum.
+    const int pn = p.d >> 6, cw = p.d & 63;
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j % p.stages;
+      mbar_wait(v_full(st), uint32_t((j / p.stages) & 1));
+      if (USE_ONES) {
+        const uint32_t tile = sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES;
+#ifdef CB_FP16
+        const unsigned short one_bits = 0x3C00;   // fp16 1.0
+#else
+        const unsigned short one_bits = 0x3F80;   // bf16 1.0
+#endif
+        for (int r = lane; r < ATT_BN; r += 32) {
+          const uint32_t addr = tile + uint32_t(r) * 128u + (((uint32_t(cw) >> 3) ^ (uint32_t(r) & 7u)) << 4) + uint32_t(cw & 7) * 2u;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(one_bits) : "memory");
+        }
+        fence_proxy_async_smem();
+      }
+      mbar_arrive(v_ready(st));
     }
   } else {
     // ===================== softmax warpgroups =====================
@@ -318,28 +348,33 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
 using namespace cb;
 
-extern "C" int cb_attention(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads,
-                            int64_t nq, int64_t nk, int d, int dpad, float scale, cudaStream_t stream) {
+extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld,
+                            void* out, int64_t batch, int64_t heads, int64_t nq, int64_t nk, int d, float scale,
+                            cudaStream_t stream) {
   CB_REQUIRE(q && k && v && out, "cb_attention: null pointer");
   CB_REQUIRE(batch > 0 && heads > 0 && nq > 0 && nk > 0, "cb_attention: empty problem");
-  CB_REQUIRE(d > 0 && d % 8 == 0 && dpad % 64 == 0 && dpad >= d && dpad <= 192,
-             "cb_attention: head dim %d (padded %d) unsupported: d %% 8 == 0, dpad in {64,128,192}", d, dpad);
+  CB_REQUIRE(d > 0 && d % 8 == 0 && d <= 192, "cb_attention: head dim %d unsupported (multiple of 8, <= 192)", d);
+  CB_REQUIRE(q_ld >= heads * d && k_ld >= heads * d && v_ld >= heads * d && q_ld % 8 == 0 && k_ld % 8 == 0 && v_ld % 8 == 0,
+             "cb_attention: row strides must be >= heads * d and multiples of 8 elements");
+  const int dpad = (d + 63) / 64 * 64;
   const int64_t bh = batch * heads;
   CB_REQUIRE(bh <= 65535, "cb_attention: batch*heads = %lld exceeds the grid limit", (long long)bh);
   CUtensorMap mq, mk, mv;
-  uint32_t box[3] = {64, 128, 1};
+  uint32_t box[4] = {64, 128, 1, 1};
   {
-    uint64_t dims[3] = {(uint64_t)dpad, (uint64_t)nq, (uint64_t)bh};
-    uint64_t str[3] = {1, (uint64_t)dpad, (uint64_t)dpad * nq};
-    int rc = make_tmap_act(&mq, q, 3, dims, str, box);
+    // element (j, token, head, b) = base[(b * tokens + token) * ld + head * d + j]; inner extent d < box 64 -> zero fill
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)nq, (uint64_t)heads, (uint64_t)batch};
+    uint64_t str[4] = {1, (uint64_t)q_ld, (uint64_t)d, (uint64_t)(nq * q_ld)};
+    int rc = make_tmap_act(&mq, q, 4, dims, str, box);
     if (rc) return rc;
   }
   {
-    uint64_t dims[3] = {(uint64_t)dpad, (uint64_t)nk, (uint64_t)bh};
-    uint64_t str[3] = {1, (uint64_t)dpad, (uint64_t)dpad * nk};
-    int rc = make_tmap_act(&mk, k, 3, dims, str, box);
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)nk, (uint64_t)heads, (uint64_t)batch};
+    uint64_t strk[4] = {1, (uint64_t)k_ld, (uint64_t)d, (uint64_t)(nk * k_ld)};
+    uint64_t strv[4] = {1, (uint64_t)v_ld, (uint64_t)d, (uint64_t)(nk * v_ld)};
+    int rc = make_tmap_act(&mk, k, 4, dims, strk, box);
     if (rc) return rc;
-    rc = make_tmap_act(&mv, v, 3, dims, str, box);
+    rc = make_tmap_act(&mv, v, 4, dims, strv, box);
     if (rc) return rc;
   }
   AttnParams p{};
@@ -347,7 +382,7 @@ extern "C" int cb_attention(const void* q, const void* k, const void* v, void* o
   p.nwg = dpad <= 128 ? 2 : 1;           // TMEM: nwg * (128 + dpad) columns <= 512
   p.stages = dpad <= 64 ? 4 : (dpad <= 128 ? 2 : 1);   // smem: (nwg + 2*stages) * np panels of 16 KB
   p.p_alias = (p.nwg * (128 + dpad + 64) > 512) ? 1 : 0;   // no room for a separate P region: P overwrites S
-  p.use_ones = dpad > d;
+  p.use_ones = dpad > d;                 // spare column d of V carries 1.0 -> O[:, d] = softmax row sum
   p.scale_log2 = scale * 1.4426950408889634f;
   p.idesc_qk = make_idesc_f16(128, 128, 0, 0);
   p.idesc_pv = make_idesc_f16(128, dpad, 0, 1);   // B = V is MN-major

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...engine import ACT, PackedModule, f32, head_pad, packw, qkv_workspace, require_cuda, zero_workspace
+from ...engine import ACT, PackedModule, f32, packw, require_cuda
 
 GEGLU_BN = ops.GEGLU_BN  # N tile of the fused GEGLU projection (x / gate rows interleaved per 64 output columns)
 
@@ -165,25 +165,18 @@ class CrossAttention(PackedModule, LoraBranches):
              residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x2d: bf16 [batch*nq, query_dim]; ctx2d: bf16 [batch*nk, context_dim] or None for self-attention."""
         p = self.packed(x2d.device)
-        h, d = self.heads, self.dim_head
-        dpad = head_pad(d)
-        dev = x2d.device
+        h, d, inner = self.heads, self.dim_head, self.inner_dim
         if ctx2d is None:
             if "wqkv" not in p:
                 raise ValueError("self-attention requested on a CrossAttention built with a different context_dim")
             nk = nq
-            qkv = qkv_workspace("qkv", 3, 2, batch * h, nq, d, dpad, dev)
-            ops.igemm(x2d, p["wqkv"], 3 * self.inner_dim, mode=ops.EPI_HEADS, out=qkv,
-                      heads=(d, dpad, h, nq, batch * h * nq * dpad))
-            q, k, v = qkv[0], qkv[1], qkv[2]
+            qkv = ops.igemm(x2d, p["wqkv"], 3 * inner)             # [M, q | k | v]: read in place by the attention kernel
+            q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
         else:
-            qb = zero_workspace(f"q_d{d}", (1, batch * h, nq, dpad), dev)
-            kv = qkv_workspace("kv", 2, 1, batch * h, nk, d, dpad, dev)
-            ops.igemm(x2d, p["wq"], self.inner_dim, mode=ops.EPI_HEADS, out=qb, heads=(d, dpad, h, nq, 0))
-            ops.igemm(ctx2d, p["wkv"], 2 * self.inner_dim, mode=ops.EPI_HEADS, out=kv,
-                      heads=(d, dpad, h, nk, batch * h * nk * dpad))
-            q, k, v = qb[0], kv[0], kv[1]
-        a = ops.attention(q, k, v, batch, h, nq, nk, d, dpad, self.scale)
+            q = ops.igemm(x2d, p["wq"], inner)
+            kv = ops.igemm(ctx2d, p["wkv"], 2 * inner)
+            k, v = kv[:, :inner], kv[:, inner:]
+        a = ops.attention(q, k, v, batch, h, nq, nk, d, self.scale)
         return ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
 
     def forward(self, x, context=None, mask=None):

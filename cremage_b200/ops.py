@@ -326,12 +326,16 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
 # attention / norms
 # ------------------------------------------------------------------------------------------------------------------
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batch: int, heads: int, nq: int, nk: int, d: int,
-              dpad: int, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q,k,v: bf16 [batch*heads, tokens, dpad] -> out bf16 [batch*nq, heads*d]."""
+              scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q: 16-bit [batch*nq, heads*d] (a column slice of a wider projection output is fine: row stride = q.stride(0));
+    k, v: [batch*nk, heads*d] likewise -> out 16-bit [batch*nq, heads*d]."""
     _need_cuda(q, k, v)
+    for t, n in ((q, nq), (k, nk), (v, nk)):
+        assert t.dtype == ACT and t.dim() == 2 and t.stride(1) == 1 and t.shape == (batch * n, heads * d), (t.shape, t.stride())
     if out is None:
         out = torch.empty((batch * nq, heads * d), dtype=ACT, device=q.device)
-    _launch("cb_attention", lambda: _lib.load().cb_attention(_p(q), _p(k), _p(v), _p(out), batch, heads, nq, nk, d, dpad, scale, _stream()),
+    _launch("cb_attention", lambda: _lib.load().cb_attention(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+                                                             batch, heads, nq, nk, d, scale, _stream()),
             flops=4.0 * batch * heads * nq * nk * d, tag=f"bh={batch * heads} nq={nq} nk={nk} d={d}")
     return out
 

@@ -94,11 +94,13 @@ int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
 /* ---------------------------------------------------------------------------------------------------------------
  * fused flash-style attention on tcgen05 (QK^T -> online softmax -> PV), replaces
  *   CrossAttention / CrossAttentionOriginal / MemoryEfficientCrossAttention cores  ldm/modules/attention.py:418-423,646-657,811
- * q,k,v: 16-bit [bh][tokens][dpad] (dpad multiple of 64, pad columns zero, EXCEPT when dpad > d: column d of v must
- * hold 1.0 -- the tensor core then accumulates the softmax row sum in O[:, d]); out: 16-bit [b][nq][heads*d]
+ * q, k, v: 16-bit, read in place from the projection GEMMs' row-major outputs: element (b, token, head, j) lives at
+ * base[(b * tokens + token) * ld + head * d + j] (ld = elements between rows, >= heads * d, multiple of 8; q/k/v may be
+ * column slices of one [tokens, 3 * heads * d] tensor).  The head dim is padded to a multiple of 64 inside the kernel by
+ * TMA's out-of-bounds zero fill.  out: 16-bit [b][nq][heads*d]
  * ------------------------------------------------------------------------------------------------------------- */
-int cb_attention(const void* q, const void* k, const void* v, void* out, int64_t batch, int64_t heads, int64_t nq,
-                 int64_t nk, int d, int dpad, float scale, cudaStream_t stream);
+int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, void* out,
+                 int64_t batch, int64_t heads, int64_t nq, int64_t nk, int d, float scale, cudaStream_t stream);
 
 /* row softmax: dst[r][:] = softmax(scale * src[r][:]); src fp32 (src_f32 = 1) or bf16, dst bf16 (may alias a bf16
  * src); VAE AttnBlock, ldm/modules/diffusionmodules/model.py:196-198 */

@@ -52,13 +52,14 @@ def bench_attn(B, iters, warm):
                                    ("self 16x16 d160", 8, 256, 256, 160), ("self 8x8 d160", 8, 64, 64, 160),
                                    ("cross 64x64 d40", 8, 4096, 77, 40), ("cross 32x32 d80", 8, 1024, 77, 80),
                                    ("cross 16x16 d160", 8, 256, 77, 160)]:
-        dpad = (d + 63) // 64 * 64
-        q, k, v = act(B * heads, nq, dpad), act(B * heads, nk, dpad), act(B * heads, nk, dpad)
-        for t in (q, k, v):
-            t[..., d:] = 0
-        if dpad > d:
-            v[..., d] = 1.0
-        ms = timeit(lambda: ops.attention(q, k, v, B, heads, nq, nk, d, dpad, d ** -0.5), iters, warm)
+        inner = heads * d
+        if nq == nk:   # self-attention: q | k | v column slices of one projection output, as the modules run it
+            qkv = act(B * nq, 3 * inner)
+            q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
+        else:
+            q, kv = act(B * nq, inner), act(B * nk, 2 * inner)
+            k, v = kv[:, :inner], kv[:, inner:]
+        ms = timeit(lambda: ops.attention(q, k, v, B, heads, nq, nk, d, d ** -0.5), iters, warm)
         fl = 4.0 * B * heads * nq * nk * d
         print(f"{name:22s} bh={B * heads:4d} nq={nq:5d} nk={nk:5d} d={d:3d}: {ms:8.3f} ms  {fl / ms / 1e9:8.1f} TFLOP/s  "
               f"{fl / ms / 1e9 / tf_peak:6.1%} of burst peak")
