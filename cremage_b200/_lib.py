@@ -40,7 +40,7 @@ class IGemmDesc(C.Structure):
         ("out_scale", C.c_float),
         ("heads_d", C.c_int), ("heads_dpad", C.c_int), ("heads_h", C.c_int), ("heads_tokens", C.c_int),
         ("heads_which_stride", C.c_int64),
-        ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int), ("cta_pair", C.c_int), ("nsub", C.c_int),
+        ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int), ("cta_pair", C.c_int), ("nsub", C.c_int), ("ksplit", C.c_int),
     ]
 
 
@@ -66,6 +66,7 @@ SIGNATURES = {
     "cb_timestep_embedding": [_vp, _i64, _int, _vp, _vp, _vp],
     "cb_conv3x3_small_cin": [_vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _i64, _vp, _vp],
     "cb_silu_add": [_vp, _vp, _i64, _vp, _vp],
+    "cb_splitk_reduce": [_vp, _int, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp],
     "cb_diag_gaussian": [_vp, _vp, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp],
     "cb_cfg_scale_input": [_vp, _i64, _i64, _f32, _vp, _vp],
     "cb_axpby_f32": [_vp, _f32, _vp, _f32, _i64, _vp, _vp],

@@ -45,6 +45,8 @@ struct IGemmKParams {
   int two, m_pairs;      // CTA-pair mode (cta_group::2): a cluster of 2 CTAs owns M tiles 2*mp, 2*mp+1 of one N tile
   int nsub, n_groups;    // N sub-tiles that share one A stage (1 or 2), groups of sub-tiles = ceil(n_tiles / nsub)
   int nacc;              // TMEM accumulator ring: 2 slots (nsub 1) or 3 slots (nsub 2: 3 x bn <= 512 columns)
+  int ksplit, taps_per_split, num_k_split;   // split-K by tap groups: work item (tile, s) reduces taps [s*tps, (s+1)*tps)
+  long long split_stride;                    // elements between the fp32 partial outputs of consecutive splits
   int resident_b;        // 1: B of this CTA's N tile stays in smem, CTA walks M tiles of that N tile
   int m_step;            // resident mode: stride between the M tiles of one CTA ( = gridDim.x / n_tiles )
   // K loop
@@ -79,12 +81,13 @@ struct TileSched {
   const IGemmKParams& p;
   __device__ explicit TileSched(const IGemmKParams& pp) : p(pp) {}
   __device__ __forceinline__ bool get(int i, int& mt, int& nt) const {
-    // `nt` is the N GROUP index: the group's sub-tiles are n-tiles nt*nsub .. nt*nsub + nsub-1 (see subs())
+    // `nt` is the N GROUP index: the group's sub-tiles are n-tiles nt*nsub .. nt*nsub + nsub-1 (see subs());
+    // with split-K the K-split index rides in the upper bits: nt = s * n_groups + group (see split() / group())
     if (p.two) {
       const long long t = (long long)(blockIdx.x >> 1) + (long long)i * (gridDim.x >> 1);
-      if (t >= (long long)p.m_pairs * p.n_groups) return false;
-      nt = int(t % p.n_groups);
-      mt = 2 * int(t / p.n_groups) + int(blockIdx.x & 1);   // may be == m_tiles (odd count): an all-out-of-bounds tile
+      if (t >= (long long)p.m_pairs * p.n_groups * p.ksplit) return false;
+      nt = int(t % (p.n_groups * p.ksplit));
+      mt = 2 * int(t / (p.n_groups * p.ksplit)) + int(blockIdx.x & 1);   // may be == m_tiles (odd count): an all-out-of-bounds tile
       return true;
     }
     if (p.resident_b) {
@@ -93,11 +96,13 @@ struct TileSched {
       return mt < p.m_tiles;
     }
     const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
-    if (t >= (long long)p.m_tiles * p.n_groups) return false;
-    nt = int(t % p.n_groups);
-    mt = int(t / p.n_groups);
+    if (t >= (long long)p.m_tiles * p.n_groups * p.ksplit) return false;
+    nt = int(t % (p.n_groups * p.ksplit));
+    mt = int(t / (p.n_groups * p.ksplit));
     return true;
   }
+  __device__ __forceinline__ int split(int nt) const { return p.ksplit == 1 ? 0 : nt / p.n_groups; }
+  __device__ __forceinline__ int group(int nt) const { return p.ksplit == 1 ? nt : nt % p.n_groups; }
   template <int NSUB>
   __device__ __forceinline__ int subs(int ng) const {   // sub-tiles of group ng that exist
     if (NSUB == 1) return 1;
@@ -366,11 +371,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const int th = (mt / p.tiles_w) % p.tiles_h;
         const int tn = mt / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
-        const int subs = sched.subs<NSUB>(nt);
+        const int ng = sched.group(nt), ks = sched.split(nt);
+        const int subs = sched.subs<NSUB>(ng);
         const uint32_t tx_bytes = A_STAGE_BYTES + (p.resident_b ? 0u : uint32_t(subs) * b_chunk_bytes);
-        const int brow0 = nt * NSUB * p.bn;   // first weight row of the group
-        int tap = 0, ch = 0;
-        for (int kt = 0; kt < p.num_k; ++kt) {
+        const int brow0 = ng * NSUB * p.bn;   // first weight row of the group
+        int tap = ks * p.taps_per_split, ch = 0;
+        for (int kt = ks * p.num_k_split, kt_end = kt + p.num_k_split; kt < kt_end; ++kt) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = ring_base + uint32_t(stage) * stage_bytes;
           const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], cn = n0 + p.tap_dn[tap];
@@ -404,7 +410,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       bool b_ready = !p.resident_b;
       int acc_cnt = 0;   // accumulator ring position (sub-tiles issued so far)
       for (int i = 0; sched.get(i, mt, nt); ++i) {
-        const bool dual = DUAL && sched.subs<NSUB>(nt) > 1;
+        const bool dual = DUAL && sched.subs<NSUB>(sched.group(nt)) > 1;
         // (scalars, not arrays: a dynamically indexed array would live in local memory on the issue path)
         const int slot0 = acc_cnt % NACC, slot1 = (acc_cnt + 1) % NACC;
         mbar_wait(acc_empty(slot0), (uint32_t(acc_cnt / NACC) & 1u) ^ 1u);   // epilogue drained the slot (first round passes)
@@ -416,7 +422,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         // K loop; the sub-tile count is hoisted out of the issue loop (a branch per MMA costs ~20 % on this thread)
         auto k_loop = [&](auto both_tag) {
           constexpr bool BOTH = decltype(both_tag)::value;
-          for (int kt = 0; kt < p.num_k; ++kt) {
+          for (int kt = 0; kt < p.num_k_split; ++kt) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t sa = ring_base + uint32_t(stage) * stage_bytes;
@@ -466,9 +472,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     const int ocols = GEGLU ? (p.bn >> 1) : p.bn;   // output columns per tile
     int mt, ng;
     int acc_cnt = 0;
-    for (int i = 0; sched.get(i, mt, ng); ++i)
-    for (int sub = 0, subs = sched.subs<NSUB>(ng); sub < subs; ++sub, ++acc_cnt) {
+    int ngs;
+    for (int i = 0; sched.get(i, mt, ngs); ++i)
+    for (int sub = 0, subs = sched.subs<NSUB>(ng = sched.group(ngs)); sub < subs; ++sub, ++acc_cnt) {
       const int nt = ng * NSUB + sub;
+      const int ksi = sched.split(ngs);
       const int buf = acc_cnt % NACC;
       const uint32_t use = uint32_t(acc_cnt / NACC);
       const int tw = mt % p.tiles_w;
@@ -527,7 +535,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
         }
       } else {
-        epilogue_tile_direct<EPI>(p, trow, sb, nt, n, row_ok, row, hh);
+        // split-K: this work item's fp32 partial goes to its own slab of the workspace
+        epilogue_tile_direct<EPI>(p, trow, sb, nt, n, row_ok, row + (long long)ksi * (p.split_stride / p.out_ld), hh);
       }
       tc_fence_before();
       __syncwarp();                  // every lane of this warp has drained its TMEM lanes
@@ -621,6 +630,19 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.m_tiles = p.tiles_w * p.tiles_h * tiles_n;
   p.n_tiles = int((d->mode == CB_EPI_GEGLU ? 2 * d->cout : d->cout) + d->bn - 1) / d->bn;
   p.taps = d->taps; p.chunks0 = chunks0; p.chunks1 = chunks1; p.num_k = num_k;
+  // split-K by tap groups (the M <= 1024 convs: too few tiles for 148 SMs, long K): every work item writes an fp32
+  // partial; cb_splitk_reduce folds the partials in split order and applies the epilogue (deterministic)
+  const int ksplit = d->ksplit > 1 ? d->ksplit : 1;
+  if (ksplit > 1) {
+    CB_REQUIRE(d->taps % ksplit == 0, "cb_igemm: ksplit %d does not divide %d taps", ksplit, d->taps);
+    CB_REQUIRE(d->mode == CB_EPI_LINEAR && d->out_f32 && !d->bias && !d->rowbias && !d->residual && d->act == CB_ACT_NONE &&
+               (d->out_scale == 0.f || d->out_scale == 1.f),
+               "cb_igemm: split-K launches write raw fp32 partials (no bias / activation / residual; cb_splitk_reduce applies them)");
+  }
+  p.ksplit = ksplit;
+  p.taps_per_split = d->taps / ksplit;
+  p.num_k_split = p.taps_per_split * (chunks0 + chunks1);
+  p.split_stride = d->n * d->h * d->w * d->out_ld;
   for (int i = 0; i < 9; ++i) { p.tap_dw[i] = d->tap_dw[i]; p.tap_dh[i] = d->tap_dh[i]; p.tap_dn[i] = d->tap_dn[i]; }
   p.cout = (int)d->cout; p.bn = d->bn;
   const bool two = d->cta_pair != 0;
@@ -695,7 +717,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   const size_t res_bytes = (size_t)num_k * b_chunk;
   int resident = 0;
   unsigned grid = 0;
-  if (!two && d->stages <= 0 && p.n_tiles <= g_num_sms &&
+  if (!two && ksplit == 1 && d->stages <= 0 && p.n_tiles <= g_num_sms &&
       res_bytes + 4 * (size_t)A_STAGE_BYTES + staging + fixed <= (size_t)SMEM_LIMIT) {
     const int ctas_per_nt = g_num_sms / p.n_tiles;
     if (ctas_per_nt >= 1 && p.m_tiles >= 3 * ctas_per_nt) {
@@ -716,11 +738,11 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   const size_t smem = (resident ? res_bytes : 0) + (size_t)stages * stage_bytes + staging + fixed;
   CB_REQUIRE(smem <= (size_t)SMEM_LIMIT, "cb_igemm: tile needs %zu bytes of shared memory", smem);
   if (two) {
-    const long long total = (long long)p.m_pairs * p.n_groups;
+    const long long total = (long long)p.m_pairs * p.n_groups * ksplit;
     const long long clusters = total < g_num_sms / 2 ? total : g_num_sms / 2;
     grid = (unsigned)(2 * clusters);
   } else if (!resident) {
-    const long long total = (long long)p.m_tiles * p.n_groups;
+    const long long total = (long long)p.m_tiles * p.n_groups * ksplit;
     grid = (unsigned)(total < g_num_sms ? total : g_num_sms);
   }
 
@@ -768,6 +790,72 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   } else {
     kfn<<<grid, NUM_THREADS, smem, stream>>>(mapA0, mapA1, mapB, mapO, mapR, p);
   }
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+
+// ----------------------------------------------------------------------------------------------------------------------
+// split-K reduction: out[r][c] = act?(sum_s part[s][r][c] + bias[c] + rowbias[n(r)][c]) + residual[r][c]  -> 16-bit
+// (partials summed in split order -> deterministic; 8 columns per thread, 16-byte accesses)
+// ----------------------------------------------------------------------------------------------------------------------
+namespace cb {
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long long split_stride, long long rows,
+                                     int cout, long long part_ld, const float* __restrict__ bias,
+                                     const float* __restrict__ rowbias, long long rowbias_ld, long long rows_per_image,
+                                     const act_t* __restrict__ residual, long long res_ld, act_t* __restrict__ out,
+                                     long long out_ld) {
+  const int cv = cout >> 3;
+  const long long total = rows * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cv;
+    const int c = int(i - r * cv) << 3;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(part + s * split_stride + r * part_ld + c);
+      const float4 b = *reinterpret_cast<const float4*>(part + s * split_stride + r * part_ld + c + 4);
+      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    if (bias) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += __ldg(bias + c + e);
+    }
+    if (rowbias) {
+      const float* rb = rowbias + (r / rows_per_image) * rowbias_ld + c;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += __ldg(rb + e);
+    }
+    if (residual) {
+      const uint4 rv = *reinterpret_cast<const uint4*>(residual + r * res_ld + c);
+      const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack_act2(ru[e]);
+        f[2 * e] += t.x;
+        f[2 * e + 1] += t.y;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + r * out_ld + c) =
+        make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+  }
+}
+}  // namespace cb
+
+extern "C" int cb_splitk_reduce(const float* part, int splits, int64_t rows, int64_t cout, int64_t part_ld, const float* bias,
+                                const float* rowbias, int64_t rowbias_ld, int64_t rows_per_image, const void* residual,
+                                int64_t res_ld, void* out, int64_t out_ld, cudaStream_t stream) {
+  CB_REQUIRE(part && out && splits >= 1 && rows > 0 && cout > 0 && cout % 8 == 0, "cb_splitk_reduce: bad arguments");
+  CB_REQUIRE(part_ld % 4 == 0 && out_ld % 8 == 0 && (!residual || res_ld % 8 == 0), "cb_splitk_reduce: unaligned leading dimensions");
+  CB_REQUIRE(!rowbias || rows_per_image > 0, "cb_splitk_reduce: rowbias needs rows_per_image");
+  const long long total = rows * (cout / 8);
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 8) g = 148LL * 8;
+  splitk_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(part, splits, rows * part_ld, rows, (int)cout, part_ld, bias, rowbias,
+                                                        rowbias_ld, rows_per_image, (const act_t*)residual, res_ld,
+                                                        (act_t*)out, out_ld);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

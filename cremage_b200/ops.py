@@ -159,6 +159,7 @@ def choose_tile(n: int, h: int, w: int) -> Tuple[int, int, int]:
 
 NUM_SMS = 148  # B200
 PAIR_DEFAULT = True
+SPLITK_DEFAULT = True
 
 
 def choose_bn(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
@@ -175,11 +176,12 @@ def choose_bn(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
     return best[1]
 
 
-def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32) -> Tuple[int, int]:
-    """(bn, nsub) in CTA-pair mode (74 clusters, each a 256-row tile).  nsub = 2: two N tiles share every A stage
-    (cb_igemm's sub-tile groups, 3 * bn <= 512).  Cost of a round ~ MMA columns of the tile group; tiles narrower
-    than 256 columns are shared-memory-fill bound (x1.25), and below 128 columns the single issuing thread cannot keep
-    the tensor core fed, so narrower tiles cost as much as 128."""
+def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32, splits: Sequence[int] = (1,)) -> Tuple[int, int, int]:
+    """(bn, nsub, ksplit) in CTA-pair mode (74 clusters, each a 256-row tile).  nsub = 2: two N tiles share every A stage
+    (cb_igemm's sub-tile groups, 3 * bn <= 512).  ksplit > 1: K split by tap groups over otherwise idle clusters
+    (fp32 partials + cb_splitk_reduce).  Cost of a round ~ MMA columns of the tile group; tiles narrower than 256
+    columns are shared-memory-fill bound (x1.25), and below 128 columns the single issuing thread cannot keep the
+    tensor core fed, so narrower tiles cost as much as 128; a split adds a fixed per-item and a reduce cost."""
     best = None
     m_pairs = (m_tiles + 1) // 2
     for bn in (256, 160, 128, 64, 32):
@@ -192,10 +194,12 @@ def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32) -> Tuple[in
             groups = -(-n_tiles // nsub)
             width = nsub * bn
             per = (nsub * max(bn, 128) + 16) * (1.0 if width >= 256 else 1.25)
-            cost = (-(-(m_pairs * groups) // (NUM_SMS // 2))) * per
-            if best is None or cost < best[0]:
-                best = (cost, bn, nsub)
-    return best[1], best[2]
+            for ks in splits:
+                items = m_pairs * groups * ks
+                cost = (-(-items // (NUM_SMS // 2))) * (per / ks + (24 if ks > 1 else 0)) + (30 if ks > 1 else 0)
+                if best is None or cost < best[0]:
+                    best = (cost, bn, nsub, ks)
+    return best[1], best[2], best[3]
 
 
 import os as _os
@@ -248,7 +252,8 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
           mode: int = EPI_LINEAR, out: Optional[torch.Tensor] = None, out_f32: bool = False, out_ld: Optional[int] = None,
           out_scale: float = 1.0, heads: Optional[Tuple[int, int, int, int, int]] = None, bn: Optional[int] = None,
-          stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None, nsub: int = 0) -> torch.Tensor:
+          stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None, nsub: int = 0,
+          ksplit: Optional[int] = None) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
@@ -274,17 +279,31 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         pair = PAIR_DEFAULT and num_k >= PAIR_MIN_K_CHUNKS and m_tiles >= PAIR_MIN_M_TILES
         if mode == EPI_GEGLU:
             pair = bool(GEGLU_PAIR) and m_tiles >= PAIR_MIN_M_TILES
+    # split-K (by tap groups) is available to plain 16-bit 3x3 convs; the reduce kernel applies bias / row bias / residual
+    can_split = (pair and mode == EPI_LINEAR and len(taps[0]) == 9 and not out_f32 and act == ACT_NONE and
+                 out_scale == 1.0 and cout % 8 == 0 and (out is None or out.shape[-1] % 8 == 0))
     if bn is None:
         if pair:
-            bn, auto_nsub = choose_bn_pair(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
+            bn, auto_nsub, auto_ks = choose_bn_pair(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32,
+                                                    splits=(1, 3) if (can_split and ksplit is None and SPLITK_DEFAULT) else (1,))
             if nsub == 0:
                 nsub = auto_nsub
+            if ksplit is None:
+                ksplit = auto_ks
         else:
             bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
+    ksplit = ksplit if (ksplit and can_split) else 1
     if out is None:
         ld = out_ld if out_ld is not None else cout
         out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
     ld = out_ld if out_ld is not None else (out.shape[-1] if mode != EPI_HEADS else 0)
+
+    final = None
+    if ksplit > 1:   # raw fp32 partials now, epilogue in cb_splitk_reduce
+        final = (out, bias, rowbias, residual, ld)
+        out = torch.empty((ksplit, rows, cout), dtype=torch.float32, device=a0.device)
+        bias = rowbias = residual = None
+        ld = cout
 
     d = IGemmDesc()
     d.a0, d.c0, d.a0_ld = _p(a0), c0, 0
@@ -312,13 +331,20 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     d.out_scale = out_scale
     if heads is not None:
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
-    d.bn, d.stages, d.epilogue, d.cta_pair, d.nsub = bn, stages, epilogue, int(bool(pair)), nsub
+    d.bn, d.stages, d.epilogue, d.cta_pair, d.nsub, d.ksplit = bn, stages, epilogue, int(bool(pair)), nsub, ksplit
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
             flops=2.0 * rows * len(dw) * (c0 + c1) * ncols,
-            tag=f"M={rows} K={len(dw) * (c0 + c1)} N={ncols} taps={len(dw)} bn={bn}{'x2' if pair else ''} epi={mode}"
+            tag=f"M={rows} K={len(dw) * (c0 + c1)} N={ncols} taps={len(dw)} bn={bn}{'x2' if pair else ''}{f'/k{ksplit}' if ksplit > 1 else ''} epi={mode}"
                 f"{'+res' if residual is not None else ''}{'+rowb' if rowbias is not None else ''}"
                 f"{'+act' if act else ''}{'+f32' if out_f32 else ''}" if _PROF is not None else "")
+    if final is not None:
+        part = out
+        out, bias, rowbias, residual, ld = final
+        _launch("cb_splitk_reduce", lambda: _lib.load().cb_splitk_reduce(
+            _p(part), ksplit, rows, cout, cout, _p(bias), _p(rowbias), rowbias.stride(0) if rowbias is not None else 0,
+            h * w, _p(residual), residual.shape[-1] if residual is not None else 0, _p(out), ld, _stream()),
+            nbytes=4.0 * ksplit * rows * cout + 2.0 * rows * cout)
     return out
 
 

@@ -87,9 +87,17 @@ typedef struct cb_igemm_desc {
   int epilogue;          /* CB_EPILOGUE_* (tuning / test knob; results are identical) */
   int cta_pair;          /* 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2, cluster of 2); bn % 32 == 0 */
   int nsub;              /* pair mode: 0 = auto (two N tiles share each A stage when 3 * bn <= 512), 1 = never */
+  int ksplit;            /* > 1: split K by tap groups; `out` must be an fp32 workspace [ksplit][rows][out_ld], no
+                          * bias / rowbias / residual / activation here -- cb_splitk_reduce applies them */
 } cb_igemm_desc;
 
 int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
+
+/* fold the fp32 partials of a split-K cb_igemm in split order (deterministic) and apply the epilogue:
+ * out[r][c] = sum_s part[s][r][c] + bias[c] + rowbias[r / rows_per_image][c] + residual[r][c]  -> 16-bit */
+int cb_splitk_reduce(const float* part, int splits, int64_t rows, int64_t cout, int64_t part_ld, const float* bias,
+                     const float* rowbias, int64_t rowbias_ld, int64_t rows_per_image, const void* residual,
+                     int64_t res_ld, void* out, int64_t out_ld, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * fused flash-style attention on tcgen05 (QK^T -> online softmax -> PV), replaces

@@ -245,3 +245,33 @@ def test_cta_pair_dual_n_subtiles_equal_single(n, h, w, cin, cout, bn):
     assert torch.equal(single, dual) and torch.equal(single, nodual) and torch.equal(single, staged)
     want = F.conv2d(x.float(), wt.to(ACT).float(), b.cpu(), padding=1) + emb.cpu()[:, :, None, None]
     _close(dual.view(n, h, w, cout).permute(0, 3, 1, 2), want)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(16, 8, 8, 128, 256), (4, 8, 8, 192, 96), (3, 16, 16, 64, 160), (16, 8, 8, 320, 1280)])
+@pytest.mark.parametrize("what", ["bias", "rowbias", "res"])
+def test_split_k_conv(n, h, w, cin, cout, what):
+    """Split-K by tap groups (fp32 partials + cb_splitk_reduce) for the few-tile / long-K convs of the 8x8 level."""
+    ops = _ops()
+    x = _rand(n, cin, h, w, seed=5).to(ACT)
+    wt = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=6)
+    b = _rand(cout, seed=7).cuda()
+    kw = {}
+    if what == "rowbias":
+        kw["rowbias"] = _rand(n, cout, seed=8).cuda()
+    if what == "res":
+        kw["residual"] = _rand(n * h * w, cout, seed=9).to(ACT).cuda()
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wp = ops.pack_weight(wt).cuda()
+    one = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=True, ksplit=1, **kw)
+    for ks in (3, 9):
+        split = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=True, ksplit=ks, **kw)
+        again = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=True, ksplit=ks, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(split, again)                                   # deterministic
+        assert (split.float() - one.float()).abs().max().item() <= 2e-2   # same sum, different fp32 association
+    want = F.conv2d(x.float(), wt.to(ACT).float(), b.cpu(), padding=1)
+    if what == "rowbias":
+        want = want + kw["rowbias"].cpu()[:, :, None, None]
+    if what == "res":
+        want = want + kw["residual"].float().cpu().view(n, h, w, cout).permute(0, 3, 1, 2)
+    _close(split.view(n, h, w, cout).permute(0, 3, 1, 2), want)
