@@ -41,20 +41,14 @@ struct AttnParams {
   act_t* out;
 };
 
-// p = 2^(s * scale - m) for two scores -> packed 16-bit pair
+// p = 2^(s * scale - m) for two scores -> packed 16-bit pair.  fp32 MUFU.EX2 then one packing convert: the packed
+// `ex2.approx.f16x2` form lowers to two MUFU.EX2.F16 plus a PRMT (same MUFU count, one more ALU instruction per pair).
 CB_DEVINL uint32_t exp2_pack(float s0, float s1, float scale, float m) {
   const float a0 = fmaf(s0, scale, -m), a1 = fmaf(s1, scale, -m);
-#ifdef CB_FP16
-  const __half2 h = __floats2half2_rn(a0, a1);
-  uint32_t r;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&h)));
-  return r;
-#else
   float e0, e1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
   return pack_act2(e0, e1);
-#endif
 }
 
 template <bool USE_ONES>
