@@ -35,7 +35,7 @@ constexpr int ATT_THREADS = 384;         // TMA warp, issuer (tile 0), 8 softmax
 constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
-  int nq, nk, d, dpad, np, heads, stages, nwg, use_ones, p_alias;
+  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias;
   float scale_log2;
   uint32_t idesc_qk, idesc_pv, tmem_cols;
   act_t* out;
@@ -73,30 +73,38 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   auto s_free = [&](int w) { return bars + 168u + 8u * uint32_t(w); };
   auto pv_done = [&](int w) { return bars + 184u + 8u * uint32_t(w); };
   auto v_ready = [&](int s) { return bars + 200u + 8u * uint32_t(s); };   // V tile landed AND its ones column written
-  const uint32_t tmem_slot = bars + 232u;
+  const uint32_t q_free = bars + 232u;                                     // every Q*K^T of the item has been issued and completed
+  auto o_free = [&](int w) { return bars + 240u + 8u * uint32_t(w); };     // the item's O has been read out of TMEM
+  const uint32_t tmem_slot = bars + 256u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int bh = blockIdx.y;
-  const int b_idx = bh / p.heads, h_idx = bh - b_idx * p.heads;
-
   const int nblk = (p.nk + ATT_BN - 1) / ATT_BN;
-  const int q_first = blockIdx.x * p.nwg * ATT_BM;                              // first query row of this CTA
-  const int nact = (p.nwg == 2 && q_first + ATT_BM < p.nq) ? 2 : 1;            // active query tiles
+  // persistent CTA: work items (batch*head, query-tile pair) blockIdx.x, + gridDim.x, ...  Barrier phases and the
+  // K/V ring position run on GLOBAL counters across items, so the producer prefetches the next item's Q / K / V
+  // while the softmax groups still finish the current one, and the per-CTA set-up is paid once.
+  const int rows_per_item = p.nwg * ATT_BM;
+  const int qpairs = (p.nq + rows_per_item - 1) / rows_per_item;
+  const int total_items = qpairs * p.bh;
+  auto item_q_first = [&](int item) { return (item % qpairs) * rows_per_item; };
+  auto item_bh = [&](int item) { return item / qpairs; };
+  auto item_nact = [&](int item) { return (p.nwg == 2 && item_q_first(item) + ATT_BM < p.nq) ? 2 : 1; };
 
   if (tid == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 4; ++s) {   // a stage is free once the issuer of every active tile has committed it
-      mbar_init(k_full(s), 1); mbar_init(k_empty(s), uint32_t(nact));
-      mbar_init(v_full(s), 1); mbar_init(v_empty(s), uint32_t(nact));
+    mbar_init(q_free, uint32_t(p.nwg));
+    for (int s = 0; s < 4; ++s) {   // a stage is free once BOTH issuers are done with it (an idle one just arrives)
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), uint32_t(p.nwg));
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), uint32_t(p.nwg));
     }
     for (int s = 0; s < 4; ++s) mbar_init(v_ready(s), 32);
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full(s), 1); mbar_init(p_full(s), ATT_BM);
       mbar_init(s_free(s), ATT_BM); mbar_init(pv_done(s), 1);
+      mbar_init(o_free(s), ATT_BM);
     }
     fence_mbar_init();
   }
@@ -114,34 +122,42 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   auto tP = [&](int w) {
     return p.p_alias ? tS(w) : tmem_base + uint32_t(p.nwg) * (128u + uint32_t(p.dpad)) + uint32_t(w) * 64u;
   };
+  auto stage_of = [&](int g) { return g % p.stages; };
+  auto phase_of = [&](int g) { return uint32_t((g / p.stages) & 1); };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(q_full, uint32_t(nact) * tile_bytes);
-      for (int w = 0; w < nact; ++w)
-        for (int pn = 0; pn < p.np; ++pn)
-          tma_load_4d(sQ + uint32_t(w) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapQ, q_full, pn * 64,
-                      q_first + w * ATT_BM, h_idx, b_idx);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j % p.stages;
-        const uint32_t ph = uint32_t((j / p.stages) & 1);
-        mbar_wait(k_empty(st), ph ^ 1u);
-        mbar_expect_tx(k_full(st), tile_bytes);
-        for (int pn = 0; pn < p.np; ++pn)
-          tma_load_4d(sK + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapK, k_full(st), pn * 64, j * ATT_BN,
-                      h_idx, b_idx);
-        mbar_wait(v_empty(st), ph ^ 1u);
-        mbar_expect_tx(v_full(st), tile_bytes);
-        for (int pn = 0; pn < p.np; ++pn)
-          tma_load_4d(sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapV, v_full(st), pn * 64, j * ATT_BN,
-                      h_idx, b_idx);
+      int it = 0, g = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        const int bh = item_bh(item), q_first = item_q_first(item), nact = item_nact(item);
+        const int b_idx = bh / p.heads, h_idx = bh - b_idx * p.heads;
+        mbar_wait(q_free, uint32_t(it & 1) ^ 1u);     // previous item's Q*K^T are complete (first item passes)
+        mbar_expect_tx(q_full, uint32_t(nact) * tile_bytes);
+        for (int w = 0; w < nact; ++w)
+          for (int pn = 0; pn < p.np; ++pn)
+            tma_load_4d(sQ + uint32_t(w) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapQ, q_full, pn * 64,
+                        q_first + w * ATT_BM, h_idx, b_idx);
+        for (int j = 0; j < nblk; ++j, ++g) {
+          const int st = stage_of(g);
+          const uint32_t ph = phase_of(g);
+          mbar_wait(k_empty(st), ph ^ 1u);
+          mbar_expect_tx(k_full(st), tile_bytes);
+          for (int pn = 0; pn < p.np; ++pn)
+            tma_load_4d(sK + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapK, k_full(st), pn * 64, j * ATT_BN,
+                        h_idx, b_idx);
+          mbar_wait(v_empty(st), ph ^ 1u);
+          mbar_expect_tx(v_full(st), tile_bytes);
+          for (int pn = 0; pn < p.np; ++pn)
+            tma_load_4d(sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapV, v_full(st), pn * 64, j * ATT_BN,
+                        h_idx, b_idx);
+        }
       }
     }
   } else if (warp == 1 || warp == 10) {
     // ===================== MMA issuers (one thread per query tile) =====================
     const int w = (warp == 1) ? 0 : 1;
-    if (lane == 0 && w < nact) {
+    if (lane == 0 && w < p.nwg) {
       auto issue_qk = [&](int kstage) {
         const uint32_t qb = sQ + uint32_t(w) * tile_bytes, kb = sK + uint32_t(kstage) * tile_bytes;
         const int ksteps = p.dpad / 16;
@@ -159,70 +175,95 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                   p.idesc_pv, (accumulate || ks != 0) ? 1u : 0u);
         }
       };
-      auto stage_of = [&](int j) { return j % p.stages; };
-      auto phase_of = [&](int j) { return uint32_t((j / p.stages) & 1); };
-      auto do_qk = [&](int j) {     // Q*K^T of block j (j >= 1: once the scores of block j-1 are in registers)
-        if (j > 0) mbar_wait(s_free(w), uint32_t((j - 1) & 1));
-        mbar_wait(k_full(stage_of(j)), phase_of(j));
-        tc_fence_after();
-        issue_qk(stage_of(j));
-        umma_commit(s_full(w));
-        umma_commit(k_empty(stage_of(j)));
-      };
-      auto do_pv = [&](int j) {
-        mbar_wait(p_full(w), uint32_t(j & 1));
-        mbar_wait(v_ready(stage_of(j)), phase_of(j));
-        tc_fence_after();
-        issue_pv(stage_of(j), j > 0);
-        umma_commit(pv_done(w));
-        umma_commit(v_empty(stage_of(j)));
-      };
-      mbar_wait(q_full, 0);
-      do_qk(0);
-      for (int j = 0; j < nblk; ++j) {
-        if (p.p_alias) {            // P overwrites S: the next Q*K^T may only follow this block's P*V
-          do_pv(j);
-          if (j + 1 < nblk) do_qk(j + 1);
-        } else {
-          if (j + 1 < nblk) do_qk(j + 1);
-          do_pv(j);
+      int it = 0, g0 = 0;      // item count of this CTA, global block counter at the start of the item
+      int cw = 0, aw = 0;      // blocks / items this query tile has been ACTIVE for (phases of its private barriers)
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it, g0 += nblk) {
+        const bool active = w < item_nact(item);
+        mbar_wait(q_full, uint32_t(it & 1));
+        if (!active) {
+          // idle tile (ragged last query pair): stay in lockstep with the ring, release every stage it is handed
+          mbar_arrive(q_free);
+          for (int j = 0; j < nblk; ++j) {
+            mbar_wait(k_full(stage_of(g0 + j)), phase_of(g0 + j));
+            mbar_arrive(k_empty(stage_of(g0 + j)));
+            mbar_wait(v_ready(stage_of(g0 + j)), phase_of(g0 + j));
+            mbar_arrive(v_empty(stage_of(g0 + j)));
+          }
+          continue;
         }
+        auto do_qk = [&](int j) {     // Q*K^T of block j: once the scores of this tile's previous block are in registers
+          if (cw + j > 0) mbar_wait(s_free(w), uint32_t((cw + j - 1) & 1));
+          mbar_wait(k_full(stage_of(g0 + j)), phase_of(g0 + j));
+          tc_fence_after();
+          issue_qk(stage_of(g0 + j));
+          umma_commit(s_full(w));
+          umma_commit(k_empty(stage_of(g0 + j)));
+          if (j == nblk - 1) umma_commit(q_free);      // the item's last use of Q
+        };
+        auto do_pv = [&](int j) {
+          mbar_wait(p_full(w), uint32_t((cw + j) & 1));
+          mbar_wait(v_ready(stage_of(g0 + j)), phase_of(g0 + j));
+          if (j == 0 && aw > 0) mbar_wait(o_free(w), uint32_t((aw - 1) & 1));   // previous item's O has been read out
+          tc_fence_after();
+          issue_pv(stage_of(g0 + j), j > 0);
+          umma_commit(pv_done(w));
+          umma_commit(v_empty(stage_of(g0 + j)));
+        };
+        do_qk(0);
+        for (int j = 0; j < nblk; ++j) {
+          if (p.p_alias) {            // P overwrites S: the next Q*K^T may only follow this block's P*V
+            do_pv(j);
+            if (j + 1 < nblk) do_qk(j + 1);
+          } else {
+            if (j + 1 < nblk) do_qk(j + 1);
+            do_pv(j);
+          }
+        }
+        cw += nblk;
+        ++aw;
       }
     }
   } else if (warp == 11) {
     // ===================== V ones-column warp =====================
     // TMA zero-fills the pad columns of a V tile; column d becomes 1.0 so that P*V also yields the softmax row sum.
     const int pn = p.d >> 6, cw = p.d & 63;
-    for (int j = 0; j < nblk; ++j) {
-      const int st = j % p.stages;
-      mbar_wait(v_full(st), uint32_t((j / p.stages) & 1));
-      if (USE_ONES) {
-        const uint32_t tile = sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES;
+    int g = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int j = 0; j < nblk; ++j, ++g) {
+        const int st = stage_of(g);
+        mbar_wait(v_full(st), phase_of(g));
+        if (USE_ONES) {
+          const uint32_t tile = sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES;
 #ifdef CB_FP16
-        const unsigned short one_bits = 0x3C00;   // fp16 1.0
+          const unsigned short one_bits = 0x3C00;   // fp16 1.0
 #else
-        const unsigned short one_bits = 0x3F80;   // bf16 1.0
+          const unsigned short one_bits = 0x3F80;   // bf16 1.0
 #endif
-        for (int r = lane; r < ATT_BN; r += 32) {
-          const uint32_t addr = tile + uint32_t(r) * 128u + (((uint32_t(cw) >> 3) ^ (uint32_t(r) & 7u)) << 4) + uint32_t(cw & 7) * 2u;
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(one_bits) : "memory");
+          for (int r = lane; r < ATT_BN; r += 32) {
+            const uint32_t addr = tile + uint32_t(r) * 128u + (((uint32_t(cw) >> 3) ^ (uint32_t(r) & 7u)) << 4) + uint32_t(cw & 7) * 2u;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(one_bits) : "memory");
+          }
+          fence_proxy_async_smem();
         }
-        fence_proxy_async_smem();
+        mbar_arrive(v_ready(st));
       }
-      mbar_arrive(v_ready(st));
     }
   } else {
     // ===================== softmax warpgroups =====================
     const int w = (warp - 2) >> 2;
-    if (w < nact) {
-      const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
-      const int r = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
-      const uint32_t lane_off = uint32_t(quarter * 32) << 16;
-      const uint32_t tSw = tS(w) + lane_off, tOw = tO(w) + lane_off, tPw = tP(w) + lane_off;
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+    const int r = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
+    const uint32_t lane_off = uint32_t(quarter * 32) << 16;
+    const uint32_t tSw = tS(w) + lane_off, tOw = tO(w) + lane_off, tPw = tP(w) + lane_off;
+    int cw = 0;                                        // blocks this tile has been active for (barrier phases)
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      if (w >= item_nact(item)) continue;
+      const int bh = item_bh(item), q_first = item_q_first(item);
       float m_used = -INFINITY, l_run = 0.f;
 
       for (int j = 0; j < nblk; ++j) {
-        mbar_wait(s_full(w), uint32_t(j & 1));
+        const int c = cw + j;
+        mbar_wait(s_full(w), uint32_t(c & 1));
         tc_fence_after();
         uint32_t s[128];
         tmem_ld32(tSw + 0u, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
@@ -231,7 +272,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         tmem_ld32(tSw + 96u, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(s_free(w));      // the scores are in registers: Q*K^T of block j+1 may overwrite S
+        mbar_arrive(s_free(w));      // the scores are in registers: Q*K^T of the next block may overwrite S
         const int nvalid = p.nk - j * ATT_BN;
         if (nvalid < ATT_BN) {   // ragged last block: K rows beyond nk were zero filled -> mask
 #pragma unroll
@@ -252,46 +293,47 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         } else {
           const bool need = (m_blk - m_used) > RESCALE_TAU;
           if (__any_sync(0xffffffffu, need)) {
-            mbar_wait(pv_done(w), uint32_t((j - 1) & 1));   // O holds every P*V up to block j-1
+            mbar_wait(pv_done(w), uint32_t((c - 1) & 1));   // O holds every P*V up to block j-1
             tc_fence_after();
             const float alpha = need ? exp2f(m_used - m_blk) : 1.f;
             if (need) m_used = m_blk;
             if (!USE_ONES) l_run *= alpha;
 #pragma unroll 1
-            for (int c = 0; c < p.dpad; c += 32) {
+            for (int cc = 0; cc < p.dpad; cc += 32) {
               uint32_t o[32];
-              tmem_ld32(tOw + uint32_t(c), o);
+              tmem_ld32(tOw + uint32_t(cc), o);
               tmem_ld_wait();
 #pragma unroll
               for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              tmem_st32(tOw + uint32_t(c), o);
+              tmem_st32(tOw + uint32_t(cc), o);
             }
             tmem_st_wait();
           }
         }
         float rs = 0.f;
 #pragma unroll
-        for (int c = 0; c < ATT_BN; c += 64) {
+        for (int cc = 0; cc < ATT_BN; cc += 64) {
           uint32_t pk[32];
 #pragma unroll
           for (int e = 0; e < 64; e += 2) {
-            pk[e >> 1] = exp2_pack(__uint_as_float(s[c + e]), __uint_as_float(s[c + e + 1]), p.scale_log2, m_used);
+            pk[e >> 1] = exp2_pack(__uint_as_float(s[cc + e]), __uint_as_float(s[cc + e + 1]), p.scale_log2, m_used);
             if (!USE_ONES) {
               const float2 b = unpack_act2(pk[e >> 1]);
               rs += b.x + b.y;
             }
           }
-          if (c == 0 && j > 0) mbar_wait(pv_done(w), uint32_t((j - 1) & 1));   // P*V of block j-1 has finished reading P
-          tmem_st32(tPw + uint32_t(c >> 1), pk);
+          if (cc == 0 && c > 0) mbar_wait(pv_done(w), uint32_t((c - 1) & 1));   // the previous P*V has finished reading P
+          tmem_st32(tPw + uint32_t(cc >> 1), pk);
         }
         tmem_st_wait();
         if (!USE_ONES) l_run += rs;
         tc_fence_before();
         mbar_arrive(p_full(w));
       }
+      cw += nblk;
 
       // ---- epilogue: O / l -> out[b][q][head*d + :]
-      mbar_wait(pv_done(w), uint32_t((nblk - 1) & 1));
+      mbar_wait(pv_done(w), uint32_t((cw - 1) & 1));
       tc_fence_after();
       const int q = q_first + w * ATT_BM + r;
       const int b = bh / p.heads, head = bh - b * p.heads;
@@ -311,19 +353,23 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       act_t* orow = p.out + (static_cast<long long>(b) * p.nq + q) * (static_cast<long long>(p.heads) * p.d) +
                     static_cast<long long>(head) * p.d;
 #pragma unroll 1
-      for (int c = 0; c < p.d; c += 32) {
+      for (int cc = 0; cc < p.d; cc += 32) {
         uint32_t o[32];
-        tmem_ld32(tOw + uint32_t(c), o);
+        tmem_ld32(tOw + uint32_t(cc), o);
         tmem_ld_wait();
+        if (cc + 32 >= p.d) {        // last TMEM read of this item's O: the next item's first P*V may overwrite it
+          tc_fence_before();
+          mbar_arrive(o_free(w));
+        }
         if (q < p.nq) {
 #pragma unroll
-          for (int g = 0; g < 32; g += 8) {
-            if (c + g < p.d) {
+          for (int gq = 0; gq < 32; gq += 8) {
+            if (cc + gq < p.d) {
               float f[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g + e]) * inv_l;
-              *reinterpret_cast<uint4*>(orow + c + g) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
-                                                                   pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[gq + e]) * inv_l;
+              *reinterpret_cast<uint4*>(orow + cc + gq) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
+                                                                     pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
             }
           }
         }
@@ -352,7 +398,7 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
              "cb_attention: row strides must be >= heads * d and multiples of 8 elements");
   const int dpad = (d + 63) / 64 * 64;
   const int64_t bh = batch * heads;
-  CB_REQUIRE(bh <= 65535, "cb_attention: batch*heads = %lld exceeds the grid limit", (long long)bh);
+  CB_REQUIRE(bh * ((nq + 127) / 128) < (1LL << 30), "cb_attention: problem too large");
   CUtensorMap mq, mk, mv;
   uint32_t box[4] = {64, 128, 1, 1};
   {
@@ -372,7 +418,7 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
     if (rc) return rc;
   }
   AttnParams p{};
-  p.nq = (int)nq; p.nk = (int)nk; p.d = d; p.dpad = dpad; p.np = dpad / 64; p.heads = (int)heads;
+  p.nq = (int)nq; p.nk = (int)nk; p.d = d; p.dpad = dpad; p.np = dpad / 64; p.heads = (int)heads; p.bh = (int)bh;
   p.nwg = dpad <= 128 ? 2 : 1;           // TMEM: nwg * (128 + dpad) columns <= 512
   p.stages = dpad <= 64 ? 4 : (dpad <= 128 ? 2 : 1);   // smem: (nwg + 2*stages) * np panels of 16 KB
   p.p_alias = (p.nwg * (128 + dpad + 64) > 512) ? 1 : 0;   // no room for a separate P region: P overwrites S
@@ -382,7 +428,7 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   p.idesc_pv = make_idesc_f16(128, dpad, 0, 1);   // B = V is MN-major
   p.tmem_cols = 512u;
   p.out = (act_t*)out;
-  const size_t smem = (size_t)(p.nwg + 2 * p.stages) * p.np * PANEL_BYTES + 256;
+  const size_t smem = (size_t)(p.nwg + 2 * p.stages) * p.np * PANEL_BYTES + 384;
   CB_REQUIRE(smem <= 227 * 1024, "cb_attention: needs %zu bytes of shared memory", smem);
   static thread_local bool configured = false;
   if (!configured) {
@@ -390,8 +436,16 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
     CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const int rows_per_cta = p.nwg * ATT_BM;
-  dim3 grid((unsigned)((nq + rows_per_cta - 1) / rows_per_cta), (unsigned)bh);
+  const int rows_per_item = p.nwg * ATT_BM;
+  const long long items = ((nq + rows_per_item - 1) / rows_per_item) * bh;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0, sms = 0;
+    CB_CHECK_CUDA(cudaGetDevice(&dev));
+    CB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    num_sms = sms > 0 ? sms : 148;
+  }
+  dim3 grid((unsigned)(items < num_sms ? items : num_sms));   // persistent: one CTA per SM walks the work items
   if (p.use_ones) attention_kernel<true><<<grid, ATT_THREADS, smem, stream>>>(mq, mk, mv, p);
   else attention_kernel<false><<<grid, ATT_THREADS, smem, stream>>>(mq, mk, mv, p);
   CB_CHECK_CUDA(cudaGetLastError());
