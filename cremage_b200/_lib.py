@@ -41,6 +41,7 @@ class IGemmDesc(C.Structure):
         ("heads_d", C.c_int), ("heads_dpad", C.c_int), ("heads_h", C.c_int), ("heads_tokens", C.c_int),
         ("heads_which_stride", C.c_int64),
         ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int), ("cta_pair", C.c_int), ("nsub", C.c_int), ("ksplit", C.c_int),
+        ("gn_partials", C.c_void_p),
     ]
 
 
@@ -58,6 +59,8 @@ SIGNATURES = {
     "cb_pointwise_nchw_to_nhwc": [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _vp, _vp],
     "cb_groupnorm_workspace_bytes": [_i64, _i64, _i64, _int],
     "cb_groupnorm_nhwc": [_vp, _i64, _vp, _i64, _i64, _i64, _int, _f32, _vp, _vp, _int, _vp, _vp, _vp],
+    "cb_gn_partial_blocks": [_i64, _i64, _int, _int],
+    "cb_groupnorm_from_partials": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _int, _f32, _vp, _vp, _int, _vp, _vp, _vp],
     "cb_layernorm": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp],
     "cb_nchw_to_nhwc": [_vp, _int, _i64, _i64, _i64, _i64, _f32, _vp, _vp],
     "cb_nhwc_to_nchw_f32": [_vp, _int, _i64, _i64, _i64, _i64, _vp, _vp],
@@ -77,7 +80,8 @@ SIGNATURES = {
     "cb_bilinear_upsample_f32": [_vp, _i64, _i64, _i64, _int, _vp, _vp],
     "cb_image_to_u8": [_vp, _i64, _i64, _i64, _vp, _vp],
 }
-_RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64, "cb_groupnorm_workspace_bytes": C.c_int64}
+_RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64, "cb_groupnorm_workspace_bytes": C.c_int64,
+             "cb_gn_partial_blocks": C.c_int64}
 
 
 def lib_path() -> Path:

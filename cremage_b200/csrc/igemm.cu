@@ -72,7 +72,64 @@ struct IGemmKParams {
   long long hwhich_stride;
   // staged epilogue: panels per epilogue warp, and the pixel box {pbw, pbh, 32 / (pbw * pbh)} of a warp's 32 rows
   int npan, pbw, pbh;
+  // fused GroupNorm statistics of the OUTPUT (16-bit rounded values): per (image, M tile) and channel pair, the sum
+  // and the sum of squares -> gn_part[n][gn_bpi][2][cout/2], gn_bpi = tiles_w * tiles_h (M tiles per image)
+  float* gn_part;
+  int gn_bpi;
 };
+
+// ---- fused GroupNorm statistics -----------------------------------------------------------------------------------
+// V[0..15] = this row's sums of 16 channel pairs, V[16..31] = their sums of squares.  Transposed butterfly: after the
+// five exchange steps lane L holds the total over the warp's 32 rows of entry L (fixed order -> deterministic).
+template <int M>
+CB_DEVINL void gn_xchg_step(float (&V)[32], int lane) {
+  constexpr int O = M / 2;
+  const bool up = (lane & O) != 0;
+#pragma unroll
+  for (int i = 0; i < O; ++i) {
+    const float send = up ? V[i] : V[i + O];
+    const float keep = up ? V[i + O] : V[i];
+    V[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+  }
+}
+// the warp's 32-row totals of one 32-column chunk go to its slot of the tile's shared-memory table [chunk][quarter][32]
+CB_DEVINL void gn_store_chunk(float (&V)[32], int lane, float* __restrict__ slot) {
+  gn_xchg_step<32>(V, lane);
+  gn_xchg_step<16>(V, lane);
+  gn_xchg_step<8>(V, lane);
+  gn_xchg_step<4>(V, lane);
+  gn_xchg_step<2>(V, lane);
+  slot[lane] = V[0];
+}
+// One tile later (after the epilogue warps' named barrier): fold the four lane quarters of every chunk per image, in
+// quarter order, and write the tile's row of the partial table.  tab: [8 chunks][4 quarters][32]; ew = 0..7.
+CB_DEVINL void gn_flush_tile(const IGemmKParams& p, const float* __restrict__ tab, int ew, int lane, int tile_row, int img0, int nt) {
+  const int qpi = 4 / p.TN;   // lane quarters per image (tw * th % 32 == 0: TN is 1, 2 or 4)
+  for (int ci = ew; ci * 32 < p.bn; ci += EPI_WARPS) {
+    const int col0 = nt * p.bn + ci * 32;
+    if (col0 >= p.cout) break;
+    const int pair = (col0 >> 1) + (lane & 15);
+    if (2 * pair >= p.cout) continue;
+    const float* s = tab + ci * 128 + lane;
+    for (int im = 0; im < p.TN; ++im) {
+      const int img = img0 + im;
+      if (img >= p.n_img) break;
+      float t = s[(im * qpi) * 32];
+      for (int q = 1; q < qpi; ++q) t += s[(im * qpi + q) * 32];
+      p.gn_part[((static_cast<long long>(img) * p.gn_bpi + tile_row) * 2 + (lane >> 4)) * (p.cout >> 1) + pair] = t;
+    }
+  }
+}
+// accumulate the 8 final values of columns [jb, jb+8) of a chunk as they will be read back (16-bit rounded)
+CB_DEVINL void gn_accum8(float (&V)[32], int jb, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+  const uint32_t wv[4] = {w0, w1, w2, w3};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = unpack_act2(wv[e]);
+    V[(jb >> 1) + e] = t.x + t.y;
+    V[16 + (jb >> 1) + e] = fmaf(t.x, t.x, t.y * t.y);
+  }
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act == CB_ACT_SILU ? silu_f(v) : v; }
 
@@ -123,9 +180,9 @@ enum : int {
 };
 
 // 32 accumulator columns [c, c+32) of one row -> global
-template <int EPI>
+template <int EPI, bool STATS>
 __device__ __forceinline__ void epilogue_chunk(const IGemmKParams& p, const uint32_t (&v)[32], const float* __restrict__ sbias,
-                                               int nt, int c, int n, long long row) {
+                                               int nt, int c, int n, long long row, float (&V)[32]) {
   const int col0 = nt * p.bn + c;
   if (col0 >= p.cout) return;
 #pragma unroll
@@ -191,8 +248,9 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmKParams& p, const uint
         *reinterpret_cast<float4*>(optr + 4) = make_float4(f[4], f[5], f[6], f[7]);
       } else {
         act_t* optr = reinterpret_cast<act_t*>(p.out) + row * p.out_ld + col;
-        *reinterpret_cast<uint4*>(optr) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
-                                                     pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+        const uint4 o = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(optr) = o;
+        if (STATS) gn_accum8(V, j, o.x, o.y, o.z, o.w);
       }
     } else {
       // EPI_GENERIC ragged tail (cout not a multiple of 8, e.g. the 4- and 3-channel output convs): scalar path
@@ -211,15 +269,22 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmKParams& p, const uint
 }
 
 // DIRECT epilogue of this warp's share of one 128 x bn accumulator tile (thread = one row): chunks hh, hh+2, ...
-template <int EPI>
+template <int EPI, bool STATS>
 __device__ __forceinline__ void epilogue_tile_direct(const IGemmKParams& p, uint32_t trow, const float* __restrict__ sbias,
-                                                     int nt, int n, bool row_ok, long long row, int hh) {
+                                                     int nt, int n, bool row_ok, long long row, int hh, int lane,
+                                                     float* __restrict__ gtab) {
   for (int c = hh * 32; c < p.bn; c += 64) {
     if (nt * p.bn + c >= p.cout) break;
     uint32_t v[32];
     tmem_ld32(trow + uint32_t(c), v);
     tmem_ld_wait();
-    if (row_ok) epilogue_chunk<EPI>(p, v, sbias, nt, c, n, row);
+    float V[32];
+    if (STATS) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) V[i] = 0.f;
+    }
+    if (row_ok) epilogue_chunk<EPI, STATS>(p, v, sbias, nt, c, n, row, V);
+    if (STATS) gn_store_chunk(V, lane, gtab + (c >> 5) * 128);
   }
 }
 
@@ -234,10 +299,11 @@ CB_DEVINL uint4 ld_shared_v4(uint32_t addr) {
 
 // STAGED epilogue of one 32-column chunk: registers (+bias, +per-image bias, +residual read from the panel) -> the
 // 64B-swizzled panel (row = lane, 16-byte piece j at  j ^ ((lane >> 1) & 3)), ready for the TMA store.
-template <int EPI>
+template <int EPI, bool STATS>
 __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32_t (&v)[32], const uint32_t (&g)[32],
                                              const float* __restrict__ sbx, const float* __restrict__ sbg,
-                                             const float* __restrict__ rowb, bool rowb_ok, int col0, uint32_t panel, int lane) {
+                                             const float* __restrict__ rowb, bool rowb_ok, int col0, uint32_t panel, int lane,
+                                             bool row_ok, float (&V)[32]) {
   const uint32_t rowaddr = panel + uint32_t(lane) * 64u;
   const uint32_t sw = uint32_t(lane >> 1) & 3u;
 #pragma unroll
@@ -281,7 +347,12 @@ __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32
         f[2 * e + 1] += t.y;
       }
     }
-    st_shared_v4(addr, pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
+    const uint32_t o0 = pack_act2(f[0], f[1]), o1 = pack_act2(f[2], f[3]), o2 = pack_act2(f[4], f[5]), o3 = pack_act2(f[6], f[7]);
+    st_shared_v4(addr, o0, o1, o2, o3);
+    if (STATS) {
+      if (row_ok && col0 + 8 * j < p.cout) gn_accum8(V, 8 * j, o0, o1, o2, o3);
+      else gn_accum8(V, 8 * j, 0u, 0u, 0u, 0u);
+    }
   }
 }
 
@@ -314,6 +385,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const uint32_t tmem_slot = misc + 56u;
   auto resid_bar = [&](int ew) { return misc + 64u + 8u * uint32_t(ew); };
   const uint32_t bias_smem = (misc + 64u + 8u * EPI_WARPS + 15u) & ~15u;  // float[3][256]: a sub-tile's bias slice per accumulator slot
+  const uint32_t gn_smem = bias_smem + 3u * 256u * 4u;   // float[2 tiles][8 chunks][4 quarters][32] (only when gn_part)
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -469,6 +541,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     uint32_t rphase = 0;
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
     constexpr bool GEGLU = (EPI == EPI_GEGLU);
+    constexpr bool STATS_OK = (EPI == EPI_PLAIN || EPI == EPI_RES || EPI == EPI_ROWBIAS);
+    const bool do_gn = STATS_OK && p.gn_part != nullptr;
+    float* gn_tab = reinterpret_cast<float*>(smem_raw + (gn_smem - smem_u32(smem_raw)));
+    int g_prev_row = -1, g_prev_img0 = 0, g_prev_nt = 0;
     const int ocols = GEGLU ? (p.bn >> 1) : p.bn;   // output columns per tile
     int mt, ng;
     int acc_cnt = 0;
@@ -509,6 +585,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         sb[c] = (p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+      // fused GroupNorm statistics: every warp has stored the previous tile's chunk totals -> write that tile's row
+      float* gtab = gn_tab + (acc_cnt & 1) * 1024 + q * 32;
+      if (STATS_OK && do_gn) {
+        if (g_prev_row >= 0) gn_flush_tile(p, gn_tab + ((acc_cnt - 1) & 1) * 1024, ew, lane, g_prev_row, g_prev_img0, g_prev_nt);
+        g_prev_row = th * p.tiles_w + tw; g_prev_img0 = tn * p.TN; g_prev_nt = nt;
+      }
 
       mbar_wait(acc_full(buf), use & 1u);
       tc_fence_after();
@@ -526,7 +608,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           if (GEGLU) tmem_ld32(trow + uint32_t(ocols + c), g);
           tmem_ld_wait();
           const uint32_t panel = my_stg + uint32_t(k) * PANEL_BYTES;
-          staged_chunk<EPI>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane);
+          float V[32];
+          if (STATS_OK && do_gn) {
+            staged_chunk<EPI, STATS_OK>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane, row_ok, V);
+            gn_store_chunk(V, lane, gtab + (c >> 5) * 128);
+          } else {
+            staged_chunk<EPI, false>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane, row_ok, V);
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -536,13 +624,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         }
       } else {
         // split-K: this work item's fp32 partial goes to its own slab of the workspace
-        epilogue_tile_direct<EPI>(p, trow, sb, nt, n, row_ok, row + (long long)ksi * (p.split_stride / p.out_ld), hh);
+        const long long orow = row + (long long)ksi * (p.split_stride / p.out_ld);
+        if (STATS_OK && do_gn) epilogue_tile_direct<EPI, STATS_OK>(p, trow, sb, nt, n, row_ok, orow, hh, lane, gtab);
+        else epilogue_tile_direct<EPI, false>(p, trow, sb, nt, n, row_ok, orow, hh, lane, gtab);
       }
       tc_fence_before();
       __syncwarp();                  // every lane of this warp has drained its TMEM lanes
       if (lane == 0) {
         if (TWO) mbar_arrive_leader(acc_empty(buf)); else mbar_arrive(acc_empty(buf));
       }
+    }
+    if (STATS_OK && do_gn && g_prev_row >= 0) {   // the last tile's row
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      gn_flush_tile(p, gn_tab + ((acc_cnt - 1) & 1) * 1024, ew, lane, g_prev_row, g_prev_img0, g_prev_nt);
     }
     if (STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -678,6 +772,13 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     else if (d->rowbias && !d->residual) epi = EPI_ROWBIAS;
   }
   CB_REQUIRE(d->mode != CB_EPI_HEADS || epi == EPI_HEADS, "cb_igemm: the heads epilogue takes bias only (no activation / residual / row bias / scale)");
+  if (d->gn_partials) {
+    CB_REQUIRE(epi == EPI_PLAIN || epi == EPI_RES || epi == EPI_ROWBIAS, "cb_igemm: GroupNorm partials need a plain 16-bit epilogue (bias / row bias / residual)");
+    CB_REQUIRE(ksplit == 1, "cb_igemm: GroupNorm partials are not produced by split-K launches");
+    CB_REQUIRE((d->tw * d->th) % 32 == 0, "cb_igemm: GroupNorm partials need tw * th %% 32 == 0 (a warp's 32 rows inside one image)");
+    p.gn_part = d->gn_partials;
+    p.gn_bpi = p.tiles_w * p.tiles_h;
+  }
 
   // staged (TMA in / TMA out) epilogue: the small-K launches whose run time IS the epilogue; large-K convs keep the
   // direct form (their epilogue hides under the next tile's MMAs and the ring keeps its depth)
@@ -712,7 +813,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
 
   // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
   //      that N tile gets several M tiles; otherwise stream A and B through the ring
-  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 768 + 64;
+  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 768 + 64 + (d->gn_partials ? sizeof(float) * 2048 : 0);
   const size_t b_chunk = (size_t)(two ? d->bn / 2 : d->bn) * 128;
   const size_t res_bytes = (size_t)num_k * b_chunk;
   int resident = 0;

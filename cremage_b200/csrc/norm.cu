@@ -13,6 +13,19 @@ CB_DEVINL Vec8 ld_vec8(const act_t* p) {
   v.u[0] = t.x; v.u[1] = t.y; v.u[2] = t.z; v.u[3] = t.w;
   return v;
 }
+// streaming 16-byte load issued where it is written (volatile asm: ptxas keeps all U loads of a chunk in flight
+// instead of re-serialising them to save registers)
+CB_DEVINL Vec8 ld_vec8_stream(const act_t* p) {
+  Vec8 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.u[0]), "=r"(v.u[1]), "=r"(v.u[2]), "=r"(v.u[3]) : "l"(p));
+  return v;
+}
+CB_DEVINL uint4 ld_shared_v4_u(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
 CB_DEVINL void st_vec8(act_t* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) =
       make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
@@ -23,6 +36,48 @@ CB_DEVINL void unpack8(const Vec8& v, float (&f)[8]) {
     float2 t = unpack_act2(v.u[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
+  }
+}
+
+// 2^t on the FMA / ALU pipes (no MUFU): Cody-Waite split t = n + f, |f| <= 0.5, degree-5 polynomial for 2^f
+// (relative error 2.4e-6, two orders below the 16-bit output rounding), exponent added with integer arithmetic.
+CB_DEVINL float ex2_fma(float t) {
+  t = fmaxf(t, -125.f);
+  const float fl = t + 12582912.f;           // 1.5 * 2^23: n = round(t) lands in the low mantissa bits
+  const float f = t - (fl - 12582912.f);
+  float p = fmaf(1.33335581e-3f, f, 9.61812911e-3f);
+  p = fmaf(p, f, 5.55041087e-2f);
+  p = fmaf(p, f, 2.40226507e-1f);
+  p = fmaf(p, f, 6.93147182e-1f);
+  p = fmaf(p, f, 1.f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(fl) << 23));
+}
+
+// y[i] <- y[i] * sigmoid(y[i]) for 8 values.  The streaming GroupNorm+SiLU pass is co-limited by the XU pipe (16
+// MUFU/clk/SM; exp + reciprocal per element = 75 % busy at 4.7 TB/s, profiles/r1_groupnorm_fused_stats.md), so: half of
+// the exponentials run as polynomials on the FMA pipe, and one reciprocal serves four denominators
+// (1/a0 = a1 * (a2*a3) / (a0*a1*a2*a3) ...): 4 MUFU.EX2 + 2 MUFU.RCP per 8 elements instead of 16 MUFU.  The exponent is
+// clamped at 2^30 so the 4-way product stays finite; silu(x) for x < -20.8 is below the smallest 16-bit subnormal.
+CB_DEVINL void silu8(float (&y)[8]) {
+#pragma unroll
+  for (int h = 0; h < 8; h += 4) {
+    float a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float t = fminf(-1.4426950408889634f * y[h + i], 30.f);
+      float e;
+      if (i & 1) e = ex2_fma(t);
+      else asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+      a[i] = 1.f + e;
+    }
+    const float p01 = a[0] * a[1], p23 = a[2] * a[3];
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+    const float r01 = r * p23, r23 = r * p01;
+    y[h + 0] *= r01 * a[1];
+    y[h + 1] *= r01 * a[0];
+    y[h + 2] *= r23 * a[3];
+    y[h + 3] *= r23 * a[2];
   }
 }
 
@@ -128,67 +183,261 @@ __global__ void gn_stats_kernel(const act_t* __restrict__ x0, int c0, const act_
   if (threadIdx.x == 0) counters[n] = 0u;  // self-reset for the next call
 }
 
-// GroupNorm pass 2: y = silu?((x - mean) * rstd * gamma + beta) -> bf16 [n][hw][C]
+// GroupNorm pass 2 (streaming): y = silu?((x - mean) * rstd * gamma + beta) -> 16-bit [n][hw][C]; one read + one
+// write per element.  The per-(image, group) statistics come either as folded sums stats[n][groups][2] (stand-alone
+// pass 1) or as S-row partial tables part_s[n][S_s][2][c_s/2] (sum | sum of squares per channel pair, written by the
+// producing cb_igemm launches, reduced to <= GN_PART_ROWS rows by gn_fold1_kernel): the CTA folds them in a fixed
+// order in fp64 in its prologue.
+constexpr int GN_PART_ROWS = 32;
+constexpr int GN_APPLY_UNROLL = 4;   // 16-byte loads in flight per thread of the apply pass
+constexpr int GN_PART_MAXC = 2560;   // widest (concatenated) input of the from-partials path
+
+// per-thread affine coefficients of channels [c, c+8) of image n: y = a * x + b
+template <bool PARTS>
+CB_DEVINL void gn_coefficients(int c0, int c1, long long hw, int groups, float eps, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ stats,
+                               const float* __restrict__ part0, int S0, const float* __restrict__ part1, int S1, int n,
+                               int c, bool active, float (&a)[8], float (&b)[8]) {
+  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float s_col[PARTS ? 2 * GN_PART_MAXC / 2 : 1];   // [plane][pair of the concat]: column totals of the tables
+  __shared__ double s_gs[PARTS ? 128 : 1];                    // [plane][group]
+  const int C = c0 + c1;
+  const int gs = C / groups;
+  const float inv_cnt = 1.f / (float(gs) * float(hw));
+  if (PARTS) {
+    // 1. every thread totals whole columns of the S-row tables: independent, coalesced loads (8 in flight)
+    const int hc = C >> 1, h0 = c0 >> 1;
+    for (int idx = threadIdx.x; idx < C; idx += blockDim.x) {
+      const int plane = idx >= hc, pc = idx - plane * hc;
+      const float* q;
+      int S, W;
+      if (pc < h0) { S = S0; W = c0; q = part0 + (long long)n * S0 * c0 + plane * h0 + pc; }
+      else         { S = S1; W = c1; q = part1 + (long long)n * S1 * c1 + plane * (c1 >> 1) + (pc - h0); }
+      double acc = 0.0;
+      int r = 0;
+      for (; r + 8 <= S; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(q + (long long)(r + u) * W);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += (double)v[u];
+      }
+      for (; r < S; ++r) acc += (double)__ldg(q + (long long)r * W);
+      s_col[idx] = (float)acc;
+    }
+    __syncthreads();
+    // 2. per (plane, group): the group's pairs in channel order
+    if ((int)threadIdx.x < 2 * groups) {
+      const int plane = threadIdx.x / groups, g = threadIdx.x - plane * groups;
+      const float* q = s_col + plane * hc + ((g * gs) >> 1);
+      double acc = 0.0;
+      for (int i = 0; i < (gs >> 1); ++i) acc += (double)q[i];
+      s_gs[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < groups) {
+      const double mean = s_gs[threadIdx.x] * (double)inv_cnt;
+      double var = s_gs[groups + threadIdx.x] * (double)inv_cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[threadIdx.x] = (float)mean;
+      s_rstd[threadIdx.x] = rsqrtf((float)var + eps);
+    }
+    __syncthreads();
+  }
+  if (!active) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int g = (c + i) / gs;
+    float mean, rstd;
+    if (PARTS) {
+      mean = s_mean[g];
+      rstd = s_rstd[g];
+    } else {
+      const float sum = stats[((long long)n * groups + g) * 2 + 0];
+      const float sq = stats[((long long)n * groups + g) * 2 + 1];
+      mean = sum * inv_cnt;
+      rstd = rsqrtf(fmaxf(sq * inv_cnt - mean * mean, 0.f) + eps);
+    }
+    a[i] = rstd * gamma[c + i];
+    b[i] = beta[c + i] - mean * a[i];
+  }
+}
+
+template <bool SILU>
+CB_DEVINL void gn_affine_store(const Vec8& v, const float (&a)[8], const float (&b)[8], act_t* dst) {
+  float f[8];
+  unpack8(v, f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], a[k], b[k]);
+  if (SILU) silu8(f);
+  st_vec8(dst, f);
+}
+
+// register-path apply (tensors of a few chunks per CTA: launch-latency bound anyway)
+template <bool SILU, bool PARTS>
 __global__ void gn_apply_kernel(const act_t* __restrict__ x0, int c0, const act_t* __restrict__ x1,
-                                int c1, long long hw, int groups, int P, long long pix_per_cta, float eps,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                                const float* __restrict__ stats, act_t* __restrict__ out) {
+                                int c1, long long hw, int groups, int P, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ stats, const float* __restrict__ part0, int S0,
+                                const float* __restrict__ part1, int S1, act_t* __restrict__ out) {
   const int C = c0 + c1;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
   const int lp = threadIdx.x / CV;
   const int n = blockIdx.y;
-  if (lp >= P) return;  // padding threads of the warp-rounded block
   const int c = cv << 3;
-  const int gs = C / groups;
-  const float inv_cnt = 1.f / (float(gs) * float(hw));
   float a[8], b[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int g = (c + i) / gs;
-    const float sum = stats[((long long)n * groups + g) * 2 + 0];
-    const float sq = stats[((long long)n * groups + g) * 2 + 1];
-    const float mean = sum * inv_cnt;
-    const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    a[i] = rstd * gamma[c + i];
-    b[i] = beta[c + i] - mean * a[i];
-  }
+  gn_coefficients<PARTS>(c0, c1, hw, groups, eps, gamma, beta, stats, part0, S0, part1, S1, n, c, lp < P, a, b);
+  if (lp >= P) return;  // padding threads of the warp-rounded block
   const act_t* src;
   long long ld;
   if (c < c0) { src = x0 + (long long)n * hw * c0 + c; ld = c0; }
   else        { src = x1 + (long long)n * hw * c1 + (c - c0); ld = c1; }
   act_t* dst = out + (long long)n * hw * C + c;
-
-  const long long p_begin = (long long)blockIdx.x * pix_per_cta;
-  long long p_end = p_begin + pix_per_cta;
-  if (p_end > hw) p_end = hw;
-  long long p = p_begin + lp;
-  for (; p + 3LL * P < p_end; p += 4LL * P) {
-    Vec8 v[4];
+  // chunks of U*P consecutive pixels, interleaved over the CTAs of the image: at any moment the resident CTAs stream one
+  // narrow window of the tensor, not gridDim.x far-apart ranges
+  constexpr int U = GN_APPLY_UNROLL;
+  const long long chunk = (long long)U * P;
+  for (long long base = (long long)blockIdx.x * chunk; base < hw; base += (long long)gridDim.x * chunk) {
+    const long long p = base + lp;
+    if (base + chunk <= hw) {
+      Vec8 v[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld_vec8(src + (p + (long long)u * P) * ld);
+      for (int u = 0; u < U; ++u) v[u] = ld_vec8(src + (p + (long long)u * P) * ld);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float f[8];
-      unpack8(v[u], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float y = fmaf(f[i], a[i], b[i]);
-        f[i] = silu ? silu_f(y) : y;
-      }
-      st_vec8(dst + (p + (long long)u * P) * C, f);
+      for (int u = 0; u < U; ++u) gn_affine_store<SILU>(v[u], a, b, dst + (p + (long long)u * P) * C);
+    } else {
+      for (long long pp = p; pp < hw; pp += P) gn_affine_store<SILU>(ld_vec8(src + pp * ld), a, b, dst + pp * C);
     }
   }
-  for (; p < p_end; p += P) {
-    float f[8];
-    unpack8(ld_vec8(src + p * ld), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float y = fmaf(f[i], a[i], b[i]);
-      f[i] = silu ? silu_f(y) : y;
+}
+
+// Streaming apply for tensors far larger than the L2 (the VAE decoder): the input moves HBM -> shared memory with 1-D
+// bulk copies (cp.async.bulk + mbarrier complete_tx) through a GN_TMA_STAGES-deep ring per CTA, so the bytes in flight
+// per SM are set by shared memory (3 CTAs x 3 stages x 16 KiB), not by the registers of the loading threads; the
+// threads read their 16-byte vectors from the ring, normalise and store straight to global.  A chunk of U*P pixels is
+// one contiguous block per source.
+constexpr int GN_TMA_STAGES = 3;
+constexpr int GN_TMA_THREADS = 256;
+
+CB_DEVINL void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool SILU, bool PARTS>
+__global__ void __launch_bounds__(GN_TMA_THREADS, 3)
+gn_apply_tma_kernel(const act_t* __restrict__ x0, int c0, const act_t* __restrict__ x1, int c1, long long hw, int groups,
+                    int P, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const float* __restrict__ stats, const float* __restrict__ part0, int S0,
+                    const float* __restrict__ part1, int S1, act_t* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t gn_ring[];   // [stages][chunk of source 0 | chunk of source 1]
+  __shared__ __align__(8) uint64_t s_full[GN_TMA_STAGES];
+  constexpr int U = GN_APPLY_UNROLL;
+  const int C = c0 + c1;
+  const int CV = C >> 3;
+  const int cv = threadIdx.x % CV;
+  const int lp = threadIdx.x / CV;
+  const int n = blockIdx.y;
+  const int c = cv << 3;
+  const long long chunk = (long long)U * P;                  // pixels per chunk
+  const long long nfull = hw / chunk;
+  const uint32_t bytes0 = (uint32_t)(chunk * c0 * 2), bytes1 = (uint32_t)(chunk * c1 * 2);
+  const uint32_t stage_bytes = bytes0 + bytes1;
+  const uint32_t ring = smem_u32(gn_ring);
+  const act_t* g0 = x0 + (long long)n * hw * c0;
+  const act_t* g1 = c1 ? x1 + (long long)n * hw * c1 : nullptr;
+  auto issue = [&](long long i, int s) {                      // one thread: chunk i -> stage s
+    const uint32_t bar = smem_u32(&s_full[s]);
+    mbar_expect_tx(bar, stage_bytes);
+    bulk_load_1d(ring + (uint32_t)s * stage_bytes, g0 + i * chunk * c0, bytes0, bar);
+    if (bytes1) bulk_load_1d(ring + (uint32_t)s * stage_bytes + bytes0, g1 + i * chunk * c1, bytes1, bar);
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GN_TMA_STAGES; ++s) mbar_init(smem_u32(&s_full[s]), 1);
+    fence_mbar_init();
+    for (int s = 0; s < GN_TMA_STAGES; ++s) {
+      const long long i = blockIdx.x + (long long)s * gridDim.x;
+      if (i < nfull) issue(i, s);                             // the ring fills while the prologue folds the statistics
     }
-    st_vec8(dst + p * C, f);
+  }
+  float a[8], b[8];
+  gn_coefficients<PARTS>(c0, c1, hw, groups, eps, gamma, beta, stats, part0, S0, part1, S1, n, c, lp < P, a, b);
+  __syncthreads();   // barriers initialised (PARTS = false has no barrier inside gn_coefficients)
+  const bool active = lp < P;
+  // this thread's vector inside a stage: pixel u*P + lp of the chunk, channels [c, c+8) of its source
+  const uint32_t voff = c < c0 ? (uint32_t)(lp * c0 + c) * 2u : bytes0 + (uint32_t)(lp * c1 + (c - c0)) * 2u;
+  const uint32_t vstep = (uint32_t)P * (uint32_t)(c < c0 ? c0 : c1) * 2u;
+  act_t* dst = out + (long long)n * hw * C + c;
+  int s = 0;
+  uint32_t parity = 0;
+  for (long long i = blockIdx.x; i < nfull; i += gridDim.x) {
+    mbar_wait(smem_u32(&s_full[s]), parity);
+    Vec8 v[U];
+    if (active) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint4 t = ld_shared_v4_u(ring + (uint32_t)s * stage_bytes + voff + (uint32_t)u * vstep);
+        v[u].u[0] = t.x; v[u].u[1] = t.y; v[u].u[2] = t.z; v[u].u[3] = t.w;
+      }
+    }
+    __syncthreads();   // every thread holds its vectors: the stage may be refilled
+    if (threadIdx.x == 0) {
+      const long long nx = i + (long long)GN_TMA_STAGES * gridDim.x;
+      if (nx < nfull) issue(nx, s);
+    }
+    if (active) {
+      const long long p = i * chunk + lp;
+#pragma unroll
+      for (int u = 0; u < U; ++u) gn_affine_store<SILU>(v[u], a, b, dst + (p + (long long)u * P) * C);
+    }
+    if (++s == GN_TMA_STAGES) { s = 0; parity ^= 1u; }
+  }
+  // the image's last, partial chunk
+  if (blockIdx.x == gridDim.x - 1 && active) {
+    const act_t* src = c < c0 ? g0 + c : g1 + (c - c0);
+    const long long ld = c < c0 ? c0 : c1;
+    for (long long pp = nfull * chunk + lp; pp < hw; pp += P) gn_affine_store<SILU>(ld_vec8(src + pp * ld), a, b, dst + pp * C);
+  }
+}
+
+// First-level fold of the producers' partial tables: in[n][bpi][W] (W = 2 * (c/2) floats per M tile) ->
+// out[n][S][W], row s = sum of blocks [s*bpi/S, (s+1)*bpi/S) in block order, fp64 accumulation (deterministic).
+// grid = (S, n); a thread owns column t % W and every (256/W)-th block of the range; fully coalesced reads.
+constexpr int GN_FOLD_THREADS = 256;
+
+__global__ void __launch_bounds__(GN_FOLD_THREADS)
+gn_fold1_kernel(const float* __restrict__ in, int bpi, int W, int S, float* __restrict__ out) {
+  __shared__ double s_red[GN_FOLD_THREADS];
+  const int s = blockIdx.x, n = blockIdx.y;
+  const int b_lo = int((long long)s * bpi / S), b_hi = int((long long)(s + 1) * bpi / S);
+  const int wcols = W < GN_FOLD_THREADS ? W : GN_FOLD_THREADS;      // columns handled per sweep
+  const int lanes = GN_FOLD_THREADS / wcols;                         // block-lanes per column
+  const int col_in = threadIdx.x % wcols, bl = threadIdx.x / wcols;
+  const float* base = in + (long long)n * bpi * W;
+  float* dst = out + ((long long)n * S + s) * W;
+  for (int col0 = 0; col0 < W; col0 += wcols) {
+    const int col = col0 + col_in;
+    double acc = 0.0;
+    if (col < W && bl < lanes) {
+      int b = b_lo + bl;
+      for (; b + 3 * lanes < b_hi; b += 4 * lanes) {
+        const float v0 = __ldg(base + (long long)b * W + col);
+        const float v1 = __ldg(base + (long long)(b + lanes) * W + col);
+        const float v2 = __ldg(base + (long long)(b + 2 * lanes) * W + col);
+        const float v3 = __ldg(base + (long long)(b + 3 * lanes) * W + col);
+        acc += (double)v0; acc += (double)v1; acc += (double)v2; acc += (double)v3;
+      }
+      for (; b < b_hi; b += lanes) acc += (double)__ldg(base + (long long)b * W + col);
+    }
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    if (bl == 0 && col < W) {
+      double t = s_red[col_in];
+      for (int l = 1; l < lanes; ++l) t += s_red[l * wcols + col_in];
+      dst[col] = (float)t;
+    }
+    __syncthreads();
   }
 }
 
@@ -313,10 +562,8 @@ __global__ void gn_cluster_kernel(const act_t* __restrict__ x0, int c0, const ac
     float f[8];
     unpack8(v, f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float y = fmaf(f[i], ga[i], gb[i]);
-      f[i] = silu ? silu_f(y) : y;
-    }
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], ga[i], gb[i]);
+    if (silu) silu8(f);
     st_vec8(dst + pp * C, f);
   }
 }
@@ -456,6 +703,66 @@ GnPlan gn_plan(int64_t n, int64_t hw, int64_t C) {
   g.smem = sizeof(float) * 2 * (size_t)g.P * (size_t)C;
   return g;
 }
+// CTAs per image of the streaming apply pass: exactly the resident slots of the device (chunks are interleaved over the
+// CTAs, so any count balances; a partial second wave would cost a whole extra pass)
+// block shape of the apply pass: ~256 threads = CV channel vectors x P pixels (at ~60 registers four such CTAs fill an
+// SM; 384-thread CTAs would leave a third of the register file idle)
+int gn_apply_shape(int64_t C, int64_t hw, int* P) {
+  const int CV = int(C / 8);
+  int p = 256 / CV;
+  if (p < 1) p = 1;
+  if ((int64_t)p > hw) p = (int)hw;
+  *P = p;
+  return (CV * p + 31) / 32 * 32;
+}
+template <typename K>
+unsigned gn_apply_ctas(K kernel, int threads, size_t smem, int64_t n, int64_t hw, int P) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  long long ctas = (long long)sms * per_sm / n;
+  const long long chunks = (hw + (long long)GN_APPLY_UNROLL * P - 1) / ((long long)GN_APPLY_UNROLL * P);
+  if (ctas > chunks) ctas = chunks;
+  if (ctas < 1) ctas = 1;
+  return (unsigned)ctas;
+}
+
+// the streaming pass of both GroupNorm forms: bulk-copy ring for tensors beyond the L2, register path otherwise
+template <bool PARTS>
+int launch_gn_apply(const void* x0, int64_t c0, const void* x1, int64_t c1, int64_t n, int64_t hw, int groups, float eps,
+                    const float* gamma, const float* beta, int silu, const float* stats, const float* p0, int S0,
+                    const float* p1, int S1, void* out, cudaStream_t stream) {
+  const int64_t C = c0 + c1;
+  const int CV = int(C / 8);
+  static const long long tma_min_bytes = [] {
+    const char* e = getenv("CB_GN_TMA_MIN_BYTES");
+    return e ? atoll(e) : (32LL << 20);
+  }();
+  if (CV <= GN_TMA_THREADS && 2 * n * hw * C >= tma_min_bytes && hw >= 4LL * GN_APPLY_UNROLL * (GN_TMA_THREADS / CV)) {
+    const int P = GN_TMA_THREADS / CV;
+    const size_t smem = (size_t)GN_TMA_STAGES * GN_APPLY_UNROLL * P * C * 2;
+    auto k = silu ? gn_apply_tma_kernel<true, PARTS> : gn_apply_tma_kernel<false, PARTS>;
+    static thread_local bool cfg = false;
+    if (!cfg) {
+      CB_CHECK_CUDA(cudaFuncSetAttribute(gn_apply_tma_kernel<true, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      CB_CHECK_CUDA(cudaFuncSetAttribute(gn_apply_tma_kernel<false, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      cfg = true;
+    }
+    dim3 grid(gn_apply_ctas(k, GN_TMA_THREADS, smem, n, hw, P), (unsigned)n);
+    k<<<grid, GN_TMA_THREADS, smem, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw, groups, P, eps, gamma,
+                                              beta, stats, p0, S0, p1, S1, (act_t*)out);
+  } else {
+    int P = 1;
+    const int threads = gn_apply_shape(C, hw, &P);
+    auto k = silu ? gn_apply_kernel<true, PARTS> : gn_apply_kernel<false, PARTS>;
+    dim3 grid(gn_apply_ctas(k, threads, 0, n, hw, P), (unsigned)n);
+    k<<<grid, threads, 0, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw, groups, P, eps, gamma, beta, stats,
+                                    p0, S0, p1, S1, (act_t*)out);
+  }
+  CB_CHECK_CUDA(cudaGetLastError());
+  return CB_OK;
+}
 size_t gn_ws_floats(const GnPlan& g, int64_t n, int groups) {
   return (size_t)n * groups * 2 + (size_t)n * g.splits * groups * 2 + (size_t)n;
 }
@@ -539,11 +846,51 @@ extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int
   gn_stats_kernel<<<grid, g.threads, g.smem, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1,
                                                        (int)c1, hw, groups, g.P, g.pix_per_cta, stats, partials, counters);
   CB_CHECK_CUDA(cudaGetLastError());
-  gn_apply_kernel<<<grid, g.threads, 0, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw,
-                                                  groups, g.P, g.pix_per_cta, eps, gamma, beta, silu, stats,
-                                                  (act_t*)out);
-  CB_CHECK_CUDA(cudaGetLastError());
+  {
+    const int rc = launch_gn_apply<false>(x0, c0, x1, c1, n, hw, groups, eps, gamma, beta, silu, stats, nullptr, 0, nullptr, 0, out, stream);
+    if (rc) return rc;
+  }
   CB_LAUNCHED(2);
+  return CB_OK;
+}
+
+extern "C" int64_t cb_gn_partial_blocks(int64_t h, int64_t w, int tw, int th) {
+  if (h <= 0 || w <= 0 || tw <= 0 || th <= 0 || (tw * th) % 32 != 0) return 0;
+  return ((w + tw - 1) / tw) * ((h + th - 1) / th);   // one row per M tile of the image
+}
+
+extern "C" int cb_groupnorm_from_partials(const void* x0, int64_t c0, const float* part0, int64_t bpi0, const void* x1,
+                                          int64_t c1, const float* part1, int64_t bpi1, int64_t n, int64_t hw, int groups,
+                                          float eps, const float* gamma, const float* beta, int silu, void* out,
+                                          float* stats, cudaStream_t stream) {
+  CB_REQUIRE(x0 && part0 && out && stats && gamma && beta, "cb_groupnorm_from_partials: null pointer");
+  const int64_t C = c0 + c1;
+  CB_REQUIRE(c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0, "cb_groupnorm_from_partials: channels must be multiples of 8");
+  CB_REQUIRE(c1 == 0 || (x1 && part1 && bpi1 > 0), "cb_groupnorm_from_partials: c1 > 0 needs x1 and its partials");
+  CB_REQUIRE(groups > 0 && C % groups == 0 && (C / groups) % 2 == 0, "cb_groupnorm_from_partials: %lld channels / %d groups must be an even group size", (long long)C, groups);
+  CB_REQUIRE(n > 0 && n <= 65535 && hw > 0 && bpi0 > 0, "cb_groupnorm_from_partials: empty input");
+  CB_REQUIRE(C <= GN_PART_MAXC, "cb_groupnorm_from_partials: more than %d channels unsupported", GN_PART_MAXC);
+  CB_REQUIRE(groups <= 64, "cb_groupnorm_from_partials: at most 64 groups");
+  // first-level fold of a long partial table into <= GN_PART_ROWS rows (workspace: `stats`, both sources back to back)
+  const float* p0 = part0; const float* p1 = part1;
+  int S0 = (int)bpi0, S1 = (int)bpi1, launches = 1;
+  float* ws = stats;
+  if (bpi0 > GN_PART_ROWS) {
+    gn_fold1_kernel<<<dim3(GN_PART_ROWS, (unsigned)n), GN_FOLD_THREADS, 0, stream>>>(part0, (int)bpi0, (int)c0, GN_PART_ROWS, ws);
+    CB_CHECK_CUDA(cudaGetLastError());
+    p0 = ws; S0 = GN_PART_ROWS; ws += (size_t)n * GN_PART_ROWS * c0; ++launches;
+  }
+  if (c1 > 0 && bpi1 > GN_PART_ROWS) {
+    gn_fold1_kernel<<<dim3(GN_PART_ROWS, (unsigned)n), GN_FOLD_THREADS, 0, stream>>>(part1, (int)bpi1, (int)c1, GN_PART_ROWS, ws);
+    CB_CHECK_CUDA(cudaGetLastError());
+    p1 = ws; S1 = GN_PART_ROWS; ++launches;
+  }
+  {
+    const int rc = launch_gn_apply<true>(x0, c0, x1, c1, n, hw, groups, eps, gamma, beta, silu, nullptr, p0, S0,
+                                         c1 > 0 ? p1 : nullptr, S1, out, stream);
+    if (rc) return rc;
+  }
+  CB_LAUNCHED(launches);
   return CB_OK;
 }
 

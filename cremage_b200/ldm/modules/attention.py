@@ -315,8 +315,9 @@ class SpatialTransformer(PackedModule, LoraBranches):
         h2d = ops.igemm(g.view(b * n, c), p["wi"], self.inner_dim, bias=p["bi"])
         for blk in self.transformer_blocks:
             h2d = blk._run(h2d, b, n, ctx2d, nk)
-        out = ops.igemm(h2d, p["wo"], c, bias=p["bo"], residual=x.view(b * n, c))
-        return out.view(b, hh, ww, c)
+        # rows as a (b, 1, n) pixel grid so that the fused GroupNorm statistics of the output are per image
+        out = ops.igemm(h2d.view(b, 1, n, h2d.shape[-1]), p["wo"], c, bias=p["bo"], residual=x.view(b * n, c), gn_stats=True)
+        return ops.nhwc(out, b, hh, ww, c)
 
     def forward(self, x, context=None):
         require_cuda(x, "SpatialTransformer.forward")

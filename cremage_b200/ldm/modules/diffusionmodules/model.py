@@ -37,7 +37,7 @@ class Upsample(PackedModule):
         if not self.with_conv:
             return up
         n, h, w, c = up.shape
-        return ops.igemm(up, p["w"], c, taps=ops.TAPS_3X3, bias=p["b"]).view(n, h, w, c)
+        return ops.nhwc(ops.igemm(up, p["w"], c, taps=ops.TAPS_3X3, bias=p["b"], gn_stats=True), n, h, w, c)
 
     def forward(self, x):
         require_cuda(x, "Upsample.forward")
@@ -67,8 +67,8 @@ class Downsample(PackedModule):
             raise ValueError("cremage_b200: Downsample needs even spatial extents")
         xs = ops.parity_split(x)
         out = ops.igemm(xs.view(4 * n, h // 2, w // 2, c), p["w"], c, out_grid=(n, h // 2, w // 2),
-                        taps=ops.taps_3x3_stride2_asym(n), bias=p["b"])
-        return out.view(n, h // 2, w // 2, c)
+                        taps=ops.taps_3x3_stride2_asym(n), bias=p["b"], gn_stats=True)
+        return ops.nhwc(out, n, h // 2, w // 2, c)
 
     def forward(self, x):
         require_cuda(x, "Downsample.forward")
@@ -111,10 +111,10 @@ class ResnetBlock(PackedModule):
         n, hh, ww, _ = x.shape
         co = self.out_channels
         g = ops.groupnorm(x, p["g1"], p["b1"], self.norm1.eps, silu=True)
-        h = ops.igemm(g, p["w1"], co, taps=ops.TAPS_3X3, bias=p["c1"]).view(n, hh, ww, co)
+        h = ops.nhwc(ops.igemm(g, p["w1"], co, taps=ops.TAPS_3X3, bias=p["c1"], gn_stats=True), n, hh, ww, co)
         g2 = ops.groupnorm(h, p["g2"], p["b2"], self.norm2.eps, silu=True)
         xs = ops.igemm(x, p["ws"], co, bias=p["cs"]) if "ws" in p else x.view(-1, co)
-        return ops.igemm(g2, p["w2"], co, taps=ops.TAPS_3X3, bias=p["c2"], residual=xs).view(n, hh, ww, co)
+        return ops.nhwc(ops.igemm(g2, p["w2"], co, taps=ops.TAPS_3X3, bias=p["c2"], residual=xs, gn_stats=True), n, hh, ww, co)
 
     def forward(self, x, temb=None):
         require_cuda(x, "ResnetBlock.forward")
@@ -168,8 +168,8 @@ class AttnBlock(PackedModule):
             ops.softmax_rows(s, scale, out=pm)
             ops.igemm(p["wv_rows"], hn[i], npx, out=vt)              # v^T [c, npx] = Wv h^T
             ops.igemm(pm, vt, c, bias=p["bv"], out=o[i])             # O = P v + bv
-        out = ops.igemm(o.view(n * npx, c), p["wo"], c, bias=p["bo"], residual=x.view(n * npx, c))
-        return out.view(n, hh, ww, c)
+        out = ops.igemm(o.view(n, 1, npx, c), p["wo"], c, bias=p["bo"], residual=x.view(n * npx, c), gn_stats=True)
+        return ops.nhwc(out, n, hh, ww, c)
 
     def forward(self, x):
         require_cuda(x, "AttnBlock.forward")

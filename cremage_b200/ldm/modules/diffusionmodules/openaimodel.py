@@ -63,7 +63,8 @@ class Upsample(PackedModule):
         if not self.use_conv:
             return up
         n, h, w, _ = up.shape
-        return ops.igemm(up, p["w"], self.out_channels, taps=ops.TAPS_3X3, bias=p["b"]).view(n, h, w, self.out_channels)
+        return ops.nhwc(ops.igemm(up, p["w"], self.out_channels, taps=ops.TAPS_3X3, bias=p["b"], gn_stats=True),
+                        n, h, w, self.out_channels)
 
     def forward(self, x):
         require_cuda(x, "Upsample.forward")
@@ -94,8 +95,8 @@ class Downsample(PackedModule):
             raise ValueError("cremage_b200: Downsample needs even spatial extents")
         xs = ops.parity_split(x)
         out = ops.igemm(xs.view(4 * n, h // 2, w // 2, c), p["w"], self.out_channels, out_grid=(n, h // 2, w // 2),
-                        taps=ops.taps_3x3_stride2(n), bias=p["b"])
-        return out.view(n, h // 2, w // 2, self.out_channels)
+                        taps=ops.taps_3x3_stride2(n), bias=p["b"], gn_stats=True)
+        return ops.nhwc(out, n, h // 2, w // 2, self.out_channels)
 
     def forward(self, x):
         require_cuda(x, "Downsample.forward")
@@ -165,7 +166,7 @@ class ResBlock(TimestepBlock, PackedModule):
         n, hh, ww, _ = x.shape
         co = self.out_channels
         g = ops.groupnorm(x, p["g1"], p["b1"], self.in_layers[0].eps, silu=True, x1=skip)
-        h = ops.igemm(g, p["w1"], co, taps=ops.TAPS_3X3, bias=p["c1"], rowbias=emb_bias).view(n, hh, ww, co)
+        h = ops.nhwc(ops.igemm(g, p["w1"], co, taps=ops.TAPS_3X3, bias=p["c1"], rowbias=emb_bias, gn_stats=True), n, hh, ww, co)
         g2 = ops.groupnorm(h, p["g2"], p["b2"], self.out_layers[0].eps, silu=True)
         if "ws" in p:
             xs = ops.igemm(x, p["ws"], co, a1=skip, bias=p["cs"])
@@ -173,8 +174,8 @@ class ResBlock(TimestepBlock, PackedModule):
             if skip is not None:
                 raise ValueError("identity skip connection with a concatenated input")
             xs = x.view(-1, co)
-        out = ops.igemm(g2, p["w2"], co, taps=ops.TAPS_3X3, bias=p["c2"], residual=xs)
-        return out.view(n, hh, ww, co)
+        out = ops.igemm(g2, p["w2"], co, taps=ops.TAPS_3X3, bias=p["c2"], residual=xs, gn_stats=True)
+        return ops.nhwc(out, n, hh, ww, co)
 
     def _emb_out(self, emb: torch.Tensor) -> torch.Tensor:
         p = self.packed(emb.device)

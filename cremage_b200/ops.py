@@ -210,6 +210,16 @@ GEGLU_PAIR = int(_os.environ.get("CB_GEGLU_PAIR", "1"))
 GEGLU_BN = int(_os.environ.get("CB_GEGLU_BN", "256"))   # N tile of the fused GEGLU projection (x | gate halves)
 
 
+# GroupNorm statistics fused into the producing launch's epilogue; the GroupNorm is then a fold of the partials + ONE
+# streaming pass (one read + one write per element).  Pays for tensors that do not stay in the 126 MB L2 between
+# producer and GroupNorm (the VAE decoder's 128^2..512^2 levels, hires / SDXL top levels at large batch): measured
+# 2.5 -> 4.7 TB/s there; for L2-resident tensors the single-pass cluster kernel is as fast (UNet step unchanged
+# either way, profiles/r1_groupnorm_fused_stats.md), so small outputs keep it.
+GN_FUSE = int(_os.environ.get("CB_GN_FUSE", "1"))
+GN_FUSE_MIN_K_CHUNKS = int(_os.environ.get("CB_GN_FUSE_MIN_K_CHUNKS", "1"))
+GN_FUSE_MIN_BYTES = int(_os.environ.get("CB_GN_FUSE_MIN_BYTES", str(64 << 20)))
+
+
 TAPS_1X1 = ([0], [0], [0])
 TAPS_3X3 = ([kw - 1 for kh in range(3) for kw in range(3)], [kh - 1 for kh in range(3) for kw in range(3)], [0] * 9)
 
@@ -253,11 +263,13 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           mode: int = EPI_LINEAR, out: Optional[torch.Tensor] = None, out_f32: bool = False, out_ld: Optional[int] = None,
           out_scale: float = 1.0, heads: Optional[Tuple[int, int, int, int, int]] = None, bn: Optional[int] = None,
           stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None, nsub: int = 0,
-          ksplit: Optional[int] = None) -> torch.Tensor:
+          ksplit: Optional[int] = None, gn_stats: bool = False) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
     heads: (d, dpad, n_heads, tokens_per_batch, which_stride) for EPI_HEADS (then `out` must be given).
+    gn_stats: the output feeds a GroupNorm -- when the launch qualifies (see `_gn_fusable`) its epilogue also writes
+    per-block partial statistics, attached to the returned tensor as `_gn_part` for `groupnorm` to pick up.
     """
     _need_cuda(a0, a1, wgt, bias, rowbias, residual, out)
     assert a0.dtype == ACT and wgt.dtype == ACT and a0.is_contiguous() and wgt.is_contiguous()
@@ -293,6 +305,11 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         else:
             bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
     ksplit = ksplit if (ksplit and can_split) else 1
+    gn_part = None
+    if (gn_stats and GN_FUSE and ksplit == 1 and mode == EPI_LINEAR and not out_f32 and act == ACT_NONE and out_scale == 1.0
+            and cout % 8 == 0 and num_k >= GN_FUSE_MIN_K_CHUNKS and 2 * rows * cout >= GN_FUSE_MIN_BYTES and (tw * th) % 32 == 0 and out is None and out_ld is None):
+        bpi = (-(-w // tw)) * (-(-h // th))   # one row of partials per M tile of an image
+        gn_part = torch.empty((n, bpi, 2, cout // 2), dtype=torch.float32, device=a0.device)
     if out is None:
         ld = out_ld if out_ld is not None else cout
         out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
@@ -332,6 +349,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     if heads is not None:
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
     d.bn, d.stages, d.epilogue, d.cta_pair, d.nsub, d.ksplit = bn, stages, epilogue, int(bool(pair)), nsub, ksplit
+    d.gn_partials = _p(gn_part)
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
             flops=2.0 * rows * len(dw) * (c0 + c1) * ncols,
@@ -345,7 +363,18 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
             _p(part), ksplit, rows, cout, cout, _p(bias), _p(rowbias), rowbias.stride(0) if rowbias is not None else 0,
             h * w, _p(residual), residual.shape[-1] if residual is not None else 0, _p(out), ld, _stream()),
             nbytes=4.0 * ksplit * rows * cout + 2.0 * rows * cout)
+    if gn_part is not None:
+        out._gn_part = gn_part
     return out
+
+
+def nhwc(t: torch.Tensor, n: int, h: int, w: int, c: int) -> torch.Tensor:
+    """[rows, c] -> [n, h, w, c] view that keeps the fused GroupNorm partials of the producing launch attached."""
+    v = t.view(n, h, w, c)
+    part = getattr(t, "_gn_part", None)
+    if part is not None:
+        v._gn_part = part
+    return v
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -408,6 +437,17 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     if ws <= 0:
         raise ValueError(f"groupnorm: unsupported shape n={n} hw={hw} c={c0 + c1} groups={groups}")
     stats = torch.empty((ws // 4,), dtype=torch.float32, device=x0.device)
+    part0 = getattr(x0, "_gn_part", None)
+    part1 = getattr(x1, "_gn_part", None) if x1 is not None else None
+    if (part0 is not None and (x1 is None or part1 is not None) and ((c0 + c1) // groups) % 2 == 0 and n <= 65535
+            and c0 + c1 <= 2560 and groups <= 64):
+        # statistics came with the producers' epilogues: fold + one streaming pass
+        stats = torch.empty((n * 32 * (c0 + c1),), dtype=torch.float32, device=x0.device)
+        _launch("cb_groupnorm_from_partials", lambda: _lib.load().cb_groupnorm_from_partials(
+            _p(x0), c0, _p(part0), part0.shape[1], _p(x1), c1, _p(part1), 0 if part1 is None else part1.shape[1], n, hw,
+            groups, eps, _p(gamma), _p(beta), int(silu), _p(out), _p(stats), _stream()),
+            nbytes=4.0 * n * hw * (c0 + c1), tag=f"n={n} hw={hw} c={c0}+{c1}")
+        return out
     _launch("cb_groupnorm_nhwc", lambda: _lib.load().cb_groupnorm_nhwc(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(gamma), _p(beta), int(silu),
                                         _p(out), _p(stats), _stream()),
             nbytes=4.0 * n * hw * (c0 + c1),  # algorithmic: one bf16 read + one bf16 write per element

@@ -89,6 +89,10 @@ typedef struct cb_igemm_desc {
   int nsub;              /* pair mode: 0 = auto (two N tiles share each A stage when 3 * bn <= 512), 1 = never */
   int ksplit;            /* > 1: split K by tap groups; `out` must be an fp32 workspace [ksplit][rows][out_ld], no
                           * bias / rowbias / residual / activation here -- cb_splitk_reduce applies them */
+  float* gn_partials;    /* optional: fused GroupNorm statistics of the (16-bit rounded) output for a following
+                          * cb_groupnorm_from_partials: fp32 [n][cb_gn_partial_blocks(h, w, tw, th)][2][cout/2], per M tile of
+                          * the image and channel pair the sum and the sum of squares; plain 16-bit epilogues only
+                          * (bias / rowbias / residual), ksplit <= 1, tw * th % 32 == 0.  Every entry is written. */
 } cb_igemm_desc;
 
 int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
@@ -126,6 +130,17 @@ int64_t cb_groupnorm_workspace_bytes(int64_t c, int64_t n, int64_t hw, int group
 int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int64_t c1, int64_t n, int64_t hw, int groups,
                       float eps, const float* gamma, const float* beta, int silu, void* out, float* stats,
                       cudaStream_t stream);
+
+/* GroupNorm (+SiLU) whose statistics were accumulated by the producing cb_igemm launches (gn_partials): a fold of
+ * the partials in fixed order (deterministic, fp64 accumulation) + ONE streaming pass (one read, one write per
+ * element -- the algorithmic minimum).  part0 / part1: the partial buffers of the two sources with bpi0 / bpi1 blocks
+ * per image (cb_gn_partial_blocks of the producing launch); stats: n * 32 * (c0 + c1) floats of workspace (the
+ * partial tables reduced to 32 rows per image; the final fold runs in the apply kernel's prologue). */
+int64_t cb_gn_partial_blocks(int64_t h, int64_t w, int tw, int th);   /* 0: tile not supported */
+int cb_groupnorm_from_partials(const void* x0, int64_t c0, const float* part0, int64_t bpi0, const void* x1, int64_t c1,
+                               const float* part1, int64_t bpi1, int64_t n, int64_t hw, int groups, float eps,
+                               const float* gamma, const float* beta, int silu, void* out, float* stats,
+                               cudaStream_t stream);
 
 /* LayerNorm over the last dim of bf16 [rows][c] (nn.LayerNorm, ldm/modules/attention.py:900-902) */
 int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, const float* gamma, const float* beta, void* out,

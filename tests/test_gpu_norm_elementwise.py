@@ -125,3 +125,76 @@ def test_sampler_steps_match_reference_expressions():
     assert (xo.cpu() - xr).abs().max().item() < 1e-4
     xin = ops.cfg_scale_input(x.cuda(), 0.25)
     assert torch.equal(xin.cpu(), torch.cat([x * 0.25, x * 0.25]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GroupNorm statistics fused into the producing cb_igemm launch (gn_partials) + fold + streaming apply
+# ---------------------------------------------------------------------------------------------------------------
+def _conv_with_stats(ops, x_nhwc, cin, cout, seed, *, epilogue=0, pair=None, residual=None, rowbias=None, bn=None, taps3=True):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    k = 3 if taps3 else 1
+    wt = torch.randn(cout, cin, k, k, generator=g) * (k * k * cin) ** -0.5
+    b = torch.randn(cout, generator=g) * 0.5
+    out = ops.igemm(x_nhwc, ops.pack_weight(wt).cuda(), cout, taps=ops.TAPS_3X3 if taps3 else ops.TAPS_1X1, bias=b.cuda(),
+                    residual=residual, rowbias=rowbias, epilogue=epilogue, pair=pair, bn=bn, ksplit=1, gn_stats=True)
+    return out
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,epilogue,pair,what", [
+    (2, 32, 32, 256, 320, 1, False, "plain"),     # direct epilogue, single CTA, ragged N tiles (320 = 2 x 160)
+    (2, 32, 32, 256, 320, 2, False, "res"),       # staged epilogue + residual panel
+    (2, 32, 32, 256, 320, 0, True, "rowb"),       # CTA pairs (auto epilogue), per-image bias
+    (3, 8, 8, 256, 128, 0, False, "res"),         # two images per 128-row tile (tn = 2), odd image count
+    (1, 24, 40, 128, 64, 1, False, "plain"),      # tiles overhang the pixel grid
+    (2, 16, 16, 128, 256, 2, True, "plain"),      # staged + pairs
+])
+def test_fused_groupnorm_partials_match_tensor_sums(monkeypatch, n, h, w, cin, cout, epilogue, pair, what):
+    from cremage_b200 import ops
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_K_CHUNKS", 1)
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_BYTES", 0)
+    x = _rand(n, h, w, cin, seed=11).to(ACT).cuda()
+    res = _rand(n * h * w, cout, seed=12).to(ACT).cuda() if what == "res" else None
+    rowb = _rand(n, cout, seed=13).cuda() if what == "rowb" else None
+    out = _conv_with_stats(ops, x, cin, cout, 14, epilogue=epilogue, pair=pair, residual=res, rowbias=rowb)
+    torch.cuda.synchronize()
+    part = getattr(out, "_gn_part", None)
+    assert part is not None and part.shape[0] == n and part.shape[2] == 2 and part.shape[3] == cout // 2
+    o = out.float().view(n, h * w, cout // 2, 2)
+    want_sum = o.sum(dim=(1, 3))
+    want_sq = (o * o).sum(dim=(1, 3))
+    got = part.double().sum(dim=1)
+    scale = want_sq.abs().max().item()
+    assert (got[:, 0].float() - want_sum).abs().max().item() <= 1e-4 * max(1.0, want_sum.abs().max().item())
+    assert (got[:, 1].float() - want_sq).abs().max().item() <= 1e-4 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1,silu", [(2, 32, 32, 320, 0, True), (2, 16, 16, 128, 64, True), (3, 8, 8, 256, 128, False),
+                                               (1, 64, 64, 128, 0, True)])
+def test_groupnorm_from_fused_partials(monkeypatch, n, h, w, c0, c1, silu):
+    """cb_groupnorm_from_partials (fold + one streaming pass) == the stand-alone GroupNorm on the same tensors; with
+    c1 > 0 the 32 groups straddle the two sources of the concat."""
+    from cremage_b200 import ops
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_K_CHUNKS", 1)
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_BYTES", 0)
+    x = _rand(n, h, w, 64, seed=21).to(ACT).cuda()
+    a = ops.nhwc(_conv_with_stats(ops, x, 64, c0, 22), n, h, w, c0)
+    b = ops.nhwc(_conv_with_stats(ops, x, 64, c1, 23, taps3=False), n, h, w, c1) if c1 else None
+    assert getattr(a, "_gn_part", None) is not None and (b is None or getattr(b, "_gn_part", None) is not None)
+    c = c0 + c1
+    gamma = _rand(c, seed=2, scale=0.2, shift=1.0).cuda()
+    beta = _rand(c, seed=3, scale=0.2).cuda()
+    prof = ops.LaunchProfile()
+    with prof:
+        got = ops.groupnorm(a, gamma, beta, 1e-5, silu, x1=b)
+    assert any(k[0] == "cb_groupnorm_from_partials" for k in prof.by_shape()), prof.by_shape()
+    plain_a = a.clone()
+    plain_b = b.clone() if b is not None else None
+    ref = ops.groupnorm(plain_a, gamma, beta, 1e-5, silu, x1=plain_b)
+    torch.cuda.synchronize()
+    xa = torch.cat([a, b], dim=-1) if b is not None else a
+    want = F.group_norm(xa.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)
+    if silu:
+        want = F.silu(want)
+    want = want.permute(0, 2, 3, 1)
+    assert (got.float() - want).abs().max().item() < 3e-2
+    assert (got.float() - ref.float()).abs().max().item() < 1e-2

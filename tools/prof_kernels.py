@@ -130,6 +130,44 @@ def bench_norm(B, iters, warm):
         print(f"{name:22s} elems={rows * c / 1e6:8.1f} M: {ms * 1e3:9.1f} us  {by / ms / 1e6:8.1f} GB/s  {by / ms / 1e6 / bw_peak:6.1%} of HBM peak")
 
 
+def bench_gnfused(B, iters, warm):
+    """GroupNorm statistics fused into the producing conv's epilogue: conv without / with partials, then the
+    GroupNorm from partials (fold + streaming pass) against the stand-alone GroupNorm on the same tensor."""
+    _, bw_peak = peaks()
+    print("== fused GroupNorm statistics: conv (plain | +partials) and GroupNorm (stand-alone | from partials) ==")
+    saved = ops.GN_FUSE_MIN_K_CHUNKS, ops.GN_FUSE_MIN_BYTES
+    ops.GN_FUSE_MIN_K_CHUNKS, ops.GN_FUSE_MIN_BYTES = 1, 0
+    for name, n, h, w, cin, cout, k3, res in [
+            ("unet 320@64 3x3", B, 64, 64, 320, 320, True, True), ("unet 640@32 3x3", B, 32, 32, 640, 640, True, True),
+            ("unet 1280@16 3x3", B, 16, 16, 1280, 1280, True, True), ("unet 1280@8 3x3", B, 8, 8, 1280, 1280, True, False),
+            ("unet 320@64 1x1+res", B, 64, 64, 320, 320, False, True), ("unet 640@32 1x1+res", B, 32, 32, 640, 640, False, True),
+            ("unet 1280@16 1x1+res", B, 16, 16, 1280, 1280, False, True),
+            ("vae 512@128 3x3", B // 2, 128, 128, 512, 512, True, True), ("vae 256@256 3x3", B // 2, 256, 256, 256, 256, True, True),
+            ("vae 128@512 3x3", B // 2, 512, 512, 128, 128, True, True)]:
+        x = act(n, h, w, cin)
+        kk = 3 if k3 else 1
+        wt = ops.pack_weight(torch.randn(cout, cin, kk, kk, device="cuda") * (kk * kk * cin) ** -0.5)
+        bias = torch.zeros(cout, device="cuda")
+        r = act(n * h * w, cout) if res else None
+        taps = ops.TAPS_3X3 if k3 else ops.TAPS_1X1
+        xin = x if k3 else x.view(n, 1, h * w, cin)
+        t0 = timeit(lambda: ops.igemm(xin, wt, cout, taps=taps, bias=bias, residual=r), iters, warm)
+        t1 = timeit(lambda: ops.igemm(xin, wt, cout, taps=taps, bias=bias, residual=r, gn_stats=True), iters, warm)
+        y = ops.nhwc(ops.igemm(xin, wt, cout, taps=taps, bias=bias, residual=r, gn_stats=True), n, h, w, cout)
+        if getattr(y, "_gn_part", None) is None:
+            print(f"{name:22s} conv {t0 * 1e3:8.1f} us: no partials (split-K launch)")
+            continue
+        yp = y.clone()
+        g, b = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+        t2 = timeit(lambda: ops.groupnorm(yp, g, b, 1e-5, True), iters, warm)
+        t3 = timeit(lambda: ops.groupnorm(y, g, b, 1e-5, True), iters, warm)
+        by = 4.0 * n * h * w * cout
+        print(f"{name:22s} conv {t0 * 1e3:8.1f} -> {t1 * 1e3:8.1f} us | gn {t2 * 1e3:8.1f} us ({by / t2 / 1e6 / bw_peak:5.1%}) -> "
+              f"{t3 * 1e3:8.1f} us ({by / t3 / 1e6:7.1f} GB/s, {by / t3 / 1e6 / bw_peak:5.1%} of HBM peak) | "
+              f"net {(t1 + t3 - t0 - t2) * 1e3:+8.1f} us")
+    ops.GN_FUSE_MIN_K_CHUNKS, ops.GN_FUSE_MIN_BYTES = saved
+
+
 def bench_sampler(iters, warm):
     """Per-step latent update kernels (fused CFG mix + update) at sizes where bandwidth, not launch latency, decides:
     algorithmic bytes = 4 B x (streams read + written) per element."""
@@ -168,5 +206,7 @@ if __name__ == "__main__":
         bench_igemm(a.batch, a.iters, a.warm, a.filter)
     if a.only in ("all", "norm"):
         bench_norm(a.batch, a.iters, a.warm)
+    if a.only in ("all", "gnfused"):
+        bench_gnfused(a.batch, a.iters, a.warm)
     if a.only in ("all", "sampler"):
         bench_sampler(a.iters, a.warm)

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Graph-replayed UNet step latency (SD1.5, UNet batch 16) + VAE decode time, for A/B runs of tuning knobs
+(environment variables read by cremage_b200.ops):   CB_GN_FUSE=0 python tools/unet_step.py"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def timed(fn, k):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / k
+
+
+def main():
+    pipe = bench.build_pipeline()
+    unet, vae = pipe.model.diffusion_model, pipe.first_stage_model
+    pa, pkw = bench.unet_probe_inputs("ddim50_b8")
+    z = torch.randn(8, 4, 64, 64, device="cuda")
+    if "--quick" in sys.argv:   # under ncu: capture + two replays, nothing else
+        with torch.no_grad():
+            for _ in range(4):
+                unet(*pa, **pkw)
+        torch.cuda.synchronize()
+        return
+    with torch.no_grad():
+        for _ in range(3):
+            unet(*pa, **pkw)
+            vae.decode(z)
+        u = min(timed(lambda: unet(*pa, **pkw), 20) for _ in range(3))
+        v = min(timed(lambda: vae.decode(z), 5) for _ in range(2))
+    tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("CB_"))
+    print(f"[{tag or 'defaults'}] unet step {u:.3f} ms | vae decode b8 {v:.3f} ms")
+
+
+if __name__ == "__main__":
+    main()
