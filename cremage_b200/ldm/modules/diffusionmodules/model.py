@@ -240,7 +240,7 @@ class Decoder(PackedModule):
 
     def _pack(self, device):
         w_in = self.conv_in.weight.detach().to(device=device, dtype=torch.float32)
-        return {"inw": w_in.permute(2, 3, 1, 0).contiguous(), "inb": f32(self.conv_in.bias, device),
+        return {"inw": ops.pack_weight(w_in), "inb": f32(self.conv_in.bias, device),
                 "og": f32(self.norm_out.weight, device), "ob": f32(self.norm_out.bias, device),
                 "ow": packw(self.conv_out.weight, device), "oc": f32(self.conv_out.bias, device)}
 
@@ -248,7 +248,9 @@ class Decoder(PackedModule):
         """z_nhwc: bf16 [n, h, w, >= z_channels] -> fp32 NHWC [n, 8h.., 8w.., 4] (first out_ch channels valid)."""
         p = self.packed(z_nhwc.device)
         block_in = self.conv_in.out_channels
-        h = ops.conv3x3_small_cin(z_nhwc, self.z_channels, p["inw"], p["inb"], block_in)
+        # (the 64-channel TMA box reads channels beyond the tensor's ceil8(z_channels) as out-of-bounds zeros)
+        h = ops.nhwc(ops.igemm(z_nhwc, p["inw"], block_in, taps=ops.TAPS_3X3, bias=p["inb"], gn_stats=True),
+                     *z_nhwc.shape[:3], block_in)
         h = self.mid.block_1._run(h)
         if isinstance(self.mid.attn_1, AttnBlock):
             h = self.mid.attn_1._run(h)
@@ -330,14 +332,15 @@ class Encoder(PackedModule):
 
     def _pack(self, device):
         w_in = self.conv_in.weight.detach().to(device=device, dtype=torch.float32)
-        return {"inw": w_in.permute(2, 3, 1, 0).contiguous(), "inb": f32(self.conv_in.bias, device),
+        return {"inw": ops.pack_weight(w_in), "inb": f32(self.conv_in.bias, device),
                 "og": f32(self.norm_out.weight, device), "ob": f32(self.norm_out.bias, device),
                 "ow": packw(self.conv_out.weight, device), "oc": f32(self.conv_out.bias, device)}
 
     def _trunk(self, x_nhwc: torch.Tensor) -> torch.Tensor:
         """image NHWC 16-bit [n, H, W, >= in_channels] -> normalised + swish features before conv_out."""
         p = self.packed(x_nhwc.device)
-        h = ops.conv3x3_small_cin(x_nhwc, self.in_channels, p["inw"], p["inb"], self.ch)
+        h = ops.nhwc(ops.igemm(x_nhwc, p["inw"], self.ch, taps=ops.TAPS_3X3, bias=p["inb"], gn_stats=True),
+                     *x_nhwc.shape[:3], self.ch)
         for i_level in range(self.num_resolutions):
             for i_block in range(self.num_res_blocks):
                 h = self.down[i_level].block[i_block]._run(h)

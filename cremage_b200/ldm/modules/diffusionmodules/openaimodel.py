@@ -414,7 +414,7 @@ class UNetModel(PackedModule):
             "te0w": packw(self.time_embed[0].weight, device), "te0b": f32(self.time_embed[0].bias, device),
             "te2w": packw(self.time_embed[2].weight, device), "te2b": f32(self.time_embed[2].bias, device),
             "embw": ops.pack_weight(embw), "embb": embb.contiguous(),
-            "inw": w_in.permute(2, 3, 1, 0).contiguous(), "inb": f32(self.input_blocks[0][0].bias, device),
+            "inw": ops.pack_weight(w_in), "inb": f32(self.input_blocks[0][0].bias, device),
             "cin": cin, "cin_pad": cin_pad,
             "og": f32(self.out[0].weight, device), "ob": f32(self.out[0].bias, device),
             "ow": packw(self.out[2].weight, device), "oc": f32(self.out[2].bias, device),
@@ -441,7 +441,8 @@ class UNetModel(PackedModule):
         ctx2d = context.reshape(n * nk, context.shape[-1]).to(ACT).contiguous()
 
         h = ops.nchw_to_nhwc(x, c_pad=p["cin_pad"])
-        h = ops.conv3x3_small_cin(h, p["cin"], p["inw"], p["inb"], mc)
+        # conv_in through the tensor-core path: the 64-channel TMA box reads channels >= cin_pad as out-of-bounds zeros
+        h = ops.nhwc(ops.igemm(h, p["inw"], mc, taps=ops.TAPS_3X3, bias=p["inb"], gn_stats=True), *h.shape[:3], mc)
         hs = [h]
         for module in list(self.input_blocks)[1:]:
             h = module._run(h, None, emb_all, ctx2d, nk)

@@ -275,3 +275,20 @@ def test_split_k_conv(n, h, w, cin, cout, what):
     if what == "res":
         want = want + kw["residual"].float().cpu().view(n, h, w, cout).permute(0, 3, 1, 2)
     _close(split.view(n, h, w, cout).permute(0, 3, 1, 2), want)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 4, 128), (1, 64, 64, 4, 320), (2, 32, 32, 3, 128), (1, 8, 8, 9, 64)])
+def test_conv3x3_tiny_cin_by_channel_oob_fill(n, h, w, cin, cout):
+    """conv_in layers (4 latent / 3 RGB channels): the NHWC input carries ceil8(cin) channels and the 64-channel TMA box
+    reads the rest as out-of-bounds zeros; the weights are zero padded to 64 by pack_weight."""
+    ops = _ops()
+    cpad = -(-cin // 8) * 8
+    x = _rand(n, cin, h, w, seed=5).to(ACT)
+    wt = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=6)
+    b = _rand(cout, seed=7)
+    x_nhwc = torch.zeros(n, h, w, cpad, dtype=ACT)
+    x_nhwc[..., :cin] = x.permute(0, 2, 3, 1)
+    out = ops.igemm(x_nhwc.cuda(), ops.pack_weight(wt).cuda(), cout, taps=ops.TAPS_3X3, bias=b.cuda())
+    torch.cuda.synchronize()
+    want = F.conv2d(x.float(), wt.to(ACT).float(), b, padding=1)
+    _close(out.view(n, h, w, cout).permute(0, 3, 1, 2), want)
