@@ -327,14 +327,6 @@ CB_DEVINL act_t to_act(float x) { return __float2bfloat16(x); }
 CB_DEVINL float from_act(act_t x) { return __bfloat162float(x); }
 #endif
 CB_DEVINL float silu_f(float x) { return x / (1.f + __expf(-x)); }
-// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (no IEEE-division fix-up path): ~3e-7 relative, far below the 16-bit output
-// rounding; the GroupNorm apply pass runs it once per element
-CB_DEVINL float silu_fast_f(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
-  return x * r;
-}
 CB_DEVINL float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 // erf by Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the 16-bit output rounding): one MUFU.RCP, one
 // MUFU.EX2 and 8 FMA-pipe instructions instead of libdevice erff's two-branch polynomial -- the GEGLU epilogue applies

@@ -39,35 +39,20 @@ CB_DEVINL void unpack8(const Vec8& v, float (&f)[8]) {
   }
 }
 
-// 2^t on the FMA / ALU pipes (no MUFU): Cody-Waite split t = n + f, |f| <= 0.5, degree-5 polynomial for 2^f
-// (relative error 2.4e-6, two orders below the 16-bit output rounding), exponent added with integer arithmetic.
-CB_DEVINL float ex2_fma(float t) {
-  t = fmaxf(t, -125.f);
-  const float fl = t + 12582912.f;           // 1.5 * 2^23: n = round(t) lands in the low mantissa bits
-  const float f = t - (fl - 12582912.f);
-  float p = fmaf(1.33335581e-3f, f, 9.61812911e-3f);
-  p = fmaf(p, f, 5.55041087e-2f);
-  p = fmaf(p, f, 2.40226507e-1f);
-  p = fmaf(p, f, 6.93147182e-1f);
-  p = fmaf(p, f, 1.f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(fl) << 23));
-}
-
-// y[i] <- y[i] * sigmoid(y[i]) for 8 values.  The streaming GroupNorm+SiLU pass is co-limited by the XU pipe (16
-// MUFU/clk/SM; exp + reciprocal per element = 75 % busy at 4.7 TB/s, profiles/r1_groupnorm_fused_stats.md), so: half of
-// the exponentials run as polynomials on the FMA pipe, and one reciprocal serves four denominators
-// (1/a0 = a1 * (a2*a3) / (a0*a1*a2*a3) ...): 4 MUFU.EX2 + 2 MUFU.RCP per 8 elements instead of 16 MUFU.  The exponent is
-// clamped at 2^30 so the 4-way product stays finite; silu(x) for x < -20.8 is below the smallest 16-bit subnormal.
+// y[i] <- y[i] * sigmoid(y[i]) for 8 values with 8 MUFU.EX2 + 2 MUFU.RCP: one reciprocal serves four denominators
+// (1/a0 = a1 * (a2*a3) / (a0*a1*a2*a3) ...), which keeps the XU pipe (16 MUFU/clk/SM) and the issue slots of the
+// streaming GroupNorm+SiLU pass below the HBM bound.  (Measured alternative: part of the exponentials as FMA-pipe
+// polynomials -- faster in short bursts, slower under the sustained power cap; profiles/r1_groupnorm_fused_stats.md.)
+// The exponent is clamped at 2^30 so the 4-way product stays finite; silu(x) for x < -20.8 is below the smallest
+// 16-bit subnormal either way.
 CB_DEVINL void silu8(float (&y)[8]) {
 #pragma unroll
   for (int h = 0; h < 8; h += 4) {
     float a[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float t = fminf(-1.4426950408889634f * y[h + i], 30.f);
       float e;
-      if (i & 1) e = ex2_fma(t);
-      else asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(-1.4426950408889634f * y[h + i], 30.f)));
       a[i] = 1.f + e;
     }
     const float p01 = a[0] * a[1], p23 = a[2] * a[3];
