@@ -63,6 +63,7 @@ SIGNATURES = {
     "cb_groupnorm_from_partials": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _int, _f32, _vp, _vp, _int, _vp, _vp, _vp],
     "cb_layernorm": [_vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp],
     "cb_nchw_to_nhwc": [_vp, _int, _i64, _i64, _i64, _i64, _f32, _vp, _vp],
+    "cb_add_nchw_to_nhwc": [_vp, _vp, _int, _i64, _i64, _i64, _vp, _vp],
     "cb_nhwc_to_nchw_f32": [_vp, _int, _i64, _i64, _i64, _i64, _vp, _vp],
     "cb_upsample2x_nhwc": [_vp, _i64, _i64, _i64, _i64, _vp, _vp],
     "cb_parity_split_nhwc": [_vp, _i64, _i64, _i64, _i64, _vp, _vp],

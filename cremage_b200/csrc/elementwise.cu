@@ -42,6 +42,31 @@ __global__ void pointwise_nchw_to_nhwc_kernel(const float* __restrict__ src, lon
   }
 }
 
+// ControlNet residual injection (cldm/cldm.py:59-66: `h += control.pop()`, `hs.pop() + control.pop()`):
+// dst[n][p][ch] = base[n][p][ch] + ctrl[n][ch][p], the control tensor arriving NCHW from the (out-of-scope) ControlNet
+template <typename T>
+__global__ void add_nchw_to_nhwc_kernel(const act_t* __restrict__ base, const T* __restrict__ ctrl, int c, long long hw,
+                                        act_t* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int ch = c0 + j;
+    const long long p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (ch < c && p < hw) ? float(ctrl[(b * c + ch) * hw + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long p = p0 + j;
+    const int ch = c0 + threadIdx.x;
+    if (p < hw && ch < c) {
+      const long long o = (b * hw + p) * c + ch;
+      dst[o] = to_act(from_act(base[o]) + tile[threadIdx.x][j]);
+    }
+  }
+}
+
 // generic tiled transpose for wide channel counts: [n][c][hw] -> [n][hw][c_pad]
 template <typename T>
 __global__ void nchw_to_nhwc_tiled_kernel(const T* __restrict__ src, int c, long long hw, int c_pad, float scale,
@@ -259,6 +284,21 @@ extern "C" int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_
     else if (src_dtype == 1) nchw_to_nhwc_tiled_kernel<__half><<<grid, block, 0, stream>>>((const __half*)src, (int)c, hw, (int)c_pad, scale, D);
     else nchw_to_nhwc_tiled_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (int)c, hw, (int)c_pad, scale, D);
   }
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
+extern "C" int cb_add_nchw_to_nhwc(const void* base, const void* ctrl, int ctrl_dtype, int64_t n, int64_t c, int64_t hw,
+                                   void* dst, cudaStream_t stream) {
+  CB_REQUIRE(base && ctrl && dst && n > 0 && c > 0 && hw > 0 && n <= 65535, "cb_add_nchw_to_nhwc: bad arguments");
+  CB_REQUIRE(ctrl_dtype >= 0 && ctrl_dtype <= 2, "cb_add_nchw_to_nhwc: ctrl_dtype must be 0 (f32), 1 (f16) or 2 (bf16)");
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
+  auto B = (const act_t*)base;
+  auto D = (act_t*)dst;
+  if (ctrl_dtype == 0) add_nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(B, (const float*)ctrl, (int)c, hw, D);
+  else if (ctrl_dtype == 1) add_nchw_to_nhwc_kernel<__half><<<grid, block, 0, stream>>>(B, (const __half*)ctrl, (int)c, hw, D);
+  else add_nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(B, (const __nv_bfloat16*)ctrl, (int)c, hw, D);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import os
 from abc import abstractmethod
-from typing import List, Optional
+from typing import Sequence, List, Optional
 
 import torch
 import torch.nn as nn
@@ -421,7 +421,10 @@ class UNetModel(PackedModule):
         }
 
     # -- forward -------------------------------------------------------------------------------------------------
-    def _forward_impl(self, x: torch.Tensor, t: torch.Tensor, context: torch.Tensor, y: torch.Tensor = None) -> torch.Tensor:
+    def _forward_impl(self, x: torch.Tensor, t: torch.Tensor, context: torch.Tensor, y: torch.Tensor = None,
+                      control: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        """control: ControlNet residuals in the order ControlledUnetModel.forward pops them (cldm/cldm.py:59-66):
+        control[0] is added to the middle block's output, control[1 + i] to the skip of output block i (NCHW)."""
         dev = x.device
         p = self.packed(dev)
         n, c, hh, ww = x.shape
@@ -448,8 +451,14 @@ class UNetModel(PackedModule):
             h = module._run(h, None, emb_all, ctx2d, nk)
             hs.append(h)
         h = self.middle_block._run(h, None, emb_all, ctx2d, nk)
-        for module in self.output_blocks:
-            h = module._run(h, hs.pop(), emb_all, ctx2d, nk)
+        control = list(control) if control else []
+        if control:
+            h = ops.add_nchw(h, control[0])
+        for i, module in enumerate(self.output_blocks):
+            skip = hs.pop()
+            if 1 + i < len(control):
+                skip = ops.add_nchw(skip, control[1 + i])
+            h = module._run(h, skip, emb_all, ctx2d, nk)
         g = ops.groupnorm(h, p["og"], p["ob"], self.out[0].eps, silu=True)
         o = ops.igemm(g, p["ow"], self.out_channels, taps=ops.TAPS_3X3, bias=p["oc"], out_f32=True)
         return ops.nhwc_to_nchw_f32(o.view(n, hh, ww, self.out_channels))
@@ -493,9 +502,13 @@ class UNetModel(PackedModule):
         versions = sum(q._version for q in params)
         stale = versions != self.__dict__.get("_cb_all_versions")
         self.__dict__["_cb_all_versions"] = versions
-        if (p is not before or stale) and self._graphed is not None:
-            self._graphed.reset()  # parameters changed: captured graphs hold stale weight buffers
+        if p is not before or stale:
+            self._reset_graphs()  # parameters changed: captured graphs hold stale weight buffers
         return p
+
+    def _reset_graphs(self):
+        if self._graphed is not None:
+            self._graphed.reset()
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop("_cb_all_params", None)   # .to() / .half() may replace Parameter objects
@@ -503,8 +516,7 @@ class UNetModel(PackedModule):
 
     def invalidate_packed(self):
         super().invalidate_packed()
-        if self._graphed is not None:
-            self._graphed.reset()
+        self._reset_graphs()
 
     def convert_to_fp16(self):
         """openaimodel.py:758-764. Storage dtype only; the kernels always compute bf16 x bf16 -> fp32."""

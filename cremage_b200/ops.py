@@ -482,6 +482,21 @@ def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None, scale: float = 1.
     return out
 
 
+def add_nchw(base: torch.Tensor, ctrl: torch.Tensor) -> torch.Tensor:
+    """base NHWC 16-bit [N,H,W,C] + ctrl NCHW [N,C,H,W] (fp32 / fp16 / bf16) -> new NHWC tensor (ControlNet residuals,
+    cldm/cldm.py:59-66)."""
+    _need_cuda(base, ctrl)
+    assert base.dtype == ACT and base.is_contiguous() and ctrl.dtype in _SRC_DTYPE
+    n, h, w, c = base.shape
+    if tuple(ctrl.shape) != (n, c, h, w):
+        raise ValueError(f"control residual {tuple(ctrl.shape)} does not match the feature map {(n, c, h, w)}")
+    ctrl = ctrl.contiguous()
+    out = torch.empty_like(base)
+    _launch("cb_add_nchw_to_nhwc", lambda: _lib.load().cb_add_nchw_to_nhwc(_p(base), _p(ctrl), _SRC_DTYPE[ctrl.dtype], n, c, h * w,
+                                                                            _p(out), _stream()))
+    return out
+
+
 def nhwc_to_nchw_f32(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
     """x: [N,H,W,C_ld] bf16 or fp32 -> fp32 [N,c,H,W]."""
     _need_cuda(x)

@@ -1,6 +1,7 @@
 """Mirror of the sgm samplers on the SDXL path (modules/sdxl/sgm/modules/diffusionmodules/sampling.py):
 BaseDiffusionSampler (:28-122: prepare_sampling_loop with x *= sqrt(1 + sigma_0^2), denoise through the guider),
-EulerEDMSampler (:155-233, s_churn = 0), EulerAncestralSampler (:361-385), DPMPP2MSampler (:459-573).
+EulerEDMSampler / HeunEDMSampler (:147-220,309-358, s_churn = 0), LinearMultistepSampler (:271-306),
+EulerAncestralSampler (:361-385), DPMPP2MSampler (:459-573).
 `sampler(denoiser, x, cond, uc, num_steps)` as in the reference; `denoiser(input, sigma, c)` is opaque, the latent
 update of each step is one fused kernel.  Step multipliers use the reference's fp32 torch expressions."""
 from typing import Dict, Union
@@ -10,7 +11,7 @@ from tqdm import tqdm
 
 from .... import ops
 from ...util import default, instantiate_from_config
-from .sampling_utils import get_ancestral_step, to_neg_log_sigma, to_sigma
+from .sampling_utils import get_ancestral_step, linear_multistep_coeff, to_neg_log_sigma, to_sigma
 
 DEFAULT_GUIDER = {"target": "sgm.modules.diffusionmodules.guiders.IdentityGuider"}
 
@@ -59,6 +60,64 @@ class EulerEDMSampler(BaseDiffusionSampler):
             # d = (x - denoised) / sigma ; x + d * (next_sigma - sigma)      (:189-200)
             x, _ = ops.step_euler_ancestral(x, None, None, 0.0, float(sigmas[i]), float(sigmas[i + 1]), 0.0,
                                             denoised=denoised.float())
+        return x
+
+
+class HeunEDMSampler(BaseDiffusionSampler):
+    """EDMSampler.sampler_step + HeunEDMSampler.possible_correction_step (:165-193,321-358): Euler predictor, one more
+    denoiser call at next_sigma, x + (d + d_new) / 2 * dt where next_sigma > 0.  Two UNet evaluations per step."""
+
+    def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if s_churn != 0.0:
+            raise NotImplementedError("cremage_b200: HeunEDMSampler with s_churn > 0 is not implemented")
+
+    @torch.no_grad()
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None):
+        x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
+        dev_sig = sigmas.to(x.device)
+        for i in self.get_sigma_gen(num_sigmas):
+            sigma, nxt = float(sigmas[i]), float(sigmas[i + 1])
+            denoised = self.denoise(x, denoiser, s_in * dev_sig[i], cond, uc).float().contiguous()
+            d = ops.axpby(x, 1.0 / sigma, denoised, -1.0 / sigma)             # to_d: (x - denoised) / sigma
+            dt = nxt - sigma
+            euler = ops.axpby(x, 1.0, d, dt)
+            if float(torch.sum(s_in.cpu() * sigmas[i + 1])) < 1e-14:           # all noise levels 0: no correction (:335-337)
+                x = euler
+                continue
+            denoised2 = self.denoise(euler, denoiser, s_in * dev_sig[i + 1], cond, uc).float().contiguous()
+            d_new = ops.axpby(euler, 1.0 / nxt, denoised2, -1.0 / nxt)
+            d_prime = ops.axpby(d, 0.5, d_new, 0.5)
+            x = ops.axpby(x, 1.0, d_prime, dt) if nxt > 0.0 else euler        # torch.where(next_sigma > 0, ...)  (:354-356)
+        return x
+
+
+class LinearMultistepSampler(BaseDiffusionSampler):
+    """:271-306: x + sum_j coeff_j * d_{i-j}, coefficients by host quadrature (linear_multistep_coeff)."""
+
+    def __init__(self, order=4, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.order = order
+
+    @torch.no_grad()
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None, **kwargs):
+        x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
+        dev_sig = sigmas.to(x.device)
+        ds = []
+        sigmas_cpu = sigmas.detach().cpu().numpy()
+        for i in self.get_sigma_gen(num_sigmas):
+            sigma = float(sigmas[i])
+            denoised = denoiser(*self.guider.prepare_inputs(x, s_in * dev_sig[i], cond, uc), **kwargs)
+            denoised = self.guider(denoised, s_in * dev_sig[i]).float().contiguous()
+            ds.append(ops.axpby(x, 1.0 / sigma, denoised, -1.0 / sigma))
+            if len(ds) > self.order:
+                ds.pop(0)
+            cur_order = min(i + 1, self.order)
+            coeffs = [linear_multistep_coeff(cur_order, sigmas_cpu, i, j) for j in range(cur_order)]
+            acc = None   # the reference's sum() adds left to right starting from 0
+            for coeff, d in zip(coeffs, reversed(ds)):
+                acc = ops.axpby(d, float(coeff)) if acc is None else ops.axpby(acc, 1.0, d, float(coeff))
+            x = ops.axpby(x, 1.0, acc, 1.0)
         return x
 
 

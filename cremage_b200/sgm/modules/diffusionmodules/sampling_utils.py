@@ -1,7 +1,24 @@
-"""Mirror of sgm/modules/diffusionmodules/sampling_utils.py helpers on the path (:23-55)."""
+"""Mirror of sgm/modules/diffusionmodules/sampling_utils.py helpers on the path (:7-55)."""
 import torch
+from scipy import integrate
 
 from ...util import append_dims
+
+
+def linear_multistep_coeff(order, t, i, j, epsrel=1e-4):
+    """sampling_utils.py:7-19 (host-side quadrature of the Lagrange basis, fp64)."""
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+
+    def fn(tau):
+        prod = 1.0
+        for k in range(order):
+            if j == k:
+                continue
+            prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=epsrel)[0]
 
 
 def get_ancestral_step(sigma_from, sigma_to, eta=1.0):

@@ -149,6 +149,11 @@ int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, const float*
 /* ---------------------------------------------------------------------------------------------------------------
  * layout / small elementwise kernels
  * ------------------------------------------------------------------------------------------------------------- */
+/* ControlNet residual injection, replaces `h += control.pop()` / `hs.pop() + control.pop()` of
+ * ControlledUnetModel.forward (cldm/cldm.py:59-66): dst[n][p][ch] = base[n][p][ch] + ctrl[n][ch][p]; base / dst NHWC
+ * 16-bit (dst may alias base), ctrl NCHW fp32 / fp16 / bf16 (ctrl_dtype 0 / 1 / 2) as the ControlNet returns it */
+int cb_add_nchw_to_nhwc(const void* base, const void* ctrl, int ctrl_dtype, int64_t n, int64_t c, int64_t hw, void* dst,
+                        cudaStream_t stream);
 /* NCHW (fp32, or fp16/bf16 when src_dtype = 1/2) -> NHWC bf16 with channel padding to c_pad (zeros), times scale */
 int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_t c, int64_t hw, int64_t c_pad, float scale,
                     void* dst, cudaStream_t stream);

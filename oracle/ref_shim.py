@@ -57,6 +57,31 @@ def install():
     _DONE = True
 
 
+def install_lightning_stub():
+    """cldm/cldm.py imports ldm.models.diffusion.ddpm (LatentDiffusion, a pytorch_lightning.LightningModule) at module
+    level; pytorch_lightning is not installed.  Nothing of it runs on the UNet path: a LightningModule = nn.Module stub
+    is enough to import the reference's ControlledUnetModel unmodified."""
+    install()
+    if "pytorch_lightning" in sys.modules:
+        return
+    import torch.nn as nn
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    class LightningModule(nn.Module):
+        pass
+
+    stub("pytorch_lightning", LightningModule=LightningModule)
+    for sub in ("utilities", "utilities.distributed", "utilities.rank_zero"):
+        stub("pytorch_lightning." + sub, rank_zero_only=lambda f: f)
+
+
 def reference_unet(cfg, sd):
     """Reference UNetModel (ldm/modules/diffusionmodules/openaimodel.py:417) for an oracle UNetConfig, loaded with `sd`
     (strict: proves the oracle's key naming equals the reference's)."""

@@ -401,8 +401,11 @@ def _spatial_transformer(sd: SD, p: str, x: Tensor, context: Tensor, heads: int,
     return x + x_in
 
 
-def unet_forward(sd: SD, cfg: UNetConfig, x: Tensor, timesteps: Tensor, context: Tensor) -> Tensor:
-    """UNetModel.forward, openaimodel.py:780-816 (fp32, y=None)."""
+def unet_forward(sd: SD, cfg: UNetConfig, x: Tensor, timesteps: Tensor, context: Tensor,
+                 control: Optional[List[Tensor]] = None, only_mid_control: bool = False) -> Tensor:
+    """UNetModel.forward, openaimodel.py:780-816 (fp32, y=None).  With `control`: ControlledUnetModel.forward,
+    cldm/cldm.py:44-70 -- the residuals are popped from the END of the list (a copy here): one after the middle block
+    (:59-60), one per output block added to the skip before the concat (:62-66) unless only_mid_control."""
     inp, mid, out = unet_layout(cfg)
     t_emb = timestep_embedding(timesteps, cfg.model_channels)
     emb = F.linear(t_emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
@@ -430,8 +433,14 @@ def unet_forward(sd: SD, cfg: UNetConfig, x: Tensor, timesteps: Tensor, context:
         h = run(f"input_blocks.{i}", layers, h)
         hs.append(h)
     h = run("middle_block", mid, h)
+    control = list(control) if control is not None else None
+    if control is not None:
+        h = h + control.pop()
     for i, layers in enumerate(out):
-        h = torch.cat([h, hs.pop()], dim=1)
+        if only_mid_control or control is None:
+            h = torch.cat([h, hs.pop()], dim=1)
+        else:
+            h = torch.cat([h, hs.pop() + control.pop()], dim=1)
         h = run(f"output_blocks.{i}", layers, h)
     h = F.group_norm(h, 32, sd["out.0.weight"], sd["out.0.bias"], 1e-5)
     return F.conv2d(F.silu(h), sd["out.2.weight"], sd["out.2.bias"], padding=1)

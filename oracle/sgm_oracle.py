@@ -257,3 +257,63 @@ def sample_dpmpp_2m_sgm(denoise_fn, x: Tensor, sigmas: Tensor, cond: dict, uc: d
         if trace is not None:
             trace.append(x.clone())
     return x
+
+
+def _cfg_denoise(denoise_fn, x: Tensor, sigma: Tensor, cond: dict, uc: dict, scale: float) -> Tensor:
+    """BaseDiffusionSampler.denoise through VanillaCFG: sampling.py:97-122, guiders.py:24-65."""
+    c_in = {k: torch.cat((uc[k], cond[k]), 0) for k in cond}
+    d_u, d_c = denoise_fn(torch.cat([x] * 2), torch.cat([sigma] * 2), c_in).chunk(2)
+    return d_u + scale * (d_c - d_u)
+
+
+def sample_heun_sgm(denoise_fn, x: Tensor, sigmas: Tensor, cond: dict, uc: dict, scale: float) -> Tensor:
+    """HeunEDMSampler with s_churn = 0: EDMSampler.sampler_step / __call__ (sampling.py:165-220) +
+    possible_correction_step (:332-358)."""
+    x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+    s_in = x.new_ones([x.shape[0]])
+    ap = lambda v: v[(...,) + (None,) * (x.ndim - v.ndim)]
+    for i in range(len(sigmas) - 1):
+        sigma, nxt = s_in * sigmas[i], s_in * sigmas[i + 1]
+        den = _cfg_denoise(denoise_fn, x, sigma, cond, uc, scale)
+        d = (x - den) / ap(sigma)
+        dt = ap(nxt - sigma)
+        euler = x + dt * d
+        if torch.sum(nxt) < 1e-14:
+            x = euler
+        else:
+            den2 = _cfg_denoise(denoise_fn, euler, nxt, cond, uc, scale)
+            d_new = (euler - den2) / ap(nxt)
+            d_prime = (d + d_new) / 2.0
+            x = torch.where(ap(nxt) > 0.0, x + d_prime * dt, euler)
+    return x
+
+
+def sample_lms_sgm(denoise_fn, x: Tensor, sigmas: Tensor, cond: dict, uc: dict, scale: float, order: int = 4) -> Tensor:
+    """LinearMultistepSampler.__call__, sampling.py:282-306; linear_multistep_coeff, sampling_utils.py:7-19."""
+    from scipy import integrate
+
+    def coeff(order_, t, i, j):
+        def fn(tau):
+            prod = 1.0
+            for k in range(order_):
+                if j == k:
+                    continue
+                prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+            return prod
+        return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+    x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+    s_in = x.new_ones([x.shape[0]])
+    ap = lambda v: v[(...,) + (None,) * (x.ndim - v.ndim)]
+    ds: List[Tensor] = []
+    sig_np = sigmas.detach().cpu().numpy()
+    for i in range(len(sigmas) - 1):
+        sigma = s_in * sigmas[i]
+        den = _cfg_denoise(denoise_fn, x, sigma, cond, uc, scale)
+        ds.append((x - den) / ap(sigma))
+        if len(ds) > order:
+            ds.pop(0)
+        cur = min(i + 1, order)
+        cs = [coeff(cur, sig_np, i, j) for j in range(cur)]
+        x = x + sum(c * d for c, d in zip(cs, reversed(ds)))
+    return x

@@ -151,3 +151,55 @@ def test_sgm_dpmpp2m_trajectory_vs_reference_golden():
     err = (z.cpu() - want).abs().max().item()
     print(f"[parity] sgm DPM++2M 6 steps: max_abs_err={err:.4e} latent_absmax={want.abs().max():.2f}")
     assert err <= 2e-2 * max(want.abs().max().item(), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# remaining sgm samplers: HeunEDMSampler, LinearMultistepSampler -- goldens from the unmodified
+# reference (oracle/make_golden_sgm_samplers.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _cond(g, dev="cpu"):
+    cond = {"crossattn": torch.from_numpy(g["cond_crossattn"]).to(dev), "vector": torch.from_numpy(g["cond_vector"]).to(dev)}
+    uc = {"crossattn": torch.from_numpy(g["uc_crossattn"]).to(dev), "vector": torch.from_numpy(g["uc_vector"]).to(dev)}
+    return cond, uc
+
+
+@pytest.mark.parametrize("which", ["heun", "lms"])
+def test_oracle_heun_lms_trajectories_match_reference_golden(which):
+    g, sd = _weights()
+    gs = gold("tiny_sgm_samplers.npz")
+    table = S.legacy_ddpm_sigma_table(1000)
+    net = lambda x, t, c: S.sgm_unet_forward(sd, S.TINY_SGM_UNET, x, t, c["crossattn"], c["vector"])
+    den = lambda x, sigma, c: S.discrete_denoise(net, table, x, sigma, c)
+    cond, uc = _cond(g)
+    fn = S.sample_heun_sgm if which == "heun" else S.sample_lms_sgm
+    with torch.no_grad():
+        z = fn(den, torch.from_numpy(g["x_T"]), S.edm_sigmas(int(gs["steps"]), **EDM), cond, uc, float(g["cfg_scale"]))
+    assert np.abs(z.numpy() - gs[which + "_final"]).max() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["heun", "lms"])
+def test_sgm_heun_lms_trajectories_vs_reference_golden(which):
+    from cremage_b200.sgm.modules.diffusionmodules.denoiser import DiscreteDenoiser
+    from cremage_b200.sgm.modules.diffusionmodules.sampling import HeunEDMSampler, LinearMultistepSampler
+    from cremage_b200.sgm.modules.diffusionmodules.wrappers import OpenAIWrapper
+    g, sd = _weights()
+    gs = gold("tiny_sgm_samplers.npz")
+    model = OpenAIWrapper(_build_sgm_unet(S.TINY_SGM_UNET, sd))
+    den = DiscreteDenoiser(scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+                           num_idx=1000,
+                           discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}).cuda()
+    common = dict(discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization", "params": EDM},
+                  num_steps=int(gs["steps"]),
+                  guider_config={"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG",
+                                 "params": {"scale": float(g["cfg_scale"])}})
+    smp = HeunEDMSampler(**common) if which == "heun" else LinearMultistepSampler(order=int(gs["lms_order"]), **common)
+    cond, uc = _cond(g, "cuda")
+    x_T = torch.from_numpy(g["x_T"]).cuda()
+    keep = x_T.clone()
+    z = smp(lambda inp, sigma, c: den(model, inp, sigma, c), x_T, cond=cond, uc=uc)
+    assert torch.equal(x_T, keep)
+    want = torch.from_numpy(gs[which + "_final"])
+    err = (z.cpu() - want).abs().max().item()
+    print(f"[parity] sgm {which} {int(gs['steps'])} steps: max_abs_err={err:.4e} latent_absmax={want.abs().max():.2f}")
+    assert err <= 2e-2 * max(want.abs().max().item(), 1.0)
