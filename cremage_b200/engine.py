@@ -146,8 +146,19 @@ class GraphedCall:
             from . import _lib
             graph = torch.cuda.CUDAGraph()
             before = _lib.launch_count()
-            with torch.cuda.graph(graph):
-                static_out = self.fn(*static_in)
+            # No garbage collection while the stream is capturing: a collection that happens to destroy an unrelated
+            # dead model's CUDA graphs / pooled memory calls cudaFree-class APIs, which invalidate a global-mode capture
+            # (seen as error 901 in long test runs).  torch.cuda.graph() collects once on entry; keep it off until exit.
+            import gc
+            gc_was_enabled = gc.isenabled()
+            gc.collect()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph):
+                    static_out = self.fn(*static_in)
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
             entry = (graph, static_in, static_out, _lib.launch_count() - before)
             self._graphs[sig] = entry
         graph, static_in, static_out, n_launches = entry

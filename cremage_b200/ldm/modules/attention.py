@@ -9,7 +9,11 @@ LoRA side branches (attention.py:79-96,148-168,306-376,966-1055) keep the refere
 (`q_lora_downs.{i}.weight`, `q_lora_ups.{i}.weight`, `q_lora_alphas.{i}`, ...) and are MERGED into the packed base
 weight when the module packs:  W_eff = W + sum_i lora_weights[i] * (alpha_i / rank_i) * up_i @ down_i  -- the same
 linear map (every branch is `up(down(x))` added to the base projection of the same input), at zero run-time cost.
-IP-adapter tokens must be empty (`ipa_num_tokens=0`); anything else raises instead of silently falling back.
+IP-Adapter tokens (attention.py:338-341,354-358,448-521; CrossAttentionOriginal :623-627,660-681): with
+`ipa_num_tokens = T > 0` the cross-attention (attn2 only, :895-901) owns `to_k_ipa` / `to_v_ipa`, the last T context
+tokens go through them, a second attention with the same queries runs over those T tokens, and
+`out + ipa_scale * out_ipa` enters to_out -- here as a second to_out GEMM with the weight pre-scaled by ipa_scale and
+the first one's result as its residual (to_out is linear), so no extra elementwise pass exists.
 """
 from __future__ import annotations
 
@@ -25,8 +29,8 @@ GEGLU_BN = ops.GEGLU_BN  # N tile of the fused GEGLU projection (x / gate rows i
 
 
 def _check_extras(lora_ranks, ipa_num_tokens):
-    if ipa_num_tokens:
-        raise NotImplementedError("cremage_b200: IP-Adapter tokens are not implemented (ipa_num_tokens must be 0)")
+    if ipa_num_tokens is not None and int(ipa_num_tokens) < 0:
+        raise ValueError("ipa_num_tokens must be >= 0")
 
 
 def zero_init_module(m):
@@ -151,14 +155,24 @@ class CrossAttention(PackedModule, LoraBranches):
         self._add_lora("k", context_dim, inner_dim)
         self._add_lora("v", context_dim, inner_dim)
         self._add_lora("out", inner_dim, query_dim)
+        self.ipa_scale = ipa_scale
+        self.ipa_num_tokens = int(ipa_num_tokens or 0)
+        if self.ipa_num_tokens > 0:   # IP-Adapter FaceID support, attention.py:338-341
+            self.to_k_ipa = nn.Linear(context_dim, inner_dim, bias=False)
+            self.to_v_ipa = nn.Linear(context_dim, inner_dim, bias=False)
 
     def _pack(self, device):
         wq, wk, wv = (self._merged(getattr(self, "to_" + n).weight, n, device) for n in ("q", "k", "v"))
+        wo = self._merged(self.to_out[0].weight, "out", device)
         p = {"wq": ops.pack_weight(wq), "wkv": ops.pack_weight(torch.cat([wk, wv], 0)),
-             "wo": ops.pack_weight(self._merged(self.to_out[0].weight, "out", device)),
-             "bo": f32(self.to_out[0].bias, device)}
+             "wo": ops.pack_weight(wo), "bo": f32(self.to_out[0].bias, device)}
         if self.context_dim == self.query_dim:
             p["wqkv"] = ops.pack_weight(torch.cat([wq, wk, wv], 0))
+        if self.ipa_num_tokens > 0:
+            wk2 = self.to_k_ipa.weight.detach().to(device=device, dtype=torch.float32)
+            wv2 = self.to_v_ipa.weight.detach().to(device=device, dtype=torch.float32)
+            p["wkv_ipa"] = ops.pack_weight(torch.cat([wk2, wv2], 0))
+            p["wo_ipa"] = ops.pack_weight(wo * float(self.ipa_scale))     # to_out(out + s * out_ipa) = to_out(out) + (s W) out_ipa
         return p
 
     def _run(self, x2d: torch.Tensor, batch: int, nq: int, ctx2d: Optional[torch.Tensor], nk: int,
@@ -172,6 +186,26 @@ class CrossAttention(PackedModule, LoraBranches):
             nk = nq
             qkv = ops.igemm(x2d, p["wqkv"], 3 * inner)             # [M, q | k | v]: read in place by the attention kernel
             q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
+        elif self.ipa_num_tokens > 0:
+            # the last T context tokens are the IP-Adapter's (attention.py:354-358); the split copies are made once per
+            # context tensor and shared by every cross-attention of the forward
+            t_ipa = self.ipa_num_tokens
+            if nk <= t_ipa:
+                raise ValueError(f"context has {nk} tokens, not more than ipa_num_tokens = {t_ipa}")
+            split = getattr(ctx2d, "_cb_ipa_split", None)
+            if split is None or split[0] != t_ipa:
+                c3 = ctx2d.view(batch, nk, -1)
+                split = (t_ipa, c3[:, :nk - t_ipa].reshape(batch * (nk - t_ipa), -1).contiguous(),
+                         c3[:, nk - t_ipa:].reshape(batch * t_ipa, -1).contiguous())
+                ctx2d._cb_ipa_split = split
+            _, ctx_text, ctx_ipa = split
+            q = ops.igemm(x2d, p["wq"], inner)
+            kv = ops.igemm(ctx_text, p["wkv"], 2 * inner)
+            kv2 = ops.igemm(ctx_ipa, p["wkv_ipa"], 2 * inner)
+            a = ops.attention(q, kv[:, :inner], kv[:, inner:], batch, h, nq, nk - t_ipa, d, self.scale)
+            a2 = ops.attention(q, kv2[:, :inner], kv2[:, inner:], batch, h, nq, t_ipa, d, self.scale)
+            y = ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
+            return ops.igemm(a2, p["wo_ipa"], self.query_dim, residual=y)
         else:
             q = ops.igemm(x2d, p["wq"], inner)
             kv = ops.igemm(ctx2d, p["wkv"], 2 * inner)
@@ -212,7 +246,7 @@ class BasicTransformerBlock(PackedModule):
                                     context_dim=context_dim if self.disable_self_attn else None, **lk)
         self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff, **lk)
         self.attn2 = CrossAttention(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
-                                    dropout=dropout, **lk)
+                                    dropout=dropout, ipa_scale=ipa_scale, ipa_num_tokens=ipa_num_tokens, **lk)
         self.norm1 = nn.LayerNorm(dim)
         self.norm2 = nn.LayerNorm(dim)
         self.norm3 = nn.LayerNorm(dim)
@@ -279,7 +313,8 @@ class SpatialTransformer(PackedModule, LoraBranches):
         self.transformer_blocks = nn.ModuleList([
             BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim[d],
                                   disable_self_attn=disable_self_attn, checkpoint=use_checkpoint,
-                                  lora_ranks=self.lora_ranks, lora_weights=self.lora_weights)
+                                  lora_ranks=self.lora_ranks, lora_weights=self.lora_weights,
+                                  ipa_scale=ipa_scale, ipa_num_tokens=ipa_num_tokens)
             for d in range(depth)])
         if self.use_linear:
             self.proj_out = nn.Linear(inner_dim, in_channels)

@@ -260,8 +260,6 @@ class UNetModel(PackedModule):
             transformer_depth = len(channel_mult) * [transformer_depth]
         transformer_depth = list(transformer_depth)
         assert len(transformer_depth) == len(channel_mult), "transformer_depth must be an int or one entry per level"
-        if ipa_num_tokens:
-            raise NotImplementedError("cremage_b200: IP-Adapter tokens are not implemented")
         if num_heads_upsample == -1:
             num_heads_upsample = num_heads
         if num_heads == -1:
@@ -300,7 +298,8 @@ class UNetModel(PackedModule):
         def make_st(ch, heads, dim_head, depth, disabled_sa=False):
             return self._ST_CLS(ch, heads, dim_head, depth=depth, context_dim=context_dim,
                                 disable_self_attn=disabled_sa, use_linear=use_linear_in_transformer,
-                                use_checkpoint=use_checkpoint, lora_ranks=lora_ranks, lora_weights=lora_weights)
+                                use_checkpoint=use_checkpoint, lora_ranks=lora_ranks, lora_weights=lora_weights,
+                                ipa_scale=ipa_scale, ipa_num_tokens=ipa_num_tokens)
 
         def head_cfg(ch, heads):
             if num_head_channels == -1:

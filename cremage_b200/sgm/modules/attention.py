@@ -11,11 +11,12 @@ class SpatialTransformer(_LdmSpatialTransformer):
 
     def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0.0, context_dim=None, disable_self_attn=False,
                  use_linear=False, attn_type="softmax", use_checkpoint=True, sdp_backend=None, lora_ranks=None,
-                 lora_weights=None):
+                 lora_weights=None, ipa_scale=1.0, ipa_num_tokens=0):
         if isinstance(context_dim, (list, tuple)) and len(context_dim) != depth:
             context_dim = depth * [context_dim[0]]          # sgm attention.py:951-960
         elif context_dim is not None and not isinstance(context_dim, (list, tuple)):
             context_dim = depth * [context_dim]
         super().__init__(in_channels, n_heads, d_head, depth=depth, dropout=dropout, context_dim=context_dim,
                          disable_self_attn=disable_self_attn, use_linear=use_linear, use_checkpoint=use_checkpoint,
-                         lora_ranks=lora_ranks, lora_weights=lora_weights)
+                         lora_ranks=lora_ranks, lora_weights=lora_weights, ipa_scale=ipa_scale,
+                         ipa_num_tokens=ipa_num_tokens)

@@ -358,9 +358,16 @@ def _resblock(sd: SD, p: str, x: Tensor, emb: Tensor) -> Tensor:
     return x + h
 
 
-def _cross_attention(sd: SD, p: str, x: Tensor, context: Optional[Tensor], heads: int) -> Tensor:
-    """CrossAttentionOriginal.forward, attention.py:611-693 with no LoRA / IP-adapter / mask."""
+def _cross_attention(sd: SD, p: str, x: Tensor, context: Optional[Tensor], heads: int,
+                     ipa: Optional[Tuple[float, int]] = None) -> Tensor:
+    """CrossAttentionOriginal.forward, attention.py:611-693 with no LoRA / mask.  ipa = (ipa_scale, ipa_num_tokens): the
+    IP-Adapter path (:623-627,660-681) -- the last ipa_num_tokens context tokens go through to_k_ipa / to_v_ipa, a second
+    softmax attention with the same queries, and `out + ipa_scale * out_ipa` before to_out."""
     ctx = x if context is None else context
+    ipa_ctx = None
+    if ipa is not None and ipa[1] > 0:
+        end = ctx.shape[1] - ipa[1]
+        ctx, ipa_ctx = ctx[:, :end, :], ctx[:, end:, :]
     q = F.linear(x, sd[p + ".to_q.weight"])
     k = F.linear(ctx, sd[p + ".to_k.weight"])
     v = F.linear(ctx, sd[p + ".to_v.weight"])
@@ -368,18 +375,24 @@ def _cross_attention(sd: SD, p: str, x: Tensor, context: Optional[Tensor], heads
     d = inner // heads
     split = lambda t: t.view(b, -1, heads, d).permute(0, 2, 1, 3).reshape(b * heads, -1, d)
     q, k, v = split(q), split(k), split(v)
+    merge = lambda t: t.view(b, heads, n, d).permute(0, 2, 1, 3).reshape(b, n, inner)
     sim = torch.einsum("b i d, b j d -> b i j", q, k) * (d ** -0.5)
     attn = sim.softmax(dim=-1)
-    out = torch.einsum("b i j, b j d -> b i d", attn, v)
-    out = out.view(b, heads, n, d).permute(0, 2, 1, 3).reshape(b, n, inner)
+    out = merge(torch.einsum("b i j, b j d -> b i d", attn, v))
+    if ipa_ctx is not None:
+        k2 = split(F.linear(ipa_ctx, sd[p + ".to_k_ipa.weight"]))
+        v2 = split(F.linear(ipa_ctx, sd[p + ".to_v_ipa.weight"]))
+        attn2 = (torch.einsum("b i d, b j d -> b i j", q, k2) * (d ** -0.5)).softmax(dim=-1)
+        out = out + ipa[0] * merge(torch.einsum("b i j, b j d -> b i d", attn2, v2))
     return F.linear(out, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
 
 
-def _transformer_block(sd: SD, p: str, x: Tensor, context: Tensor, heads: int) -> Tensor:
+def _transformer_block(sd: SD, p: str, x: Tensor, context: Tensor, heads: int,
+                       ipa: Optional[Tuple[float, int]] = None) -> Tensor:
     """BasicTransformerBlock._forward, attention.py:908-912; FeedForward/GEGLU :88-96,157-168 (exact erf GELU)."""
     ln = lambda t, nm: F.layer_norm(t, (t.shape[-1],), sd[f"{p}.{nm}.weight"], sd[f"{p}.{nm}.bias"], 1e-5)
     x = _cross_attention(sd, p + ".attn1", ln(x, "norm1"), None, heads) + x
-    x = _cross_attention(sd, p + ".attn2", ln(x, "norm2"), context, heads) + x
+    x = _cross_attention(sd, p + ".attn2", ln(x, "norm2"), context, heads, ipa) + x   # only attn2 takes IPA (:895-901)
     y = F.linear(ln(x, "norm3"), sd[p + ".ff.net.0.proj.weight"], sd[p + ".ff.net.0.proj.bias"])
     y, gate = y.chunk(2, dim=-1)
     y = y * F.gelu(gate)
@@ -387,7 +400,8 @@ def _transformer_block(sd: SD, p: str, x: Tensor, context: Tensor, heads: int) -
     return y + x
 
 
-def _spatial_transformer(sd: SD, p: str, x: Tensor, context: Tensor, heads: int, depth: int) -> Tensor:
+def _spatial_transformer(sd: SD, p: str, x: Tensor, context: Tensor, heads: int, depth: int,
+                         ipa: Optional[Tuple[float, int]] = None) -> Tensor:
     """SpatialTransformer.forward, attention.py:1031-1057; Normalize eps 1e-6 (:189); conv proj_in/out."""
     b, c, h, w = x.shape
     x_in = x
@@ -395,15 +409,17 @@ def _spatial_transformer(sd: SD, p: str, x: Tensor, context: Tensor, heads: int,
     x = F.conv2d(x, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
     x = x.permute(0, 2, 3, 1).reshape(b, h * w, -1)
     for d in range(depth):
-        x = _transformer_block(sd, f"{p}.transformer_blocks.{d}", x, context, heads)
+        x = _transformer_block(sd, f"{p}.transformer_blocks.{d}", x, context, heads, ipa)
     x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)
     x = F.conv2d(x, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
     return x + x_in
 
 
 def unet_forward(sd: SD, cfg: UNetConfig, x: Tensor, timesteps: Tensor, context: Tensor,
-                 control: Optional[List[Tensor]] = None, only_mid_control: bool = False) -> Tensor:
-    """UNetModel.forward, openaimodel.py:780-816 (fp32, y=None).  With `control`: ControlledUnetModel.forward,
+                 control: Optional[List[Tensor]] = None, only_mid_control: bool = False,
+                 ipa: Optional[Tuple[float, int]] = None) -> Tensor:
+    """UNetModel.forward, openaimodel.py:780-816 (fp32, y=None).  ipa = (ipa_scale, ipa_num_tokens) as given to the
+    constructor (:479-480), see _cross_attention.  With `control`: ControlledUnetModel.forward,
     cldm/cldm.py:44-70 -- the residuals are popped from the END of the list (a copy here): one after the middle block
     (:59-60), one per output block added to the skip before the concat (:62-66) unless only_mid_control."""
     inp, mid, out = unet_layout(cfg)
@@ -419,7 +435,7 @@ def unet_forward(sd: SD, cfg: UNetConfig, x: Tensor, timesteps: Tensor, context:
             elif kind == "res":
                 h = _resblock(sd, q, h, emb)
             elif kind == "st":
-                h = _spatial_transformer(sd, q, h, context, cfg.num_heads, cfg.transformer_depth)
+                h = _spatial_transformer(sd, q, h, context, cfg.num_heads, cfg.transformer_depth, ipa)
             elif kind == "down":  # Downsample.forward openaimodel.py:162
                 h = F.conv2d(h, sd[q + ".op.weight"], sd[q + ".op.bias"], stride=2, padding=1)
             elif kind == "up":  # Upsample.forward openaimodel.py:113-123
