@@ -722,7 +722,7 @@ int launch_gn_apply(const void* x0, int64_t c0, const void* x1, int64_t c1, int6
   const int CV = int(C / 8);
   static const long long tma_min_bytes = [] {
     const char* e = getenv("CB_GN_TMA_MIN_BYTES");
-    return e ? atoll(e) : (32LL << 20);
+    return e ? atoll(e) : 0LL;   // every tensor with at least four chunks per CTA row takes the ring
   }();
   if (CV <= GN_TMA_THREADS && 2 * n * hw * C >= tma_min_bytes && hw >= 4LL * GN_APPLY_UNROLL * (GN_TMA_THREADS / CV)) {
     const int P = GN_TMA_THREADS / CV;

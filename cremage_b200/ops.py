@@ -211,13 +211,13 @@ GEGLU_BN = int(_os.environ.get("CB_GEGLU_BN", "256"))   # N tile of the fused GE
 
 
 # GroupNorm statistics fused into the producing launch's epilogue; the GroupNorm is then a fold of the partials + ONE
-# streaming pass (one read + one write per element).  Pays for tensors that do not stay in the 126 MB L2 between
-# producer and GroupNorm (the VAE decoder's 128^2..512^2 levels, hires / SDXL top levels at large batch): measured
-# 2.5 -> 4.7 TB/s there; for L2-resident tensors the single-pass cluster kernel is as fast (UNet step unchanged
-# either way, profiles/r1_groupnorm_fused_stats.md), so small outputs keep it.
+# streaming pass (one read + one write per element) through a bulk-copy shared-memory ring.  Decides the VAE decoder
+# (tensors far beyond the 126 MB L2: 2.5 -> 5.0-5.7 TB/s); for the UNet's L2-resident tensors it is a small but repeatable
+# gain over the single-pass cluster kernel (batch 16 step 19.54 -> 19.32 ms, three back-to-back pairs; equal at batch 2),
+# profiles/r1_groupnorm_fused_stats.md -- so every qualifying producer fuses.  Tuning / A-B knobs:
 GN_FUSE = int(_os.environ.get("CB_GN_FUSE", "1"))
 GN_FUSE_MIN_K_CHUNKS = int(_os.environ.get("CB_GN_FUSE_MIN_K_CHUNKS", "1"))
-GN_FUSE_MIN_BYTES = int(_os.environ.get("CB_GN_FUSE_MIN_BYTES", str(64 << 20)))
+GN_FUSE_MIN_BYTES = int(_os.environ.get("CB_GN_FUSE_MIN_BYTES", "0"))
 
 
 TAPS_1X1 = ([0], [0], [0])
@@ -433,21 +433,23 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     c0 = x0.shape[-1]
     c1 = 0 if x1 is None else x1.shape[-1]
     out = torch.empty((*x0.shape[:-1], c0 + c1), dtype=ACT, device=x0.device)
-    ws = int(_lib.load().cb_groupnorm_workspace_bytes(c0 + c1, n, hw, groups))
-    if ws <= 0:
-        raise ValueError(f"groupnorm: unsupported shape n={n} hw={hw} c={c0 + c1} groups={groups}")
-    stats = torch.empty((ws // 4,), dtype=torch.float32, device=x0.device)
     part0 = getattr(x0, "_gn_part", None)
     part1 = getattr(x1, "_gn_part", None) if x1 is not None else None
     if (part0 is not None and (x1 is None or part1 is not None) and ((c0 + c1) // groups) % 2 == 0 and n <= 65535
             and c0 + c1 <= 2560 and groups <= 64):
-        # statistics came with the producers' epilogues: fold + one streaming pass
-        stats = torch.empty((n * 32 * (c0 + c1),), dtype=torch.float32, device=x0.device)
+        # statistics came with the producers' epilogues: fold + one streaming pass; the workspace holds the partial
+        # tables reduced to <= 32 rows per image (only written when a producer has more than 32 tiles per image)
+        need = max(int(part0.shape[1]), 0 if part1 is None else int(part1.shape[1])) > 32
+        stats = torch.empty((n * 32 * (c0 + c1) if need else 1,), dtype=torch.float32, device=x0.device)
         _launch("cb_groupnorm_from_partials", lambda: _lib.load().cb_groupnorm_from_partials(
             _p(x0), c0, _p(part0), part0.shape[1], _p(x1), c1, _p(part1), 0 if part1 is None else part1.shape[1], n, hw,
             groups, eps, _p(gamma), _p(beta), int(silu), _p(out), _p(stats), _stream()),
             nbytes=4.0 * n * hw * (c0 + c1), tag=f"n={n} hw={hw} c={c0}+{c1}")
         return out
+    ws = int(_lib.load().cb_groupnorm_workspace_bytes(c0 + c1, n, hw, groups))
+    if ws <= 0:
+        raise ValueError(f"groupnorm: unsupported shape n={n} hw={hw} c={c0 + c1} groups={groups}")
+    stats = torch.empty((ws // 4,), dtype=torch.float32, device=x0.device)
     _launch("cb_groupnorm_nhwc", lambda: _lib.load().cb_groupnorm_nhwc(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(gamma), _p(beta), int(silu),
                                         _p(out), _p(stats), _stream()),
             nbytes=4.0 * n * hw * (c0 + c1),  # algorithmic: one bf16 read + one bf16 write per element

@@ -25,8 +25,9 @@ def timed(fn, k):
 def main():
     pipe = bench.build_pipeline()
     unet, vae = pipe.model.diffusion_model, pipe.first_stage_model
-    pa, pkw = bench.unet_probe_inputs("ddim50_b8")
-    z = torch.randn(8, 4, 64, 64, device="cuda")
+    wl = next((a for a in sys.argv[1:] if a in bench.WORKLOADS), "ddim50_b8")   # e.g. euler20_b1: UNet batch 2
+    pa, pkw = bench.unet_probe_inputs(wl)
+    z = torch.randn(bench.WORKLOADS[wl][0], 4, 64, 64, device="cuda")
     if "--quick" in sys.argv:   # under ncu: capture + two replays, nothing else
         with torch.no_grad():
             for _ in range(4):
@@ -40,7 +41,7 @@ def main():
         u = min(timed(lambda: unet(*pa, **pkw), 20) for _ in range(3))
         v = min(timed(lambda: vae.decode(z), 5) for _ in range(2))
     tag = " ".join(f"{k}={v}" for k, v in sorted(os.environ.items()) if k.startswith("CB_"))
-    print(f"[{tag or 'defaults'}] unet step {u:.3f} ms | vae decode b8 {v:.3f} ms")
+    print(f"[{tag or 'defaults'}] {wl}: unet step {u:.3f} ms | vae decode {v:.3f} ms")
 
 
 if __name__ == "__main__":
