@@ -25,7 +25,9 @@ class DiffusionWrapper(nn.Module):
             raise NotImplementedError("cremage_b200: only 'crossattn' conditioning is on the SD1.5 path")
 
     def forward(self, x, t, c_concat: list = None, c_crossattn: list = None):
-        cc = torch.cat(c_crossattn, 1)
+        # (a one-element list is passed through as is: torch.cat would hand the UNet a fresh copy every step and defeat
+        # its per-context K/V cache; the values are the same)
+        cc = c_crossattn[0] if len(c_crossattn) == 1 else torch.cat(c_crossattn, 1)
         return self.diffusion_model(x, t, context=cc)
 
 

@@ -186,32 +186,46 @@ class CrossAttention(PackedModule, LoraBranches):
             nk = nq
             qkv = ops.igemm(x2d, p["wqkv"], 3 * inner)             # [M, q | k | v]: read in place by the attention kernel
             q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
-        elif self.ipa_num_tokens > 0:
-            # the last T context tokens are the IP-Adapter's (attention.py:354-358); the split copies are made once per
-            # context tensor and shared by every cross-attention of the forward
-            t_ipa = self.ipa_num_tokens
-            if nk <= t_ipa:
-                raise ValueError(f"context has {nk} tokens, not more than ipa_num_tokens = {t_ipa}")
-            split = getattr(ctx2d, "_cb_ipa_split", None)
-            if split is None or split[0] != t_ipa:
-                c3 = ctx2d.view(batch, nk, -1)
-                split = (t_ipa, c3[:, :nk - t_ipa].reshape(batch * (nk - t_ipa), -1).contiguous(),
-                         c3[:, nk - t_ipa:].reshape(batch * t_ipa, -1).contiguous())
-                ctx2d._cb_ipa_split = split
-            _, ctx_text, ctx_ipa = split
-            q = ops.igemm(x2d, p["wq"], inner)
-            kv = ops.igemm(ctx_text, p["wkv"], 2 * inner)
-            kv2 = ops.igemm(ctx_ipa, p["wkv_ipa"], 2 * inner)
-            a = ops.attention(q, kv[:, :inner], kv[:, inner:], batch, h, nq, nk - t_ipa, d, self.scale)
-            a2 = ops.attention(q, kv2[:, :inner], kv2[:, inner:], batch, h, nq, t_ipa, d, self.scale)
-            y = ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
-            return ops.igemm(a2, p["wo_ipa"], self.query_dim, residual=y)
         else:
+            pre = getattr(ctx2d, "_cb_kv", None)      # K/V of this context cached by the UNet across sampler steps
+            kvs = pre.get(id(self)) if pre is not None else None
+            if kvs is None:
+                kvs = self.compute_kv(ctx2d, batch, nk)
             q = ops.igemm(x2d, p["wq"], inner)
-            kv = ops.igemm(ctx2d, p["wkv"], 2 * inner)
+            if self.ipa_num_tokens > 0:
+                t_ipa = self.ipa_num_tokens
+                kv, kv2 = kvs
+                a = ops.attention(q, kv[:, :inner], kv[:, inner:], batch, h, nq, nk - t_ipa, d, self.scale)
+                a2 = ops.attention(q, kv2[:, :inner], kv2[:, inner:], batch, h, nq, t_ipa, d, self.scale)
+                y = ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
+                return ops.igemm(a2, p["wo_ipa"], self.query_dim, residual=y)
+            kv = kvs[0]
             k, v = kv[:, :inner], kv[:, inner:]
         a = ops.attention(q, k, v, batch, h, nq, nk, d, self.scale)
         return ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
+
+    def compute_kv(self, ctx2d: torch.Tensor, batch: int, nk: int, out=None):
+        """K | V projections of the context: ([batch*nk, 2*inner],) -- with IP-Adapter tokens ([batch*(nk-T), 2*inner],
+        [batch*T, 2*inner]) from to_k/to_v and to_k_ipa/to_v_ipa.  They depend on the context and the weights only, so the
+        UNet computes them once per context and reuses them for every sampler step (`out`: buffers to overwrite)."""
+        p = self.packed(ctx2d.device)
+        inner = self.inner_dim
+        if self.ipa_num_tokens == 0:
+            return (ops.igemm(ctx2d, p["wkv"], 2 * inner, out=None if out is None else out[0]),)
+        # the last T context tokens are the IP-Adapter's (attention.py:354-358); the split copies are made once per
+        # context tensor and shared by every cross-attention of the forward
+        t_ipa = self.ipa_num_tokens
+        if nk <= t_ipa:
+            raise ValueError(f"context has {nk} tokens, not more than ipa_num_tokens = {t_ipa}")
+        split = getattr(ctx2d, "_cb_ipa_split", None)
+        if split is None or split[0] != t_ipa:
+            c3 = ctx2d.view(batch, nk, -1)
+            split = (t_ipa, c3[:, :nk - t_ipa].reshape(batch * (nk - t_ipa), -1).contiguous(),
+                     c3[:, nk - t_ipa:].reshape(batch * t_ipa, -1).contiguous())
+            ctx2d._cb_ipa_split = split
+        _, ctx_text, ctx_ipa = split
+        return (ops.igemm(ctx_text, p["wkv"], 2 * inner, out=None if out is None else out[0]),
+                ops.igemm(ctx_ipa, p["wkv_ipa"], 2 * inner, out=None if out is None else out[1]))
 
     def forward(self, x, context=None, mask=None):
         require_cuda(x, "CrossAttention.forward")

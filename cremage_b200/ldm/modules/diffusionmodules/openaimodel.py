@@ -385,6 +385,11 @@ class UNetModel(PackedModule):
         # CUDA-graph replay of the whole forward (one capture per input signature); CREMAGE_B200_GRAPH=0 disables
         self.use_cuda_graph = os.environ.get("CREMAGE_B200_GRAPH", "1") != "0"
         self._graphed = None
+        # cross-attention K/V of the current context (they depend on the context and the weights only): computed once
+        # per context tensor, reused by every sampler step; the replayed graph then holds no K/V projection launches
+        self.use_kv_cache = os.environ.get("CREMAGE_B200_KV_CACHE", "1") != "0"
+        self._kv = None
+        self._graphed_kv = None
 
     # -- packing -------------------------------------------------------------------------------------------------
     def _own_params(self):
@@ -420,8 +425,8 @@ class UNetModel(PackedModule):
         }
 
     # -- forward -------------------------------------------------------------------------------------------------
-    def _forward_impl(self, x: torch.Tensor, t: torch.Tensor, context: torch.Tensor, y: torch.Tensor = None,
-                      control: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+    def _forward_impl(self, x: torch.Tensor, t: torch.Tensor, context: Optional[torch.Tensor], y: torch.Tensor = None,
+                      control: Optional[Sequence[torch.Tensor]] = None, kv: Optional[dict] = None) -> torch.Tensor:
         """control: ControlNet residuals in the order ControlledUnetModel.forward pops them (cldm/cldm.py:59-66):
         control[0] is added to the middle block's output, control[1 + i] to the skip of output block i (NCHW)."""
         dev = x.device
@@ -439,8 +444,11 @@ class UNetModel(PackedModule):
             emb = ops.igemm(l0, p["le2w"], ted, bias=p["le2b"], residual=emb_t)
             semb = ops.silu_add(emb)
         emb_all = ops.igemm(semb, p["embw"], self._emb_total, bias=p["embb"], out_f32=True)
-        nk = context.shape[1]
-        ctx2d = context.reshape(n * nk, context.shape[-1]).to(ACT).contiguous()
+        if kv is not None:      # context already projected (see _kv_for): ctx2d carries the cached K/V of every attn2
+            nk, ctx2d = kv["nk"], kv["ctx2d"]
+        else:
+            nk = context.shape[1]
+            ctx2d = context.reshape(n * nk, context.shape[-1]).to(ACT).contiguous()
 
         h = ops.nchw_to_nhwc(x, c_pad=p["cin_pad"])
         # conv_in through the tensor-core path: the 64-channel TMA box reads channels >= cin_pad as out-of-bounds zeros
@@ -481,13 +489,63 @@ class UNetModel(PackedModule):
         xin = x.contiguous()
         extra = () if y is None else (y.to(device=x.device).contiguous(),)
         if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
-            if self._graphed is None:
-                self._graphed = GraphedCall(self._forward_impl)
-            self.packed(x.device)  # refresh packs (and drop stale graphs) if parameters changed
-            out = self._graphed(xin, t, ctx, *extra)
+            self.packed(x.device)  # refresh packs (and drop stale graphs / cached K/V) if parameters changed
+            if self.use_kv_cache and self._kv_modules() is not None:
+                self._kv_for(ctx)
+                if self._graphed_kv is None:
+                    self._graphed_kv = GraphedCall(self._forward_kv)
+                out = self._graphed_kv(xin, t, *extra)
+            else:
+                if self._graphed is None:
+                    self._graphed = GraphedCall(self._forward_impl)
+                out = self._graphed(xin, t, ctx, *extra)
         else:
             out = self._forward_impl(xin, t, ctx, *extra)
         return out.to(x.dtype)
+
+    # -- cross-attention K/V cache ----------------------------------------------------------------------------------
+    def _forward_kv(self, x, t, *extra):
+        return self._forward_impl(x, t, None, *extra, kv=self._kv)
+
+    def _kv_modules(self):
+        """The cross-attention modules whose K/V depend on the context only, in forward order (None: a configuration
+        where attn1 also reads the context -- disable_self_attn -- keeps the uncached path)."""
+        mods = self.__dict__.get("_cb_kv_mods")
+        if mods is None:
+            from ..attention import BasicTransformerBlock
+            blocks = [m for m in self.modules() if isinstance(m, BasicTransformerBlock)]
+            mods = False if any(b.disable_self_attn for b in blocks) or not blocks else [b.attn2 for b in blocks]
+            self.__dict__["_cb_kv_mods"] = mods
+        return mods or None
+
+    def _kv_for(self, ctx: torch.Tensor) -> dict:
+        """K/V of `ctx` for every attn2.  Valid while the caller passes the SAME tensor object, unmodified (identity +
+        torch's in-place version counter; a strong reference keeps the address from being reused): the samplers hand
+        the same CFG-doubled context to every step.  A new / modified context is re-projected eagerly into the same
+        buffers (their addresses are baked into the captured graph); a new shape gets new buffers and a new graph."""
+        kv = self._kv
+        shape = tuple(ctx.shape)
+        if (kv is not None and kv["ctx"] is ctx and kv["ver"] == ctx._version and kv["shape"] == shape
+                and kv["dtype"] == ctx.dtype):
+            return kv
+        n, nk, cdim = shape
+        mods = self._kv_modules()
+        fresh = ctx.reshape(n * nk, cdim).to(ACT).contiguous()
+        if kv is not None and kv["shape"] == shape and kv["ctx2d"].device == fresh.device:
+            kv["ctx2d"].copy_(fresh)
+            kv["ctx2d"].__dict__.pop("_cb_ipa_split", None)
+            for m, bufs in zip(mods, kv["bufs"]):
+                m.compute_kv(kv["ctx2d"], n, nk, out=bufs)
+        else:
+            ctx2d = fresh.clone() if fresh.data_ptr() == ctx.data_ptr() else fresh   # never alias the caller's tensor
+            bufs = [m.compute_kv(ctx2d, n, nk) for m in mods]
+            ctx2d._cb_kv = {id(m): b for m, b in zip(mods, bufs)}
+            kv = {"ctx2d": ctx2d, "bufs": bufs, "nk": nk, "shape": shape}
+            self._kv = kv
+            if self._graphed_kv is not None:
+                self._graphed_kv.reset()
+        kv["ctx"], kv["ver"], kv["dtype"] = ctx, ctx._version, ctx.dtype
+        return kv
 
     def packed(self, device):
         before = self._cb_packed
@@ -508,9 +566,13 @@ class UNetModel(PackedModule):
     def _reset_graphs(self):
         if self._graphed is not None:
             self._graphed.reset()
+        if self.__dict__.get("_graphed_kv") is not None:
+            self._graphed_kv.reset()
+        self.__dict__["_kv"] = None   # the cached K/V were projected with the old weights
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop("_cb_all_params", None)   # .to() / .half() may replace Parameter objects
+        self.__dict__.pop("_cb_kv_mods", None)
         return super()._apply(fn, *args, **kwargs)
 
     def invalidate_packed(self):

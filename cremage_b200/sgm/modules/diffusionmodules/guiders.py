@@ -18,6 +18,7 @@ class Guider:
 class VanillaCFG(Guider):
     def __init__(self, scale: float):
         self.scale = scale
+        self._cat = {}   # key -> (uc tensor, c tensor, versions, concatenation): the same conditioning every step
 
     def __call__(self, x: torch.Tensor, sigma: torch.Tensor) -> torch.Tensor:
         x_u, x_c = x.chunk(2)
@@ -27,7 +28,14 @@ class VanillaCFG(Guider):
         c_out = dict()
         for k in c:
             if k in ["vector", "crossattn", "concat"]:
-                c_out[k] = torch.cat((uc[k], c[k]), 0)
+                # the conditioning tensors are the same objects on every sampler step: hand the UNet the SAME doubled
+                # tensor each time (values as torch.cat((uc, c), 0) of the reference) so its per-context K/V cache holds
+                hit = self._cat.get(k)
+                if (hit is None or hit[0] is not uc[k] or hit[1] is not c[k]
+                        or hit[2] != (uc[k]._version, c[k]._version)):
+                    hit = (uc[k], c[k], (uc[k]._version, c[k]._version), torch.cat((uc[k], c[k]), 0))
+                    self._cat[k] = hit
+                c_out[k] = hit[3]
             else:
                 assert c[k] == uc[k]
                 c_out[k] = c[k]
