@@ -202,6 +202,21 @@ def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32, splits: Seq
     return best[1], best[2], best[3]
 
 
+def choose_ksplit_single(tiles: int, num_k: int) -> int:
+    """Split-K factor (1, 3 or 9 tap groups) of a single-CTA 3x3 conv launch with few output tiles (small batch: the
+    8x8 / 16x16 levels have 1..4 M tiles), in units of one K block: rounds over the 148 SMs x K blocks per item, plus a
+    per-split cost for the fp32 partials and the reduce launch.  M = 128, N = 1280, K = 11520: 40 tiles stream 180 K
+    blocks each on 40 SMs; three tap groups put 120 CTAs to work on 60 blocks each."""
+    best_ks, best = 1, None
+    if tiles >= NUM_SMS:      # every SM already has a tile: splitting only adds partial traffic and a reduce launch
+        return 1
+    for ks in (1, 3, 9):
+        cost = (-(-tiles * ks // NUM_SMS)) * (num_k / ks) + (8 * ks if ks > 1 else 0)
+        if best is None or cost < best:
+            best_ks, best = ks, cost
+    return best_ks
+
+
 import os as _os
 # CTA pairs for K >= 1152 (the MMA-bound launches); below that the epilogue dominates.  Env overrides are tuning knobs.
 PAIR_MIN_K_CHUNKS = int(_os.environ.get("CB_PAIR_MIN_K_CHUNKS", "18"))
@@ -292,7 +307,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         if mode == EPI_GEGLU:
             pair = bool(GEGLU_PAIR) and m_tiles >= PAIR_MIN_M_TILES
     # split-K (by tap groups) is available to plain 16-bit 3x3 convs; the reduce kernel applies bias / row bias / residual
-    can_split = (pair and mode == EPI_LINEAR and len(taps[0]) == 9 and not out_f32 and act == ACT_NONE and
+    can_split = (mode == EPI_LINEAR and len(taps[0]) == 9 and not out_f32 and act == ACT_NONE and
                  out_scale == 1.0 and cout % 8 == 0 and (out is None or out.shape[-1] % 8 == 0))
     if bn is None:
         if pair:
@@ -304,6 +319,8 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
                 ksplit = auto_ks
         else:
             bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
+            if can_split and ksplit is None and SPLITK_DEFAULT:
+                ksplit = choose_ksplit_single(m_tiles * (-(-ncols // bn)), num_k)
     ksplit = ksplit if (ksplit and can_split) else 1
     gn_part = None
     if (gn_stats and GN_FUSE and ksplit == 1 and mode == EPI_LINEAR and not out_f32 and act == ACT_NONE and out_scale == 1.0

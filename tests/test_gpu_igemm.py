@@ -249,7 +249,8 @@ def test_cta_pair_dual_n_subtiles_equal_single(n, h, w, cin, cout, bn):
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(16, 8, 8, 128, 256), (4, 8, 8, 192, 96), (3, 16, 16, 64, 160), (16, 8, 8, 320, 1280)])
 @pytest.mark.parametrize("what", ["bias", "rowbias", "res"])
-def test_split_k_conv(n, h, w, cin, cout, what):
+@pytest.mark.parametrize("pair", [True, False])
+def test_split_k_conv(n, h, w, cin, cout, what, pair):
     """Split-K by tap groups (fp32 partials + cb_splitk_reduce) for the few-tile / long-K convs of the 8x8 level."""
     ops = _ops()
     x = _rand(n, cin, h, w, seed=5).to(ACT)
@@ -262,10 +263,10 @@ def test_split_k_conv(n, h, w, cin, cout, what):
         kw["residual"] = _rand(n * h * w, cout, seed=9).to(ACT).cuda()
     x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
     wp = ops.pack_weight(wt).cuda()
-    one = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=True, ksplit=1, **kw)
+    one = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=pair, ksplit=1, **kw)
     for ks in (3, 9):
-        split = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=True, ksplit=ks, **kw)
-        again = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=True, ksplit=ks, **kw)
+        split = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=pair, ksplit=ks, **kw)
+        again = ops.igemm(x_nhwc, wp, cout, taps=ops.TAPS_3X3, bias=b, pair=pair, ksplit=ks, **kw)
         torch.cuda.synchronize()
         assert torch.equal(split, again)                                   # deterministic
         assert (split.float() - one.float()).abs().max().item() <= 2e-2   # same sum, different fp32 association
