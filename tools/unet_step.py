@@ -23,11 +23,17 @@ def timed(fn, k):
 
 
 def main():
-    pipe = bench.build_pipeline()
-    unet, vae = pipe.model.diffusion_model, pipe.first_stage_model
     wl = next((a for a in sys.argv[1:] if a in bench.WORKLOADS), "ddim50_b8")   # e.g. euler20_b1: UNet batch 2
+    sdxl = bench.WORKLOADS[wl][1] == "sdxl"
+    if sdxl:
+        pipe = bench.build_sdxl_pipeline()
+        unet, vae = pipe.model.diffusion_model, pipe.first_stage_model
+    else:
+        pipe = bench.build_pipeline()
+        unet, vae = pipe.model.diffusion_model, pipe.first_stage_model
     pa, pkw = bench.unet_probe_inputs(wl)
-    z = torch.randn(bench.WORKLOADS[wl][0], 4, 64, 64, device="cuda")
+    lat = 128 if sdxl else 64
+    z = torch.randn(bench.WORKLOADS[wl][0], 4, lat, lat, device="cuda")
     if "--quick" in sys.argv:   # under ncu: capture + two replays, nothing else
         with torch.no_grad():
             for _ in range(4):
