@@ -13,14 +13,6 @@ CB_DEVINL Vec8 ld_vec8(const act_t* p) {
   v.u[0] = t.x; v.u[1] = t.y; v.u[2] = t.z; v.u[3] = t.w;
   return v;
 }
-// streaming 16-byte load issued where it is written (volatile asm: ptxas keeps all U loads of a chunk in flight
-// instead of re-serialising them to save registers)
-CB_DEVINL Vec8 ld_vec8_stream(const act_t* p) {
-  Vec8 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.u[0]), "=r"(v.u[1]), "=r"(v.u[2]), "=r"(v.u[3]) : "l"(p));
-  return v;
-}
 CB_DEVINL uint4 ld_shared_v4_u(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
