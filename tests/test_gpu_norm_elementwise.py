@@ -198,3 +198,24 @@ def test_groupnorm_from_fused_partials(monkeypatch, n, h, w, c0, c1, silu):
     want = want.permute(0, 2, 3, 1)
     assert (got.float() - want).abs().max().item() < 3e-2
     assert (got.float() - ref.float()).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1", [(2, 128, 128, 128, 0), (2, 64, 64, 256, 128), (1, 96, 80, 64, 0)])
+def test_streaming_groupnorm_is_bit_reproducible(monkeypatch, n, h, w, c0, c1):
+    """The bulk-copy ring of the apply pass re-fills its stages while other warps still compute, and the statistics are
+    folded from per-tile partials: twenty runs must agree bit for bit (a stage re-used too early or an unordered
+    reduction would show up as run-to-run differences), and with the torch fp32 reference."""
+    from cremage_b200 import ops
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_K_CHUNKS", 1)
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_BYTES", 0)
+    x = _rand(n, h, w, 64, seed=31).to(ACT).cuda()
+    a = ops.nhwc(_conv_with_stats(ops, x, 64, c0, 32), n, h, w, c0)
+    b = ops.nhwc(_conv_with_stats(ops, x, 64, c1, 33), n, h, w, c1) if c1 else None
+    c = c0 + c1
+    gamma, beta = _rand(c, seed=2, scale=0.2, shift=1.0).cuda(), _rand(c, seed=3, scale=0.2).cuda()
+    first = ops.groupnorm(a, gamma, beta, 1e-6, True, x1=b)
+    for _ in range(20):
+        assert torch.equal(ops.groupnorm(a, gamma, beta, 1e-6, True, x1=b), first)
+    xa = torch.cat([a, b], dim=-1) if b is not None else a
+    want = F.silu(F.group_norm(xa.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-6)).permute(0, 2, 3, 1)
+    assert (first.float() - want).abs().max().item() < 3e-2
