@@ -41,6 +41,7 @@ class IGemmDesc(C.Structure):
         ("heads_d", C.c_int), ("heads_dpad", C.c_int), ("heads_h", C.c_int), ("heads_tokens", C.c_int),
         ("heads_which_stride", C.c_int64),
         ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int), ("cta_pair", C.c_int), ("nsub", C.c_int), ("ksplit", C.c_int),
+        ("out_w_stride", C.c_int64), ("out_h_stride", C.c_int64), ("out_n_stride", C.c_int64),
         ("gn_partials", C.c_void_p),
     ]
 

@@ -797,10 +797,19 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.pbh = d->th < 32 / p.pbw ? d->th : 32 / p.pbw;
   const size_t staging = (size_t)EPI_WARPS * p.npan * PANEL_BYTES;
 
+  const bool strided_out = d->out_w_stride > 0 || d->out_h_stride > 0 || d->out_n_stride > 0;
+  if (strided_out) {
+    CB_REQUIRE(staged && epi != EPI_GEGLU, "cb_igemm: a strided output pixel grid needs the staged epilogue of a plain launch");
+    CB_REQUIRE(!d->residual && ksplit == 1 && !d->gn_partials, "cb_igemm: a strided output takes no residual / split-K / GroupNorm partials");
+    CB_REQUIRE(d->out_w_stride >= d->cout && d->out_w_stride % 8 == 0 && d->out_h_stride % 8 == 0 && d->out_n_stride % 8 == 0 &&
+               d->out_h_stride >= d->out_w_stride * d->w && d->out_n_stride >= d->out_h_stride * d->h,
+               "cb_igemm: bad output pixel strides");
+  }
   CUtensorMap mapO = mapA0, mapR = mapA0;
   if (staged) {
     uint64_t dims[4] = {(uint64_t)d->cout, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
     uint64_t str[4] = {1, (uint64_t)d->out_ld, (uint64_t)d->out_ld * d->w, (uint64_t)d->out_ld * d->w * d->h};
+    if (strided_out) { str[1] = (uint64_t)d->out_w_stride; str[2] = (uint64_t)d->out_h_stride; str[3] = (uint64_t)d->out_n_stride; }
     uint32_t box[4] = {32, (uint32_t)p.pbw, (uint32_t)p.pbh, (uint32_t)(32 / (p.pbw * p.pbh))};
     int rc = make_tmap_act(&mapO, d->out, 4, dims, str, box, 64);
     if (rc) return rc;

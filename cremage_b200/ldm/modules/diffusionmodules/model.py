@@ -29,15 +29,15 @@ class Upsample(PackedModule):
     def _pack(self, device):
         if not self.with_conv:
             return {}
-        return {"w": packw(self.conv.weight, device), "b": f32(self.conv.bias, device)}
+        w = self.conv.weight.detach().to(device=device, dtype=torch.float32)
+        return {"w4": ops.pack_weight_up2x(w), "b": f32(self.conv.bias, device)}
 
     def _run(self, x):
         p = self.packed(x.device)
-        up = ops.upsample2x(x)
         if not self.with_conv:
-            return up
-        n, h, w, c = up.shape
-        return ops.nhwc(ops.igemm(up, p["w"], c, taps=ops.TAPS_3X3, bias=p["b"], gn_stats=True), n, h, w, c)
+            return ops.upsample2x(x)
+        # nearest 2x + conv3x3 folded into four 2x2 convs over the low-resolution tensor (ops.conv3x3_up2x)
+        return ops.conv3x3_up2x(x, p["w4"], x.shape[-1], p["b"])
 
     def forward(self, x):
         require_cuda(x, "Upsample.forward")

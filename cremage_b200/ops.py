@@ -278,11 +278,14 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           mode: int = EPI_LINEAR, out: Optional[torch.Tensor] = None, out_f32: bool = False, out_ld: Optional[int] = None,
           out_scale: float = 1.0, heads: Optional[Tuple[int, int, int, int, int]] = None, bn: Optional[int] = None,
           stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None, nsub: int = 0,
-          ksplit: Optional[int] = None, gn_stats: bool = False) -> torch.Tensor:
+          ksplit: Optional[int] = None, gn_stats: bool = False,
+          out_pixel_strides: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
     heads: (d, dpad, n_heads, tokens_per_batch, which_stride) for EPI_HEADS (then `out` must be given).
+    out_pixel_strides: (w, h, n) element strides of the output pixel grid inside a larger NHWC tensor (`out` = a strided
+    view's first element; staged epilogue, no residual) -- used by `conv3x3_up2x`.
     gn_stats: the output feeds a GroupNorm -- when the launch qualifies (see `_gn_fusable`) its epilogue also writes
     per-block partial statistics, attached to the returned tensor as `_gn_part` for `groupnorm` to pick up.
     """
@@ -321,6 +324,8 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
             bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
             if can_split and ksplit is None and SPLITK_DEFAULT:
                 ksplit = choose_ksplit_single(m_tiles * (-(-ncols // bn)), num_k)
+    if out_pixel_strides is not None:
+        can_split = False
     ksplit = ksplit if (ksplit and can_split) else 1
     gn_part = None
     if (gn_stats and GN_FUSE and ksplit == 1 and mode == EPI_LINEAR and not out_f32 and act == ACT_NONE and out_scale == 1.0
@@ -367,6 +372,10 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
     d.bn, d.stages, d.epilogue, d.cta_pair, d.nsub, d.ksplit = bn, stages, epilogue, int(bool(pair)), nsub, ksplit
     d.gn_partials = _p(gn_part)
+    if out_pixel_strides is not None:
+        assert ksplit == 1 and gn_part is None and residual is None and mode == EPI_LINEAR and not out_f32
+        d.out_w_stride, d.out_h_stride, d.out_n_stride = (int(v) for v in out_pixel_strides)
+        d.epilogue = 2   # CB_EPILOGUE_STAGED: the strides live in the TMA-store tensor map
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
             flops=2.0 * rows * len(dw) * (c0 + c1) * ncols,
@@ -382,6 +391,44 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
             nbytes=4.0 * ksplit * rows * cout + 2.0 * rows * cout)
     if gn_part is not None:
         out._gn_part = gn_part
+    return out
+
+
+# nearest-2x upsample + conv3x3 (pad 1) folded: output pixel (2y+a, 2x+b) only sees the 2x2 low-resolution pixels
+# y + DY[a], x + DX[b], and every original tap (ky, kx) that lands on the same low-resolution pixel adds its weight:
+# four 2x2 convs over the LOW-resolution tensor, 16 instead of 36 multiply-adds per input pixel and channel pair, and
+# the 4x larger upsampled tensor never exists (reference: F.interpolate(scale_factor=2, mode="nearest") + conv,
+# openaimodel.py:113-123, model.py:60-64).
+_UP2X_ROWS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}   # parity -> ((low-res offset, original taps), ...)
+
+
+def pack_weight_up2x(w: torch.Tensor):
+    """OIHW 3x3 weight -> [(a, b, packed 2x2 weight, taps)] for the four output parity classes."""
+    assert w.dim() == 4 and w.shape[2:] == (3, 3)
+    w = w.detach().float()
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            k = torch.zeros(w.shape[0], w.shape[1], 2, 2, dtype=torch.float32, device=w.device)
+            dws, dhs = [], []
+            for iy, (dy, kys) in enumerate(_UP2X_ROWS[a]):
+                for ix, (dx, kxs) in enumerate(_UP2X_ROWS[b]):
+                    k[:, :, iy, ix] = sum(w[:, :, ky, kx] for ky in kys for kx in kxs)
+                    dws.append(dx)
+                    dhs.append(dy)
+            out.append((a, b, pack_weight(k), (dws, dhs, [0, 0, 0, 0])))
+    return out
+
+
+def conv3x3_up2x(x: torch.Tensor, packed, cout: int, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """conv3x3(nearest_upsample_2x(x)) for NHWC 16-bit x [N,H,W,C] -> [N,2H,2W,cout] by four 2x2 convs over x, each
+    writing its parity class of the output through a strided TMA-store tensor map."""
+    n, h, w, _ = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, cout), dtype=ACT, device=x.device)
+    for a, b, wp, taps in packed:
+        view = out[:, a::2, b::2, :]
+        igemm(x, wp, cout, taps=taps, bias=bias, out=view, out_ld=cout,
+              out_pixel_strides=(view.stride(2), view.stride(1), view.stride(0)))
     return out
 
 

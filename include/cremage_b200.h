@@ -89,6 +89,11 @@ typedef struct cb_igemm_desc {
   int nsub;              /* pair mode: 0 = auto (two N tiles share each A stage when 3 * bn <= 512), 1 = never */
   int ksplit;            /* > 1: split K by tap groups; `out` must be an fp32 workspace [ksplit][rows][out_ld], no
                           * bias / rowbias / residual / activation here -- cb_splitk_reduce applies them */
+  int64_t out_w_stride, out_h_stride, out_n_stride; /* optional (0 = dense rows of out_ld): element strides of the
+                          * output pixel grid -- row (n, h, w) is written at out + n*out_n_stride + h*out_h_stride +
+                          * w*out_w_stride.  Lets one launch fill every other pixel of a larger NHWC tensor (the four parity
+                          * classes of a nearest-2x-upsample + conv3x3 folded into 2x2 convs).  Staged epilogue only
+                          * (epilogue = CB_EPILOGUE_STAGED), no residual, 16-bit output, strides multiples of 8 elements. */
   float* gn_partials;    /* optional: fused GroupNorm statistics of the (16-bit rounded) output for a following
                           * cb_groupnorm_from_partials: fp32 [n][cb_gn_partial_blocks(h, w, tw, th)][2][cout/2], per M tile of
                           * the image and channel pair the sum and the sum of squares; plain 16-bit epilogues only

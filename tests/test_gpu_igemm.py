@@ -293,3 +293,22 @@ def test_conv3x3_tiny_cin_by_channel_oob_fill(n, h, w, cin, cout):
     torch.cuda.synchronize()
     want = F.conv2d(x.float(), wt.to(ACT).float(), b, padding=1)
     _close(out.view(n, h, w, cout).permute(0, 3, 1, 2), want)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 8, 8, 64, 64), (1, 16, 16, 128, 96), (2, 32, 32, 64, 128), (1, 12, 20, 64, 64), (3, 16, 16, 320, 320)])
+def test_conv3x3_after_nearest_upsample_folded(n, h, w, cin, cout):
+    """conv3x3(F.interpolate(x, 2, 'nearest')) as four 2x2 convs over the low-resolution tensor, each writing its output
+    parity class through a strided TMA-store map (openaimodel.py:113-123, model.py:60-64)."""
+    ops = _ops()
+    x = _rand(n, cin, h, w, seed=5).to(ACT)
+    wt = _rand(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=6)
+    b = _rand(cout, seed=7)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    out = ops.conv3x3_up2x(x_nhwc, ops.pack_weight_up2x(wt.cuda()), cout, b.cuda())
+    torch.cuda.synchronize()
+    assert out.shape == (n, 2 * h, 2 * w, cout)
+    want = F.conv2d(F.interpolate(x.float(), scale_factor=2, mode="nearest"), wt, b, padding=1)
+    _close(out.permute(0, 3, 1, 2), want)
+    # and against the unfolded form on the same kernels (upsample2x + conv3x3): only the weight rounding differs
+    ref = ops.igemm(ops.upsample2x(x_nhwc), ops.pack_weight(wt).cuda(), cout, taps=ops.TAPS_3X3, bias=b.cuda())
+    _close(out.view(-1, cout), ref)
