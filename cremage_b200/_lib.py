@@ -43,6 +43,7 @@ class IGemmDesc(C.Structure):
         ("bn", C.c_int), ("stages", C.c_int), ("epilogue", C.c_int), ("cta_pair", C.c_int), ("nsub", C.c_int), ("ksplit", C.c_int),
         ("out_w_stride", C.c_int64), ("out_h_stride", C.c_int64), ("out_n_stride", C.c_int64),
         ("gn_partials", C.c_void_p),
+        ("gn_rows_per_image", C.c_int64), ("gn_row_offset", C.c_int64),
     ]
 
 

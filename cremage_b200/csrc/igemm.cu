@@ -75,7 +75,7 @@ struct IGemmKParams {
   // fused GroupNorm statistics of the OUTPUT (16-bit rounded values): per (image, M tile) and channel pair, the sum
   // and the sum of squares -> gn_part[n][gn_bpi][2][cout/2], gn_bpi = tiles_w * tiles_h (M tiles per image)
   float* gn_part;
-  int gn_bpi;
+  int gn_bpi, gn_row0;   // rows per image of the table, first row of this launch
 };
 
 // ---- fused GroupNorm statistics -----------------------------------------------------------------------------------
@@ -116,7 +116,7 @@ CB_DEVINL void gn_flush_tile(const IGemmKParams& p, const float* __restrict__ ta
       if (img >= p.n_img) break;
       float t = s[(im * qpi) * 32];
       for (int q = 1; q < qpi; ++q) t += s[(im * qpi + q) * 32];
-      p.gn_part[((static_cast<long long>(img) * p.gn_bpi + tile_row) * 2 + (lane >> 4)) * (p.cout >> 1) + pair] = t;
+      p.gn_part[((static_cast<long long>(img) * p.gn_bpi + p.gn_row0 + tile_row) * 2 + (lane >> 4)) * (p.cout >> 1) + pair] = t;
     }
   }
 }
@@ -778,6 +778,11 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     CB_REQUIRE((d->tw * d->th) % 32 == 0, "cb_igemm: GroupNorm partials need tw * th %% 32 == 0 (a warp's 32 rows inside one image)");
     p.gn_part = d->gn_partials;
     p.gn_bpi = p.tiles_w * p.tiles_h;
+    if (d->gn_rows_per_image > 0) {
+      CB_REQUIRE(d->gn_row_offset >= 0 && d->gn_row_offset + p.gn_bpi <= d->gn_rows_per_image, "cb_igemm: GroupNorm partial rows out of range");
+      p.gn_row0 = (int)d->gn_row_offset;
+      p.gn_bpi = (int)d->gn_rows_per_image;
+    }
   }
 
   // staged (TMA in / TMA out) epilogue: the small-K launches whose run time IS the epilogue; large-K convs keep the
@@ -800,7 +805,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   const bool strided_out = d->out_w_stride > 0 || d->out_h_stride > 0 || d->out_n_stride > 0;
   if (strided_out) {
     CB_REQUIRE(staged && epi != EPI_GEGLU, "cb_igemm: a strided output pixel grid needs the staged epilogue of a plain launch");
-    CB_REQUIRE(!d->residual && ksplit == 1 && !d->gn_partials, "cb_igemm: a strided output takes no residual / split-K / GroupNorm partials");
+    CB_REQUIRE(!d->residual && ksplit == 1, "cb_igemm: a strided output takes no residual / split-K");
     CB_REQUIRE(d->out_w_stride >= d->cout && d->out_w_stride % 8 == 0 && d->out_h_stride % 8 == 0 && d->out_n_stride % 8 == 0 &&
                d->out_h_stride >= d->out_w_stride * d->w && d->out_n_stride >= d->out_h_stride * d->h,
                "cb_igemm: bad output pixel strides");

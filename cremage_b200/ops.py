@@ -279,13 +279,15 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           out_scale: float = 1.0, heads: Optional[Tuple[int, int, int, int, int]] = None, bn: Optional[int] = None,
           stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None, nsub: int = 0,
           ksplit: Optional[int] = None, gn_stats: bool = False,
-          out_pixel_strides: Optional[Tuple[int, int, int]] = None) -> torch.Tensor:
+          out_pixel_strides: Optional[Tuple[int, int, int]] = None,
+          gn_table: Optional[Tuple[torch.Tensor, int]] = None) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
     heads: (d, dpad, n_heads, tokens_per_batch, which_stride) for EPI_HEADS (then `out` must be given).
     out_pixel_strides: (w, h, n) element strides of the output pixel grid inside a larger NHWC tensor (`out` = a strided
     view's first element; staged epilogue, no residual) -- used by `conv3x3_up2x`.
+    gn_table: (shared partial table [n, rows, 2, cout/2], first row of this launch) -- see conv3x3_up2x.
     gn_stats: the output feeds a GroupNorm -- when the launch qualifies (see `_gn_fusable`) its epilogue also writes
     per-block partial statistics, attached to the returned tensor as `_gn_part` for `groupnorm` to pick up.
     """
@@ -372,6 +374,9 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
     d.bn, d.stages, d.epilogue, d.cta_pair, d.nsub, d.ksplit = bn, stages, epilogue, int(bool(pair)), nsub, ksplit
     d.gn_partials = _p(gn_part)
+    if gn_table is not None:
+        assert gn_part is None and ksplit == 1 and (tw * th) % 32 == 0
+        d.gn_partials, d.gn_rows_per_image, d.gn_row_offset = _p(gn_table[0]), gn_table[0].shape[1], gn_table[1]
     if out_pixel_strides is not None:
         assert ksplit == 1 and gn_part is None and residual is None and mode == EPI_LINEAR and not out_f32
         d.out_w_stride, d.out_h_stride, d.out_n_stride = (int(v) for v in out_pixel_strides)
@@ -425,10 +430,19 @@ def conv3x3_up2x(x: torch.Tensor, packed, cout: int, bias: Optional[torch.Tensor
     writing its parity class of the output through a strided TMA-store tensor map."""
     n, h, w, _ = x.shape
     out = torch.empty((n, 2 * h, 2 * w, cout), dtype=ACT, device=x.device)
-    for a, b, wp, taps in packed:
+    # fused GroupNorm statistics: the four launches fill disjoint row ranges of ONE partial table of the output
+    tw, th, _ = choose_tile(n, h, w)
+    bpi = (-(-w // tw)) * (-(-h // th))
+    table = None
+    if GN_FUSE and cout % 8 == 0 and (tw * th) % 32 == 0 and 2 * out.numel() >= GN_FUSE_MIN_BYTES:
+        table = torch.empty((n, 4 * bpi, 2, cout // 2), dtype=torch.float32, device=x.device)
+    for i, (a, b, wp, taps) in enumerate(packed):
         view = out[:, a::2, b::2, :]
         igemm(x, wp, cout, taps=taps, bias=bias, out=view, out_ld=cout,
-              out_pixel_strides=(view.stride(2), view.stride(1), view.stride(0)))
+              out_pixel_strides=(view.stride(2), view.stride(1), view.stride(0)),
+              gn_table=None if table is None else (table, i * bpi))
+    if table is not None:
+        out._gn_part = table
     return out
 
 

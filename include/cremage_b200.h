@@ -98,6 +98,9 @@ typedef struct cb_igemm_desc {
                           * cb_groupnorm_from_partials: fp32 [n][cb_gn_partial_blocks(h, w, tw, th)][2][cout/2], per M tile of
                           * the image and channel pair the sum and the sum of squares; plain 16-bit epilogues only
                           * (bias / rowbias / residual), ksplit <= 1, tw * th % 32 == 0.  Every entry is written. */
+  int64_t gn_rows_per_image, gn_row_offset; /* optional: this launch fills rows [gn_row_offset, + its own M tiles per image)
+                          * of a table with gn_rows_per_image rows per image (0 = a table of its own): the four parity
+                          * launches of a folded upsample conv share one table */
 } cb_igemm_desc;
 
 int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);

@@ -219,3 +219,27 @@ def test_streaming_groupnorm_is_bit_reproducible(monkeypatch, n, h, w, c0, c1):
     xa = torch.cat([a, b], dim=-1) if b is not None else a
     want = F.silu(F.group_norm(xa.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-6)).permute(0, 2, 3, 1)
     assert (first.float() - want).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 128), (1, 32, 32, 128, 64), (3, 8, 8, 64, 320)])
+def test_groupnorm_after_folded_upsample_conv_uses_the_shared_partial_table(monkeypatch, n, h, w, cin, cout):
+    """The four parity launches of conv3x3_up2x fill disjoint row ranges of one GroupNorm partial table."""
+    from cremage_b200 import ops
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_BYTES", 0)
+    x = _rand(n, h, w, cin, seed=41).to(ACT).cuda()
+    wt = _rand(cout, cin, 3, 3, seed=42, scale=(9 * cin) ** -0.5)
+    b = _rand(cout, seed=43, scale=0.5)
+    y = ops.conv3x3_up2x(x, ops.pack_weight_up2x(wt.cuda()), cout, b.cuda())
+    part = getattr(y, "_gn_part", None)
+    assert part is not None and part.shape[0] == n and part.shape[1] % 4 == 0
+    o = y.float().view(n, 4 * h * w, cout // 2, 2)
+    got = part.double().sum(dim=1)
+    assert (got[:, 0].float() - o.sum(dim=(1, 3))).abs().max().item() <= 1e-4 * max(1.0, o.sum(dim=(1, 3)).abs().max().item())
+    assert (got[:, 1].float() - (o * o).sum(dim=(1, 3))).abs().max().item() <= 1e-4 * max(1.0, (o * o).sum(dim=(1, 3)).abs().max().item())
+    gamma, beta = _rand(cout, seed=2, scale=0.2, shift=1.0).cuda(), _rand(cout, seed=3, scale=0.2).cuda()
+    prof = ops.LaunchProfile()
+    with prof:
+        out = ops.groupnorm(y, gamma, beta, 1e-5, True)
+    assert any(k[0] == "cb_groupnorm_from_partials" for k in prof.by_shape())
+    want = F.silu(F.group_norm(y.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)).permute(0, 2, 3, 1)
+    assert (out.float() - want).abs().max().item() < 3e-2
