@@ -280,7 +280,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None, nsub: int = 0,
           ksplit: Optional[int] = None, gn_stats: bool = False,
           out_pixel_strides: Optional[Tuple[int, int, int]] = None,
-          gn_table: Optional[Tuple[torch.Tensor, int]] = None) -> torch.Tensor:
+          gn_table: Optional[Tuple[torch.Tensor, int]] = None, algo_flops: Optional[float] = None) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
@@ -383,7 +383,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         d.epilogue = 2   # CB_EPILOGUE_STAGED: the strides live in the TMA-store tensor map
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
-            flops=2.0 * rows * len(dw) * (c0 + c1) * ncols,
+            flops=2.0 * rows * len(dw) * (c0 + c1) * ncols if algo_flops is None else algo_flops,
             tag=f"M={rows} K={len(dw) * (c0 + c1)} N={ncols} taps={len(dw)} bn={bn}{'x2' if pair else ''}{f'/k{ksplit}' if ksplit > 1 else ''} epi={mode}"
                 f"{'+res' if residual is not None else ''}{'+rowb' if rowbias is not None else ''}"
                 f"{'+act' if act else ''}{'+f32' if out_f32 else ''}" if _PROF is not None else "")
@@ -440,7 +440,10 @@ def conv3x3_up2x(x: torch.Tensor, packed, cout: int, bias: Optional[torch.Tensor
         view = out[:, a::2, b::2, :]
         igemm(x, wp, cout, taps=taps, bias=bias, out=view, out_ld=cout,
               out_pixel_strides=(view.stride(2), view.stride(1), view.stride(0)),
-              gn_table=None if table is None else (table, i * bpi))
+              gn_table=None if table is None else (table, i * bpi),
+              # profile bookkeeping: the algorithmic work is the REFERENCE op's (conv3x3 over the 2H x 2W grid,
+              # SURVEY 8d); each of the four launches is credited a quarter of it although it executes 4/9 of that
+              algo_flops=2.0 * (n * h * w) * 9 * x.shape[-1] * cout)
     if table is not None:
         out._gn_part = table
     return out
