@@ -43,9 +43,9 @@ WORKLOADS = {
     "sdxl30_b4": (4, "sdxl", 30),
 }
 CFG_SCALE = 7.5
-# dram__bytes_read.sum + dram__bytes_write.sum summed over the 213 igemm launches of one SD1.5 UNet forward at batch 16
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the 222 igemm launches of one SD1.5 UNet forward at batch 16
 # (the same launches `roofline.achieved` aggregates): ncu --metrics capture profiles/r1_igemm_dram_traffic_unet_b16_v2.csv
-# (9.51 GB read + 1.61 GB written; weights alone are 1.72 GB, every activation is written and read once more by its
+# (9.56 GB read + 1.56 GB written; weights alone are 1.72 GB, every activation is written and read once more by its
 # consumer, the rest is A-tile re-reads that miss the 126 MB L2)
 IGEMM_DRAM_TRAFFIC_NOTE = 11.12e9
 # algorithmic work per image (BASELINE.md section 3, 2*MACs of the reference graph)
