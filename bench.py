@@ -185,6 +185,7 @@ def make_sdxl_runner(eng, workload):
     denoiser = lambda inp, sigma, c: eng.denoiser(eng.model, inp, sigma, c)
 
     def run(inp):
+        smp.guider._cat.clear()   # a new batch is a new prompt: its context is projected to K/V again (once per batch)
         cond = {"crossattn": inp["cond"], "vector": inp["cond_vec"]}
         uc = {"crossattn": inp["uncond"], "vector": inp["uncond_vec"]}
         z = smp(denoiser, inp["x_T"], cond=cond, uc=uc)
