@@ -12,11 +12,15 @@ import os
 
 from . import build as _build
 
-_LIB = None
-# fp16 (the reference's GPU precision, default) or bf16; one precision per process
+_LIBS = {}
+# The library is built once per 16-bit storage type (fp16: the reference's own GPU precision, the default; bf16: fp32's
+# exponent range).  DTYPE is the build the calling code is currently routed to: the process default comes from
+# CREMAGE_B200_DTYPE, `ops.precision("bf16")` switches it for a region (the SDXL first stage, which the reference runs
+# outside fp16 autocast because its activations overflow fp16: sgm/models/diffusion.py:119-137).
 DTYPE = os.environ.get("CREMAGE_B200_DTYPE", "fp16").lower()
 if DTYPE not in _build.DTYPES:
     raise ValueError(f"CREMAGE_B200_DTYPE must be one of {_build.DTYPES}, got {DTYPE!r}")
+DEFAULT_DTYPE = DTYPE
 
 
 class IGemmDesc(C.Structure):
@@ -87,17 +91,20 @@ _RESTYPES = {"cb_last_error": C.c_char_p, "cb_launch_count": C.c_int64, "cb_grou
              "cb_gn_partial_blocks": C.c_int64}
 
 
-def lib_path() -> Path:
-    override = os.environ.get("CREMAGE_B200_LIB")   # A/B comparison of library builds (tools/)
-    return Path(override) if override else _build.lib_path(DTYPE)
+def lib_path(dtype: str = None) -> Path:
+    dtype = DTYPE if dtype is None else dtype
+    override = os.environ.get("CREMAGE_B200_LIB")   # A/B comparison of library builds (tools/); default dtype only
+    return Path(override) if (override and dtype == DEFAULT_DTYPE) else _build.lib_path(dtype)
 
 
-def load() -> C.CDLL:
-    """Load (building first if needed) the CUDA library. Raises if that is impossible."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    path = lib_path()
+def load(dtype: str = None) -> C.CDLL:
+    """Load (building first if needed) the CUDA library of `dtype` (default: the current routing, `DTYPE`).
+    Raises if that is impossible."""
+    dtype = DTYPE if dtype is None else dtype
+    lib = _LIBS.get(dtype)
+    if lib is not None:
+        return lib
+    path = lib_path(dtype)
     if not path.exists():
         _build.build()
     lib = C.CDLL(str(path))
@@ -105,9 +112,9 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.cb_act_dtype() != {"fp16": 1, "bf16": 2}[DTYPE]:
-        raise RuntimeError(f"{path} was not built for {DTYPE}")
-    _LIB = lib
+    if lib.cb_act_dtype() != {"fp16": 1, "bf16": 2}[dtype]:
+        raise RuntimeError(f"{path} was not built for {dtype}")
+    _LIBS[dtype] = lib
     return lib
 
 
@@ -124,4 +131,6 @@ def check(rc: int, what: str) -> None:
 
 
 def launch_count() -> int:
-    return int(load().cb_launch_count())
+    """Kernels launched directly (outside graph replays) by every loaded build of the library."""
+    load()
+    return sum(int(lib.cb_launch_count()) for lib in _LIBS.values())

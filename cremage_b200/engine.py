@@ -9,7 +9,23 @@ import torch.nn as nn
 
 from . import ops
 
-ACT = ops.ACT
+# Bumped whenever ANY PackedModule's parameters may have been replaced (`.to()/.half()/.cuda()/.cpu()` on the module or on
+# a sub-tree, `load_state_dict`).  A root module that owns CUDA graphs over its whole tree compares it on every call: a
+# sub-tree `_apply` (UNetModel.convert_to_fp16 -> blocks.half(), openaimodel.py:758-764) never reaches the root's own
+# `_apply`, and neither `.half()` nor `p.data = ...` bumps `Parameter._version`.
+PACK_EPOCH = 0
+
+
+def _bump_epoch():
+    global PACK_EPOCH
+    PACK_EPOCH += 1
+
+
+def param_fingerprint(params):
+    """(storage address, dtype, version) of every parameter: changes on .to()/.half()/`p.data = ...`/in-place updates
+    through autograd-visible ops.  (An edit through `p.data.<op>_()` is invisible to torch itself: call
+    `invalidate_packed()` after such an edit.)"""
+    return tuple((p.data_ptr(), p.dtype, p._version) for p in params)
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:
@@ -32,10 +48,12 @@ class PackedModule(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         self._cb_packed = None
+        _bump_epoch()
         return super()._apply(fn, *args, **kwargs)
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._cb_packed = None
+        _bump_epoch()
         return super()._load_from_state_dict(*args, **kwargs)
 
     def _pack(self, device: torch.device) -> dict:  # pragma: no cover - overridden
@@ -45,14 +63,25 @@ class PackedModule(nn.Module):
         return list(self.parameters(recurse=True))
 
     def packed(self, device: torch.device) -> dict:
-        key = (str(device),) + tuple(p._version for p in self._own_params())
+        key = (str(device), ops.ACT) + param_fingerprint(self._own_params())
         if self._cb_packed is None or self._cb_key != key:
-            with torch.no_grad():
-                self._cb_packed = self._pack(device)
+            # one pack per 16-bit type: a module used under both builds of the library (ops.precision) keeps both
+            cache = self.__dict__.setdefault("_cb_pack_cache", {})
+            if self._cb_packed is None:
+                cache.clear()
+            hit = cache.get(key)
+            if hit is None:
+                with torch.no_grad():
+                    hit = self._pack(device)
+                for k in [k for k in cache if k[:2] == key[:2]]:
+                    del cache[k]            # same device and dtype, older parameters
+                cache[key] = hit
+            self._cb_packed = hit
             self._cb_key = key
         return self._cb_packed
 
     def invalidate_packed(self):
+        _bump_epoch()
         for m in self.modules():
             if isinstance(m, PackedModule):
                 m._cb_packed = None
@@ -74,12 +103,12 @@ _WORKSPACES: Dict[Tuple, torch.Tensor] = {}
 
 def zero_workspace(tag: str, shape: Tuple[int, ...], device: torch.device, init=None) -> torch.Tensor:
     """Persistent zero-filled buffer; `init(buf)` runs once at creation (e.g. the attention row-sum column)."""
-    key = (tag, tuple(shape), str(device))
+    key = (tag, tuple(shape), str(device), ops.ACT)
     buf = _WORKSPACES.get(key)
     if buf is None:
         if torch.cuda.is_current_stream_capturing():
             raise RuntimeError("workspace allocation during CUDA-graph capture; run one eager call first")
-        buf = torch.zeros(shape, dtype=ACT, device=device)
+        buf = torch.zeros(shape, dtype=ops.ACT, device=device)
         if init is not None:
             init(buf)
         _WORKSPACES[key] = buf
@@ -121,15 +150,16 @@ class GraphedCall:
     """Captures `fn(*tensors)` once per input signature and replays it. Inputs are copied into static buffers, the
     output is a static buffer (cloned on return unless `clone_output=False`)."""
 
-    def __init__(self, fn: Callable, warmup: int = 2, clone_output: bool = True):
+    def __init__(self, fn: Callable, warmup: int = 2, clone_output: bool = True, keepalive: Optional[Callable] = None):
         self.fn = fn
         self.warmup = warmup
         self.clone_output = clone_output
+        self.keepalive = keepalive      # () -> objects the captured kernels read (packed weights): held per graph
         self._graphs: Dict[Tuple, Tuple] = {}
 
     @staticmethod
     def _sig(tensors):
-        return tuple((tuple(t.shape), t.dtype, str(t.device)) for t in tensors)
+        return (ops.ACT,) + tuple((tuple(t.shape), t.dtype, str(t.device)) for t in tensors)
 
     def __call__(self, *tensors: torch.Tensor) -> torch.Tensor:
         sig = self._sig(tensors)
@@ -159,9 +189,11 @@ class GraphedCall:
             finally:
                 if gc_was_enabled:
                     gc.enable()
-            entry = (graph, static_in, static_out, _lib.launch_count() - before)
+            # the graph's kernels hold raw pointers: keep what they read alive for as long as the graph can be replayed
+            held = self.keepalive() if self.keepalive is not None else None
+            entry = (graph, static_in, static_out, _lib.launch_count() - before, held)
             self._graphs[sig] = entry
-        graph, static_in, static_out, n_launches = entry
+        graph, static_in, static_out, n_launches, _held = entry
         for dst, src in zip(static_in, tensors):
             dst.copy_(src)
         graph.replay()

@@ -134,8 +134,11 @@ class DDIMSampler(object):
         sqrt_aprev = float(a_prev.sqrt())
         dir_coef = float((1. - a_prev - sigma_t ** 2).sqrt())
         sig = float(sigma_t)
-        if sig != 0.0 and noise is None:
-            noise = torch.randn_like(x) * temperature
+        if noise is None:
+            # the reference draws noise_like(x.shape) on EVERY step, also when sigma_t == 0 (:597): same RNG consumption
+            noise = torch.randn(x.shape, device=x.device)
+            if temperature != 1.:
+                noise = noise * temperature
         if sig == 0.0:
             noise = None
         if cc is None:

@@ -13,7 +13,8 @@ import torch
 
 from ....k_diffusion.external import CompVisDenoiser
 from ....k_diffusion.sampling import (get_sigmas_karras, sample_dpm_2, sample_dpm_2_ancestral, sample_dpmpp_2m,
-                                         sample_dpmpp_2s_ancestral, sample_euler, sample_euler_ancestral, sample_heun,
+                                         sample_dpmpp_2m_sde, sample_dpmpp_2s_ancestral, sample_dpmpp_3m_sde,
+                                         sample_dpmpp_sde, sample_euler, sample_euler_ancestral, sample_heun,
                                          sample_lms)
 from .ldm_wrapper_for_k_diffusion import LDMWrapperForKDiffusion
 
@@ -172,3 +173,33 @@ class Dpmpp2sAncestralSampler(KDiffusionSamplerBase):
     @torch.no_grad()
     def do_sample(self):
         return sample_dpmpp_2s_ancestral(self.ldm_wrapper_model, self.x, self.sigmas), None
+
+
+class DpmppSdeSampler(KDiffusionSamplerBase):                    # :373-381
+    @torch.no_grad()
+    def compute_sigmas(self, n):
+        return get_sigmas_karras(n, self.sigma_min, self.sigma_max, device=self.device)
+
+    @torch.no_grad()
+    def do_sample(self):
+        return sample_dpmpp_sde(self.ldm_wrapper_model, self.x, self.sigmas), None
+
+
+class Dpmpp2mSdeSampler(KDiffusionSamplerBase):                  # :393-401
+    @torch.no_grad()
+    def compute_sigmas(self, n):
+        return get_sigmas_karras(n, self.sigma_min, self.sigma_max, device=self.device)
+
+    @torch.no_grad()
+    def do_sample(self):
+        return sample_dpmpp_2m_sde(self.ldm_wrapper_model, self.x, self.sigmas), None
+
+
+class Dpmpp3mSdeSampler(KDiffusionSamplerBase):                  # :403-411
+    @torch.no_grad()
+    def compute_sigmas(self, n):
+        return get_sigmas_karras(n, self.sigma_min, self.sigma_max, device=self.device)
+
+    @torch.no_grad()
+    def do_sample(self):
+        return sample_dpmpp_3m_sde(self.ldm_wrapper_model, self.x, self.sigmas), None

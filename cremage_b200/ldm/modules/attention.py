@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
-from ...engine import ACT, PackedModule, f32, packw, require_cuda
+from ...engine import PackedModule, f32, packw, require_cuda
 
 GEGLU_BN = ops.GEGLU_BN  # N tile of the fused GEGLU projection (x / gate rows interleaved per 64 output columns)
 
@@ -126,7 +126,7 @@ class FeedForward(PackedModule, LoraBranches):
     def forward(self, x):
         require_cuda(x, "FeedForward.forward")
         shp = x.shape
-        y = self._run(x.reshape(-1, shp[-1]).to(ACT).contiguous())
+        y = self._run(x.reshape(-1, shp[-1]).to(ops.ACT).contiguous())
         return y.view(*shp[:-1], self.dim_out).to(x.dtype)
 
 
@@ -232,11 +232,11 @@ class CrossAttention(PackedModule, LoraBranches):
         if mask is not None:
             raise NotImplementedError("cremage_b200: attention masks are not used on the SD path")
         b, n, _ = x.shape
-        x2d = x.reshape(b * n, -1).to(ACT).contiguous()
+        x2d = x.reshape(b * n, -1).to(ops.ACT).contiguous()
         ctx2d, nk = None, n
         if context is not None:
             nk = context.shape[1]
-            ctx2d = context.reshape(b * nk, -1).to(ACT).contiguous()
+            ctx2d = context.reshape(b * nk, -1).to(ops.ACT).contiguous()
         elif not self.is_self and self.context_dim != self.query_dim:
             raise ValueError("context is required for this CrossAttention")
         return self._run(x2d, b, n, ctx2d, nk).view(b, n, self.query_dim).to(x.dtype)
@@ -290,11 +290,11 @@ class BasicTransformerBlock(PackedModule):
     def forward(self, x, context=None):
         require_cuda(x, "BasicTransformerBlock.forward")
         b, n, c = x.shape
-        x2d = x.reshape(b * n, c).to(ACT).contiguous()
+        x2d = x.reshape(b * n, c).to(ops.ACT).contiguous()
         ctx2d, nk = None, n
         if context is not None:
             nk = context.shape[1]
-            ctx2d = context.reshape(b * nk, -1).to(ACT).contiguous()
+            ctx2d = context.reshape(b * nk, -1).to(ops.ACT).contiguous()
         return self._run(x2d, b, n, ctx2d, nk).view(b, n, c).to(x.dtype)
 
 
@@ -373,6 +373,6 @@ class SpatialTransformer(PackedModule, LoraBranches):
         ctx2d, nk = None, 0
         if context is not None:
             nk = context.shape[1]
-            ctx2d = context.reshape(-1, context.shape[-1]).to(ACT).contiguous()
+            ctx2d = context.reshape(-1, context.shape[-1]).to(ops.ACT).contiguous()
         y = self._run(ops.nchw_to_nhwc(x), ctx2d, nk)
         return ops.nhwc_to_nchw_f32(y).to(x.dtype)

@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 
 from .... import ops
-from ....engine import ACT, PackedModule, f32, packw, require_cuda
+from ....engine import PackedModule, f32, packw, require_cuda
 
 
 def Normalize(in_channels, num_groups=32):
@@ -145,7 +145,7 @@ class AttnBlock(PackedModule):
         return {"g": f32(self.norm.weight, device), "b": f32(self.norm.bias, device),
                 "wq": packw(self.q.weight, device), "bq": f32(self.q.bias, device),
                 "wk": packw(self.k.weight, device), "bk": f32(self.k.bias, device),
-                "wv_rows": self.v.weight.detach().to(device=device, dtype=torch.float32).reshape(c, c).to(ACT).contiguous(),
+                "wv_rows": self.v.weight.detach().to(device=device, dtype=torch.float32).reshape(c, c).to(ops.ACT).contiguous(),
                 "bv": f32(self.v.bias, device),
                 "wo": packw(self.proj_out.weight, device), "bo": f32(self.proj_out.bias, device)}
 
@@ -158,10 +158,10 @@ class AttnBlock(PackedModule):
         hn = ops.groupnorm(x, p["g"], p["b"], self.norm.eps, silu=False).view(n, npx, c)
         q = ops.igemm(hn.view(n * npx, c), p["wq"], c, bias=p["bq"]).view(n, npx, c)
         k = ops.igemm(hn.view(n * npx, c), p["wk"], c, bias=p["bk"]).view(n, npx, c)
-        o = torch.empty((n, npx, c), dtype=ACT, device=x.device)
+        o = torch.empty((n, npx, c), dtype=ops.ACT, device=x.device)
         s = torch.empty((npx, npx), dtype=torch.float32, device=x.device)
-        pm = torch.empty((npx, npx), dtype=ACT, device=x.device)
-        vt = torch.empty((c, npx), dtype=ACT, device=x.device)
+        pm = torch.empty((npx, npx), dtype=ops.ACT, device=x.device)
+        vt = torch.empty((c, npx), dtype=ops.ACT, device=x.device)
         scale = float(int(c) ** (-0.5))
         for i in range(n):
             ops.igemm(q[i], k[i], npx, out=s)                        # S = q k^T, the "weights" operand is k itself

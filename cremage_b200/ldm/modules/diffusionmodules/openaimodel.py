@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .... import ops
-from ....engine import ACT, GraphedCall, PackedModule, f32, packw, require_cuda
+from ....engine import GraphedCall, PackedModule, f32, packw, require_cuda
 from ..attention import SpatialTransformer
 from .util import conv_nd, linear, normalization, timestep_freqs, zero_module
 
@@ -178,7 +178,7 @@ class ResBlock(TimestepBlock, PackedModule):
 
     def _emb_out(self, emb: torch.Tensor) -> torch.Tensor:
         p = self.packed(emb.device)
-        semb = ops.silu_add(emb.to(ACT).contiguous())
+        semb = ops.silu_add(emb.to(ops.ACT).contiguous())
         return ops.igemm(semb, p["we"], self.out_channels, bias=p["be"], out_f32=True)
 
     def forward(self, x, emb):
@@ -215,7 +215,7 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
         ctx2d, nk = None, 0
         if context is not None:
             nk = context.shape[1]
-            ctx2d = context.reshape(-1, context.shape[-1]).to(ACT).contiguous()
+            ctx2d = context.reshape(-1, context.shape[-1]).to(ops.ACT).contiguous()
         y = self._run(ops.nchw_to_nhwc(x), None, lambda layer: layer._emb_out(emb), ctx2d, nk)
         return ops.nhwc_to_nchw_f32(y).to(x.dtype)
 
@@ -439,7 +439,7 @@ class UNetModel(PackedModule):
             semb = ops.igemm(e, p["te2w"], ted, bias=p["te2b"], act=ops.ACT_SILU)  # silu(emb): every consumer applies SiLU first
         else:  # emb = time_embed(t_emb) + label_emb(y)   (sgm openaimodel.py:851-859), then the shared SiLU
             emb_t = ops.igemm(e, p["te2w"], ted, bias=p["te2b"])
-            l0 = ops.igemm(y.to(ACT).contiguous(), p["le0w"], ted, bias=p["le0b"], act=ops.ACT_SILU)
+            l0 = ops.igemm(y.to(ops.ACT).contiguous(), p["le0w"], ted, bias=p["le0b"], act=ops.ACT_SILU)
             emb = ops.igemm(l0, p["le2w"], ted, bias=p["le2b"], residual=emb_t)
             semb = ops.silu_add(emb)
         emb_all = ops.igemm(semb, p["embw"], self._emb_total, bias=p["embb"], out_f32=True)
@@ -447,7 +447,7 @@ class UNetModel(PackedModule):
             nk, ctx2d = kv["nk"], kv["ctx2d"]
         else:
             nk = context.shape[1]
-            ctx2d = context.reshape(n * nk, context.shape[-1]).to(ACT).contiguous()
+            ctx2d = context.reshape(n * nk, context.shape[-1]).to(ops.ACT).contiguous()
 
         h = ops.nchw_to_nhwc(x, c_pad=p["cin_pad"])
         # conv_in through the tensor-core path: the 64-channel TMA box reads channels >= cin_pad as out-of-bounds zeros
@@ -492,11 +492,11 @@ class UNetModel(PackedModule):
             if self.use_kv_cache and self._kv_modules() is not None:
                 self._kv_for(ctx)
                 if self._graphed_kv is None:
-                    self._graphed_kv = GraphedCall(self._forward_kv)
+                    self._graphed_kv = GraphedCall(self._forward_kv, keepalive=self._graph_keepalive)
                 out = self._graphed_kv(xin, t, *extra)
             else:
                 if self._graphed is None:
-                    self._graphed = GraphedCall(self._forward_impl)
+                    self._graphed = GraphedCall(self._forward_impl, keepalive=self._graph_keepalive)
                 out = self._graphed(xin, t, ctx, *extra)
         else:
             out = self._forward_impl(xin, t, ctx, *extra)
@@ -529,7 +529,7 @@ class UNetModel(PackedModule):
             return kv
         n, nk, cdim = shape
         mods = self._kv_modules()
-        fresh = ctx.reshape(n * nk, cdim).to(ACT).contiguous()
+        fresh = ctx.reshape(n * nk, cdim).to(ops.ACT).contiguous()
         if kv is not None and kv["shape"] == shape and kv["ctx2d"].device == fresh.device:
             kv["ctx2d"].copy_(fresh)
             kv["ctx2d"].__dict__.pop("_cb_ipa_split", None)
@@ -551,16 +551,32 @@ class UNetModel(PackedModule):
         p = super().packed(device)
         # captured graphs hold the packed weight buffers of EVERY sub-module: any in-place parameter update anywhere in
         # the tree (optimiser step, LoRA alpha edit, weight patching) must drop them, not only this module's own packs
+        from .... import engine
+        epoch = engine.PACK_EPOCH
         params = self.__dict__.get("_cb_all_params")
-        if params is None:
+        stale = False
+        if params is None or epoch != self.__dict__.get("_cb_epoch"):
+            # some PackedModule somewhere was moved / cast / reloaded since the last call (possibly a sub-tree of this
+            # model: convert_to_fp16 -> blocks.half() never passes through this module's own _apply): re-list the
+            # parameters and compare where they live
             params = list(self.parameters())
             self.__dict__["_cb_all_params"] = params
+            self.__dict__["_cb_epoch"] = epoch
+            where = tuple((q.data_ptr(), q.dtype) for q in params)
+            stale = where != self.__dict__.get("_cb_all_where")
+            self.__dict__["_cb_all_where"] = where
+            self.__dict__.pop("_cb_kv_mods", None)
         versions = sum(q._version for q in params)
-        stale = versions != self.__dict__.get("_cb_all_versions")
+        stale = stale or versions != self.__dict__.get("_cb_all_versions")
         self.__dict__["_cb_all_versions"] = versions
         if p is not before or stale:
             self._reset_graphs()  # parameters changed: captured graphs hold stale weight buffers
         return p
+
+    def _graph_keepalive(self):
+        """Everything the captured kernels read besides the static inputs: the packed weights of every sub-module and
+        the cached K/V buffers."""
+        return [m._cb_packed for m in self.modules() if isinstance(m, PackedModule)] + [self.__dict__.get("_kv")]
 
     def _reset_graphs(self):
         if self._graphed is not None:
@@ -579,7 +595,7 @@ class UNetModel(PackedModule):
         self._reset_graphs()
 
     def convert_to_fp16(self):
-        """openaimodel.py:758-764. Storage dtype only; the kernels always compute bf16 x bf16 -> fp32."""
+        """openaimodel.py:758-764. Parameter storage dtype only; the kernels always compute 16-bit x 16-bit -> fp32 (ops.ACT)."""
         for blocks in (self.input_blocks, self.middle_block, self.output_blocks):
             blocks.half()
 

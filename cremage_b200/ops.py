@@ -1,7 +1,7 @@
 """Torch-tensor front end of the C ABI (include/cremage_b200.h): argument marshalling only, no arithmetic.
 
 Every function here enqueues hand-written sm_100a kernels on the current CUDA stream through ctypes. Activations are
-NHWC bf16. Weight repacking helpers (pure layout work done once at load time) live here too.
+NHWC 16-bit (`ops.ACT`: fp16 by default, bf16 under CREMAGE_B200_DTYPE=bf16 or `ops.precision("bf16")`). Weight repacking helpers (pure layout work done once at load time) live here too.
 """
 from __future__ import annotations
 
@@ -18,8 +18,35 @@ EPI_LINEAR, EPI_GEGLU, EPI_HEADS = 0, 1, 2
 EPILOGUE_AUTO, EPILOGUE_DIRECT, EPILOGUE_STAGED = 0, 1, 2
 ACT_NONE, ACT_SILU = 0, 1
 
-# 16-bit activation / weight dtype of the loaded library build (fp16 unless CREMAGE_B200_DTYPE=bf16)
-ACT = torch.float16 if _lib.DTYPE == "fp16" else torch.bfloat16
+# 16-bit activation / weight dtype the calls are currently routed to (fp16 unless CREMAGE_B200_DTYPE=bf16); read it as
+# `ops.ACT` at call time -- `precision()` switches it together with the library build for a region.
+_TORCH_DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16}
+ACT = _TORCH_DTYPE[_lib.DTYPE]
+
+
+class precision:
+    """`with ops.precision("bf16"):` routes every call in the region to the bf16 build of the library (and makes
+    `ops.ACT` torch.bfloat16).  Weight packs, workspaces and captured graphs are keyed by the dtype, so a module may be
+    used under both.  Not re-entrant across threads (one Python thread drives the GPU, as in the reference)."""
+
+    def __init__(self, dtype: str):
+        if dtype not in _TORCH_DTYPE:
+            raise ValueError(f"precision must be one of {tuple(_TORCH_DTYPE)}, got {dtype!r}")
+        self.dtype = dtype
+
+    def __enter__(self):
+        global ACT
+        self._prev = _lib.DTYPE
+        _lib.DTYPE = self.dtype
+        ACT = _TORCH_DTYPE[self.dtype]
+        _lib.load(self.dtype)
+        return self
+
+    def __exit__(self, *exc):
+        global ACT
+        _lib.DTYPE = self._prev
+        ACT = _TORCH_DTYPE[self._prev]
+        return False
 
 
 def _stream() -> int:

@@ -1,7 +1,7 @@
 """Mirror of the sgm samplers on the SDXL path (modules/sdxl/sgm/modules/diffusionmodules/sampling.py):
 BaseDiffusionSampler (:28-122: prepare_sampling_loop with x *= sqrt(1 + sigma_0^2), denoise through the guider),
-EulerEDMSampler / HeunEDMSampler (:147-220,309-358, s_churn = 0), LinearMultistepSampler (:271-306),
-EulerAncestralSampler (:361-385), DPMPP2MSampler (:459-573).
+EulerEDMSampler / HeunEDMSampler (:147-220,309-358, incl. s_churn > 0), LinearMultistepSampler (:271-306),
+EulerAncestralSampler (:361-385), DPMPP2SAncestralSampler (:384-457), DPMPP2MSampler (:459-573).
 `sampler(denoiser, x, cond, uc, num_steps)` as in the reference; `denoiser(input, sigma, c)` is opaque, the latent
 update of each step is one fused kernel.  Step multipliers use the reference's fp32 torch expressions."""
 from typing import Dict, Union
@@ -45,41 +45,49 @@ class BaseDiffusionSampler:
         return gen
 
 
-class EulerEDMSampler(BaseDiffusionSampler):
+class EDMSampler(BaseDiffusionSampler):
+    """:147-220.  gamma > 0 (s_churn) adds `randn_like(x) * s_noise * sqrt(sigma_hat^2 - sigma^2)` in front of the step
+    and evaluates the denoiser at sigma_hat; like the reference the draw only happens when gamma > 0."""
+
     def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        if s_churn != 0.0:
-            raise NotImplementedError("cremage_b200: EulerEDMSampler with s_churn > 0 is not implemented")
+        self.s_churn, self.s_tmin, self.s_tmax, self.s_noise = s_churn, s_tmin, s_tmax, s_noise
 
+    def _churn(self, x, sigmas, i, num_sigmas):
+        gamma = min(self.s_churn / (num_sigmas - 1), 2 ** 0.5 - 1) if self.s_tmin <= sigmas[i] <= self.s_tmax else 0.0
+        sigma_hat = sigmas[i] * (gamma + 1.0)
+        if gamma > 0:
+            eps = torch.randn_like(x)
+            x = ops.axpby(x, 1.0, eps.float().contiguous(), float(self.s_noise * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5))
+        return x, sigma_hat
+
+
+class EulerEDMSampler(EDMSampler):
     @torch.no_grad()
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None):
         x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
-        dev_sig = sigmas.to(x.device)
         for i in self.get_sigma_gen(num_sigmas):
-            denoised = self.denoise(x, denoiser, s_in * dev_sig[i], cond, uc)
-            # d = (x - denoised) / sigma ; x + d * (next_sigma - sigma)      (:189-200)
-            x, _ = ops.step_euler_ancestral(x, None, None, 0.0, float(sigmas[i]), float(sigmas[i + 1]), 0.0,
+            x, sigma_hat = self._churn(x, sigmas, i, num_sigmas)
+            denoised = self.denoise(x, denoiser, s_in * sigma_hat.to(x.device), cond, uc)
+            # d = (x - denoised) / sigma_hat ; x + d * (next_sigma - sigma_hat)      (:165-193)
+            x, _ = ops.step_euler_ancestral(x, None, None, 0.0, float(sigma_hat), float(sigmas[i + 1]), 0.0,
                                             denoised=denoised.float())
         return x
 
 
-class HeunEDMSampler(BaseDiffusionSampler):
+class HeunEDMSampler(EDMSampler):
     """EDMSampler.sampler_step + HeunEDMSampler.possible_correction_step (:165-193,321-358): Euler predictor, one more
     denoiser call at next_sigma, x + (d + d_new) / 2 * dt where next_sigma > 0.  Two UNet evaluations per step."""
-
-    def __init__(self, s_churn=0.0, s_tmin=0.0, s_tmax=float("inf"), s_noise=1.0, *args, **kwargs):
-        super().__init__(*args, **kwargs)
-        if s_churn != 0.0:
-            raise NotImplementedError("cremage_b200: HeunEDMSampler with s_churn > 0 is not implemented")
 
     @torch.no_grad()
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None):
         x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
         dev_sig = sigmas.to(x.device)
         for i in self.get_sigma_gen(num_sigmas):
-            sigma, nxt = float(sigmas[i]), float(sigmas[i + 1])
-            denoised = self.denoise(x, denoiser, s_in * dev_sig[i], cond, uc).float().contiguous()
-            d = ops.axpby(x, 1.0 / sigma, denoised, -1.0 / sigma)             # to_d: (x - denoised) / sigma
+            x, sigma_hat = self._churn(x, sigmas, i, num_sigmas)
+            sigma, nxt = float(sigma_hat), float(sigmas[i + 1])
+            denoised = self.denoise(x, denoiser, s_in * sigma_hat.to(x.device), cond, uc).float().contiguous()
+            d = ops.axpby(x, 1.0 / sigma, denoised, -1.0 / sigma)             # to_d: (x - denoised) / sigma_hat
             dt = nxt - sigma
             euler = ops.axpby(x, 1.0, d, dt)
             if float(torch.sum(s_in.cpu() * sigmas[i + 1])) < 1e-14:           # all noise levels 0: no correction (:335-337)
@@ -121,12 +129,21 @@ class LinearMultistepSampler(BaseDiffusionSampler):
         return x
 
 
-class EulerAncestralSampler(BaseDiffusionSampler):
+class AncestralSampler(BaseDiffusionSampler):
+    """:222-268.  `ancestral_step` calls `noise_sampler(x)` on EVERY step -- also the last one, where torch.where
+    discards it -- so the global RNG advances exactly as in the reference."""
+
     def __init__(self, eta=1.0, s_noise=1.0, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.eta, self.s_noise = eta, s_noise
         self.noise_sampler = lambda x: torch.randn_like(x)
 
+    def _noise(self, x, next_sigma):
+        noise = self.noise_sampler(x)                       # drawn unconditionally (:246-250)
+        return noise.float().contiguous() if float(next_sigma) > 0.0 else None
+
+
+class EulerAncestralSampler(AncestralSampler):
     @torch.no_grad()
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None):
         x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
@@ -135,9 +152,48 @@ class EulerAncestralSampler(BaseDiffusionSampler):
             sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=self.eta)
             denoised = self.denoise(x, denoiser, s_in * dev_sig[i], cond, uc)
             # euler step to sigma_down, then x + noise * s_noise * sigma_up where next_sigma > 0   (:338-358,374-383)
-            noise = self.noise_sampler(x).float().contiguous() if float(sigmas[i + 1]) > 0.0 else None
+            noise = self._noise(x, sigmas[i + 1])
             x, _ = ops.step_euler_ancestral(x, None, noise, 0.0, float(sigmas[i]), float(sigma_down),
                                             float(sigma_up) * self.s_noise, denoised=denoised.float())
+        return x
+
+
+class DPMPP2SAncestralSampler(AncestralSampler):
+    """:384-457: Euler-ancestral skeleton with a DPM-Solver++(2S) midpoint correction (a second denoiser call at
+    sigma(s), s = t + h/2 in -log sigma) wherever sigma_down > 0."""
+
+    def get_variables(self, sigma, sigma_down):
+        t, t_next = [to_neg_log_sigma(s) for s in (sigma, sigma_down)]
+        h = t_next - t
+        s = t + 0.5 * h
+        return h, s, t, t_next
+
+    def get_mult(self, h, s, t, t_next):
+        mult1 = to_sigma(s) / to_sigma(t)
+        mult2 = (-0.5 * h).expm1()
+        mult3 = to_sigma(t_next) / to_sigma(t)
+        mult4 = (-h).expm1()
+        return mult1, mult2, mult3, mult4
+
+    @torch.no_grad()
+    def __call__(self, denoiser, x, cond, uc=None, num_steps=None):
+        x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
+        dev_sig = sigmas.to(x.device)
+        for i in self.get_sigma_gen(num_sigmas):
+            sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1], eta=self.eta)
+            denoised = self.denoise(x, denoiser, s_in * dev_sig[i], cond, uc).float().contiguous()
+            if float(torch.sum(s_in.cpu() * sigma_down)) < 1e-14:            # all noise levels 0: plain Euler step (:424-426)
+                x, _ = ops.step_euler_ancestral(x, None, None, 0.0, float(sigmas[i]), float(sigma_down), 0.0,
+                                                denoised=denoised)
+            else:
+                h, s, t, t_next = self.get_variables(sigmas[i], sigma_down)
+                m1, m2, m3, m4 = self.get_mult(h, s, t, t_next)
+                x2 = ops.axpby(x, float(m1), denoised, -float(m2))
+                denoised2 = self.denoise(x2, denoiser, s_in * to_sigma(s).to(x.device), cond, uc).float().contiguous()
+                x = ops.axpby(x, float(m3), denoised2, -float(m4))
+            noise = self._noise(x, sigmas[i + 1])
+            if noise is not None:
+                x = ops.axpby(x, 1.0, noise, float(self.s_noise * sigma_up))
         return x
 
 

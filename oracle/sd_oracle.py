@@ -782,6 +782,162 @@ def sample_dpmpp_2s_ancestral(model, x: Tensor, sigmas: Tensor, noise: Sequence[
 
 
 # ======================================================================================================================
+# SDE family and stochastic churn.  `noise` is the sequence the injected noise_sampler / randn_like returns.
+# ======================================================================================================================
+def _churned(x: Tensor, sigmas: Tensor, i: int, noise_it, s_churn: float, s_tmin: float, s_tmax: float, s_noise: float):
+    """k_diffusion/sampling.py:124-133: the reference draws on every step, the draw only enters when gamma > 0."""
+    gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+    eps = next(noise_it) * s_noise
+    sigma_hat = sigmas[i] * (gamma + 1)
+    if gamma > 0:
+        x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+    return x, sigma_hat
+
+
+def sample_euler_churn(model, x: Tensor, sigmas: Tensor, noise: Sequence[Tensor], s_churn: float, s_tmin: float = 0.0,
+                       s_tmax: float = float("inf"), s_noise: float = 1.0) -> Tensor:
+    """k_diffusion/sampling.py:118-144."""
+    s_in, it = x.new_ones([x.shape[0]]), iter(noise)
+    for i in range(len(sigmas) - 1):
+        x, sigma_hat = _churned(x, sigmas, i, it, s_churn, s_tmin, s_tmax, s_noise)
+        denoised = model(x, sigma_hat * s_in)
+        x = x + ((x - denoised) / sigma_hat) * (sigmas[i + 1] - sigma_hat)
+    return x
+
+
+def sample_heun_churn(model, x: Tensor, sigmas: Tensor, noise: Sequence[Tensor], s_churn: float, s_tmin: float = 0.0,
+                      s_tmax: float = float("inf"), s_noise: float = 1.0) -> Tensor:
+    """k_diffusion/sampling.py:167-193."""
+    s_in, it = x.new_ones([x.shape[0]]), iter(noise)
+    for i in range(len(sigmas) - 1):
+        x, sigma_hat = _churned(x, sigmas, i, it, s_churn, s_tmin, s_tmax, s_noise)
+        denoised = model(x, sigma_hat * s_in)
+        d = (x - denoised) / sigma_hat
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            d_2 = (x_2 - model(x_2, sigmas[i + 1] * s_in)) / sigmas[i + 1]
+            x = x + ((d + d_2) / 2) * dt
+    return x
+
+
+def sample_dpm_2_churn(model, x: Tensor, sigmas: Tensor, noise: Sequence[Tensor], s_churn: float, s_tmin: float = 0.0,
+                       s_tmax: float = float("inf"), s_noise: float = 1.0) -> Tensor:
+    """k_diffusion/sampling.py:196-224."""
+    s_in, it = x.new_ones([x.shape[0]]), iter(noise)
+    for i in range(len(sigmas) - 1):
+        x, sigma_hat = _churned(x, sigmas, i, it, s_churn, s_tmin, s_tmax, s_noise)
+        denoised = model(x, sigma_hat * s_in)
+        d = (x - denoised) / sigma_hat
+        if sigmas[i + 1] == 0:
+            x = x + d * (sigmas[i + 1] - sigma_hat)
+        else:
+            sigma_mid = sigma_hat.log().lerp(sigmas[i + 1].log(), 0.5).exp()
+            x_2 = x + d * (sigma_mid - sigma_hat)
+            d_2 = (x_2 - model(x_2, sigma_mid * s_in)) / sigma_mid
+            x = x + d_2 * (sigmas[i + 1] - sigma_hat)
+    return x
+
+
+def sample_dpmpp_sde(model, x: Tensor, sigmas: Tensor, noise: Sequence[Tensor], eta: float = 1.0, s_noise: float = 1.0,
+                     r: float = 0.5) -> Tensor:
+    """k_diffusion/sampling.py:551-590: two noise draws per step (midpoint, end)."""
+    s_in, it = x.new_ones([x.shape[0]]), iter(noise)
+    sigma_fn = lambda t: t.neg().exp()
+    t_fn = lambda sigma: sigma.log().neg()
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        if sigmas[i + 1] == 0:
+            x = x + ((x - denoised) / sigmas[i]) * (sigmas[i + 1] - sigmas[i])
+            continue
+        t, t_next = t_fn(sigmas[i]), t_fn(sigmas[i + 1])
+        h = t_next - t
+        s = t + h * r
+        fac = 1 / (2 * r)
+        sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(s), eta)
+        s_ = t_fn(sd)
+        x_2 = (sigma_fn(s_) / sigma_fn(t)) * x - (t - s_).expm1() * denoised + next(it) * s_noise * su
+        denoised_2 = model(x_2, sigma_fn(s) * s_in)
+        sd, su = get_ancestral_step(sigma_fn(t), sigma_fn(t_next), eta)
+        t_next_ = t_fn(sd)
+        denoised_d = (1 - fac) * denoised + fac * denoised_2
+        x = (sigma_fn(t_next_) / sigma_fn(t)) * x - (t - t_next_).expm1() * denoised_d + next(it) * s_noise * su
+    return x
+
+
+def sample_dpmpp_2m_sde(model, x: Tensor, sigmas: Tensor, noise: Sequence[Tensor], eta: float = 1.0, s_noise: float = 1.0,
+                        solver_type: str = "midpoint") -> Tensor:
+    """k_diffusion/sampling.py:619-662."""
+    s_in, it = x.new_ones([x.shape[0]]), iter(noise)
+    old_denoised, h_last, h = None, None, None
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        if sigmas[i + 1] == 0:
+            x = denoised
+        else:
+            t, s = -sigmas[i].log(), -sigmas[i + 1].log()
+            h = s - t
+            eta_h = eta * h
+            x = sigmas[i + 1] / sigmas[i] * (-eta_h).exp() * x + (-h - eta_h).expm1().neg() * denoised
+            if old_denoised is not None:
+                r = h_last / h
+                if solver_type == "heun":
+                    x = x + ((-h - eta_h).expm1().neg() / (-h - eta_h) + 1) * (1 / r) * (denoised - old_denoised)
+                else:
+                    x = x + 0.5 * (-h - eta_h).expm1().neg() * (1 / r) * (denoised - old_denoised)
+            if eta:
+                x = x + next(it) * sigmas[i + 1] * (-2 * eta_h).expm1().neg().sqrt() * s_noise
+        old_denoised, h_last = denoised, h
+    return x
+
+
+def sample_dpmpp_3m_sde(model, x: Tensor, sigmas: Tensor, noise: Sequence[Tensor], eta: float = 1.0,
+                        s_noise: float = 1.0) -> Tensor:
+    """k_diffusion/sampling.py:664-717."""
+    s_in, it = x.new_ones([x.shape[0]]), iter(noise)
+    den_1, den_2, h, h_1, h_2 = None, None, None, None, None
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in)
+        if sigmas[i + 1] == 0:
+            x = denoised
+        else:
+            t, s = -sigmas[i].log(), -sigmas[i + 1].log()
+            h = s - t
+            h_eta = h * (eta + 1)
+            x = torch.exp(-h_eta) * x + (-h_eta).expm1().neg() * denoised
+            if h_2 is not None:
+                r0, r1 = h_1 / h, h_2 / h
+                d1_0 = (denoised - den_1) / r0
+                d1_1 = (den_1 - den_2) / r1
+                d1 = d1_0 + (d1_0 - d1_1) * r0 / (r0 + r1)
+                d2 = (d1_0 - d1_1) / (r0 + r1)
+                phi_2 = h_eta.neg().expm1() / h_eta + 1
+                phi_3 = phi_2 / h_eta - 0.5
+                x = x + phi_2 * d1 - phi_3 * d2
+            elif h_1 is not None:
+                r = h_1 / h
+                phi_2 = h_eta.neg().expm1() / h_eta + 1
+                x = x + phi_2 * ((denoised - den_1) / r)
+            if eta:
+                x = x + next(it) * sigmas[i + 1] * (-2 * h * eta).expm1().neg().sqrt() * s_noise
+        den_1, den_2 = denoised, den_1
+        h_1, h_2 = h, h_1
+    return x
+
+
+def kdiff_stochastic_encode(alphas_cumprod: Tensor, x0: Tensor, t: Tensor, sampling_steps: int, noise: Tensor) -> Tensor:
+    """KDiffusionSamplerBase.stochastic_encode, ldm/models/diffusion/k_diffusion_samplers.py:260-297: per-sample index
+    `t * 1000 / steps` (truncated) into the DDPM sqrt(alpha-bar) tables (np.sqrt of the fp32 table, :112-113)."""
+    sqrt_ac = torch.from_numpy(np.sqrt(alphas_cumprod.cpu().numpy())).float()
+    sqrt_1m = torch.from_numpy(np.sqrt(1.0 - alphas_cumprod.cpu().numpy())).float()
+    idx = (t * 1000.0 / sampling_steps).long()
+    shape = (-1,) + (1,) * (x0.ndim - 1)
+    return sqrt_ac[idx].reshape(shape) * x0 + sqrt_1m[idx].reshape(shape) * noise
+
+
+# ======================================================================================================================
 # VAE encoder (SURVEY 8f N2): the step before the path for img2img
 # ======================================================================================================================
 def encoder_param_shapes(cfg: DecoderConfig) -> Dict[str, Tuple[int, ...]]:

@@ -317,3 +317,71 @@ def sample_lms_sgm(denoise_fn, x: Tensor, sigmas: Tensor, cond: dict, uc: dict, 
         cs = [coeff(cur, sig_np, i, j) for j in range(cur)]
         x = x + sum(c * d for c, d in zip(cs, reversed(ds)))
     return x
+
+
+def _sgm_ancestral_step(sigma_from: Tensor, sigma_to: Tensor, eta: float = 1.0):
+    """sampling_utils.py:23-39."""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = torch.minimum(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    return (sigma_to ** 2 - sigma_up ** 2) ** 0.5, sigma_up
+
+
+def sample_euler_ancestral_sgm(denoise_fn, x: Tensor, sigmas: Tensor, cond: dict, uc: dict, scale: float,
+                               noise, eta: float = 1.0, s_noise: float = 1.0) -> Tensor:
+    """EulerAncestralSampler, sampling.py:222-268,361-382; noise[i] = the (always drawn) noise_sampler output of step i."""
+    x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+    s_in = x.new_ones([x.shape[0]])
+    ap = lambda v: v[(...,) + (None,) * (x.ndim - v.ndim)]
+    for i in range(len(sigmas) - 1):
+        sigma, nxt = s_in * sigmas[i], s_in * sigmas[i + 1]
+        sd, su = _sgm_ancestral_step(sigma, nxt, eta)
+        den = _cfg_denoise(denoise_fn, x, sigma, cond, uc, scale)
+        x = x + ap(sd - sigma) * ((x - den) / ap(sigma))
+        x = torch.where(ap(nxt) > 0.0, x + noise[i] * s_noise * ap(su), x)
+    return x
+
+
+def sample_dpmpp_2s_ancestral_sgm(denoise_fn, x: Tensor, sigmas: Tensor, cond: dict, uc: dict, scale: float,
+                                  noise, eta: float = 1.0, s_noise: float = 1.0) -> Tensor:
+    """DPMPP2SAncestralSampler, sampling.py:384-457."""
+    x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+    s_in = x.new_ones([x.shape[0]])
+    ap = lambda v: v[(...,) + (None,) * (x.ndim - v.ndim)]
+    for i in range(len(sigmas) - 1):
+        sigma, nxt = s_in * sigmas[i], s_in * sigmas[i + 1]
+        sd, su = _sgm_ancestral_step(sigma, nxt, eta)
+        den = _cfg_denoise(denoise_fn, x, sigma, cond, uc, scale)
+        x_euler = x + ap(sd - sigma) * ((x - den) / ap(sigma))
+        if torch.sum(sd) < 1e-14:
+            x = x_euler
+        else:
+            t, t_next = sigma.log().neg(), sd.log().neg()
+            h = t_next - t
+            s = t + 0.5 * h
+            x2 = ap(s.neg().exp() / t.neg().exp()) * x - ap((-0.5 * h).expm1()) * den
+            den2 = _cfg_denoise(denoise_fn, x2, s.neg().exp(), cond, uc, scale)
+            x_d = ap(t_next.neg().exp() / t.neg().exp()) * x - ap((-h).expm1()) * den2
+            x = torch.where(ap(sd) > 0.0, x_d, x_euler)
+        x = torch.where(ap(nxt) > 0.0, x + noise[i] * s_noise * ap(su), x)
+    return x
+
+
+def sample_euler_edm_sgm(denoise_fn, x: Tensor, sigmas: Tensor, cond: dict, uc: dict, scale: float, noise=None,
+                         s_churn: float = 0.0, s_tmin: float = 0.0, s_tmax: float = float("inf"),
+                         s_noise: float = 1.0) -> Tensor:
+    """EulerEDMSampler incl. s_churn, sampling.py:147-220 (the draw happens only when gamma > 0)."""
+    x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
+    s_in = x.new_ones([x.shape[0]])
+    ap = lambda v: v[(...,) + (None,) * (x.ndim - v.ndim)]
+    it = iter(noise) if noise is not None else None
+    n = len(sigmas)
+    for i in range(n - 1):
+        gamma = min(s_churn / (n - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        sigma, nxt = s_in * sigmas[i], s_in * sigmas[i + 1]
+        sigma_hat = sigma * (gamma + 1.0)
+        if gamma > 0:
+            x = x + next(it) * s_noise * ap(sigma_hat ** 2 - sigma ** 2) ** 0.5
+        den = _cfg_denoise(denoise_fn, x, sigma_hat, cond, uc, scale)
+        x = x + ap(nxt - sigma_hat) * ((x - den) / ap(sigma_hat))
+    return x

@@ -65,6 +65,116 @@ def test_dropin_install_aliases_reference_import_paths():
         dropin.install(only=["ldm.modules.encoders.modules"])
 
 
+def test_reference_import_lines_resolve_after_install():
+    """The reference's NON-mirrored code imports names from the aliased modules that the hot path never defines
+    (ldm/models/diffusion/ddpm.py:38-41, cldm/cldm.py:12-24, cremage/utils/sampler_utils.py:6-18).  After install()
+    every one of those lines must still import: mirrored names from cremage_b200, the rest from the reference's own
+    module through the mirror's module-level __getattr__."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref_shim.install()
+    ref_shim.install_lightning_stub()
+    from cremage_b200 import dropin
+    dropin.install()
+    try:
+        ns = {}
+        # ldm/models/diffusion/ddpm.py:38-41
+        exec("from ldm.models.autoencoder import VQModelInterface, IdentityFirstStage, AutoencoderKL", ns)
+        exec("from ldm.modules.diffusionmodules.util import make_beta_schedule, extract_into_tensor, noise_like", ns)
+        exec("from ldm.models.diffusion.ddim import DDIMSampler", ns)
+        # cldm/cldm.py:12-24
+        exec("from ldm.modules.diffusionmodules.util import (conv_nd, linear, zero_module, timestep_embedding)", ns)
+        exec("from ldm.modules.attention import SpatialTransformer", ns)
+        exec("from ldm.modules.diffusionmodules.openaimodel import UNetModel, TimestepEmbedSequential, ResBlock, "
+             "Downsample, AttentionBlock", ns)
+        # cremage/utils/sampler_utils.py:6-18
+        for name in ("EulerSampler", "EulerAncestralSampler", "HeunSampler", "Dpm2Sampler", "Dpm2AncestralSampler",
+                     "LmsSampler", "Dpmpp2sAncestralSampler", "DpmppSdeSampler", "Dpmpp2mSampler", "Dpmpp2mSdeSampler",
+                     "Dpmpp3mSdeSampler"):
+            exec(f"from ldm.models.diffusion.k_diffusion_samplers import {name}", ns)
+            assert ns[name].__module__.startswith("cremage_b200."), name
+        for mirrored in ("AutoencoderKL", "DDIMSampler", "UNetModel", "ResBlock", "SpatialTransformer",
+                         "make_beta_schedule"):
+            assert ns[mirrored].__module__.startswith("cremage_b200."), mirrored
+        for fallback in ("VQModelInterface", "IdentityFirstStage", "noise_like", "AttentionBlock",
+                         "timestep_embedding"):
+            assert not ns[fallback].__module__.startswith("cremage_b200."), fallback
+        assert tuple(ns["noise_like"]((2, 3), "cpu").shape) == (2, 3)          # the reference's own function runs
+        import ldm.modules.diffusionmodules.util as u
+        with pytest.raises(AttributeError):
+            u.no_such_name_anywhere
+    finally:
+        dropin.uninstall()
+
+
+def test_unmirrored_name_degrades_to_a_placeholder_when_the_reference_module_cannot_load(monkeypatch):
+    """No reference tree (or its dependencies missing): the import line still succeeds, the name raises on USE."""
+    from cremage_b200 import dropin
+
+    def boom(name):
+        raise ImportError("no reference here")
+    monkeypatch.setattr(dropin, "_load_reference_module", boom)
+    dropin.install(only=["ldm.models.autoencoder"])
+    try:
+        ns = {}
+        exec("from ldm.models.autoencoder import VQModelInterface, AutoencoderKL", ns)
+        assert ns["AutoencoderKL"].__module__.startswith("cremage_b200.")
+        with pytest.raises(NotImplementedError, match="not part of the B200 hot path"):
+            ns["VQModelInterface"]()
+    finally:
+        dropin.uninstall()
+
+
+def test_subtree_cast_and_data_swap_invalidate_packs_and_graphs():
+    """`blocks.half()` (UNetModel.convert_to_fp16) and `p.data = ...` bump no Parameter._version and never
+    pass through the root's _apply; the process-wide pack epoch + the (address, dtype) fingerprint must catch both."""
+    from cremage_b200 import engine
+    from cremage_b200.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    with torch.device("meta"):
+        m = UNetModel(image_size=32, in_channels=4, out_channels=4, model_channels=32, attention_resolutions=[1],
+                      num_res_blocks=1, channel_mult=[1], num_heads=2, use_spatial_transformer=True,
+                      transformer_depth=1, context_dim=16, use_checkpoint=False, legacy=False)
+    m = m.to_empty(device="cpu")
+    e0 = engine.PACK_EPOCH
+    m.convert_to_fp16()                                   # sub-tree _apply only
+    assert engine.PACK_EPOCH > e0
+    p = next(m.input_blocks.parameters())
+    fp0 = engine.param_fingerprint([p])
+    p.data = p.data.clone()                               # same version counter, new storage
+    assert engine.param_fingerprint([p]) != fp0
+    e1 = engine.PACK_EPOCH
+    m.load_state_dict(m.state_dict())
+    assert engine.PACK_EPOCH > e1
+
+
+@pytest.mark.gpu
+def test_convert_to_fp16_after_a_graphed_forward_repacks():
+    """A captured graph must not replay pointers into packs freed by a sub-tree cast (engine.py)."""
+    from oracle import sd_oracle as O
+    from tests._models import build_unet, gold
+    g = gold("tiny_unet.npz")
+    sd = O.make_weights(O.unet_param_shapes(O.TINY_UNET), seed=100)
+    unet = build_unet(O.TINY_UNET, sd)
+    x, t, ctx = (torch.from_numpy(g[k]).cuda() for k in ("x", "t", "context"))
+    y0 = unet(x, t, context=ctx)
+    y0b = unet(x, t, context=ctx)                          # graph replay
+    assert torch.equal(y0, y0b)
+    unet.convert_to_fp16()                                 # frees the sub-modules' packs; root _apply never runs
+    torch.cuda.empty_cache()
+    junk = [torch.full((1 << 20,), float("nan"), device="cuda") for _ in range(64)]   # reuse whatever was freed
+    y1 = unet(x, t, context=ctx)
+    del junk
+    want = torch.from_numpy(g["out"])
+    assert torch.isfinite(y1).all() and (y1.float().cpu() - want).abs().max().item() < 3e-2
+    with torch.no_grad():                                  # weight patch through .data: new storage, same version
+        w = unet.out[2].weight
+        w.data = (w.data.float() * 2.0).to(w.dtype)
+        unet.out[2].bias.data = (unet.out[2].bias.data.float() * 2.0).to(w.dtype)
+    y2 = unet(x, t, context=ctx)
+    assert (y2.float() - 2.0 * y1.float()).abs().max().item() < 2e-2
+
+
 @pytest.mark.gpu
 def test_weights_survive_half_and_device_round_trips():
     """The reference does load_state_dict -> .half() -> .to(device), and low_vram_shift moves the UNet to the CPU and back

@@ -203,3 +203,77 @@ def test_sgm_heun_lms_trajectories_vs_reference_golden(which):
     err = (z.cpu() - want).abs().max().item()
     print(f"[parity] sgm {which} {int(gs['steps'])} steps: max_abs_err={err:.4e} latent_absmax={want.abs().max():.2f}")
     assert err <= 2e-2 * max(want.abs().max().item(), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DPMPP2SAncestralSampler, EulerAncestralSampler (noise drawn on every step), EulerEDMSampler with s_churn > 0:
+# goldens from the unmodified reference with injected noise (oracle/make_golden_samplers2.py)
+# ---------------------------------------------------------------------------------------------------------------
+SGM2 = ["dpmpp2s_ancestral", "euler_ancestral", "euler_churn"]
+
+
+@pytest.mark.parametrize("which", SGM2)
+def test_oracle_ancestral_churn_trajectories_match_reference_golden(which):
+    g, sd = _weights()
+    gs = gold("tiny_sgm_samplers2.npz")
+    table = S.legacy_ddpm_sigma_table(1000)
+    net = lambda x, t, c: S.sgm_unet_forward(sd, S.TINY_SGM_UNET, x, t, c["crossattn"], c["vector"])
+    den = lambda x, sigma, c: S.discrete_denoise(net, table, x, sigma, c)
+    cond, uc = _cond(g)
+    noise = list(torch.from_numpy(gs["noise"]))
+    sig = S.edm_sigmas(int(gs["steps"]), **EDM)
+    x_T, scale = torch.from_numpy(g["x_T"]), float(g["cfg_scale"])
+    with torch.no_grad():
+        if which == "dpmpp2s_ancestral":
+            z = S.sample_dpmpp_2s_ancestral_sgm(den, x_T, sig, cond, uc, scale, noise)
+        elif which == "euler_ancestral":
+            z = S.sample_euler_ancestral_sgm(den, x_T, sig, cond, uc, scale, noise)
+        else:
+            z = S.sample_euler_edm_sgm(den, x_T, sig, cond, uc, scale, noise, s_churn=float(gs["s_churn"]))
+    assert np.abs(z.numpy() - gs[which]).max() < 1e-3 * max(1.0, np.abs(gs[which]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", SGM2)
+def test_sgm_ancestral_churn_trajectories_vs_reference_golden(which):
+    from cremage_b200.sgm.modules.diffusionmodules.denoiser import DiscreteDenoiser
+    from cremage_b200.sgm.modules.diffusionmodules import sampling as SM
+    from cremage_b200.sgm.modules.diffusionmodules.wrappers import OpenAIWrapper
+    g, sd = _weights()
+    gs = gold("tiny_sgm_samplers2.npz")
+    model = OpenAIWrapper(_build_sgm_unet(S.TINY_SGM_UNET, sd))
+    den = DiscreteDenoiser(scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+                           num_idx=1000,
+                           discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}).cuda()
+    common = dict(discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization", "params": EDM},
+                  num_steps=int(gs["steps"]),
+                  guider_config={"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG",
+                                 "params": {"scale": float(g["cfg_scale"])}})
+    noise = torch.from_numpy(gs["noise"]).cuda()
+    it = iter(range(noise.shape[0]))
+    draws = []
+
+    def sampler_noise(x):
+        draws.append(1)
+        return noise[next(it)]
+
+    cond, uc = _cond(g, "cuda")
+    x_T = torch.from_numpy(g["x_T"]).cuda()
+    denoiser = lambda inp, sigma, c: den(model, inp, sigma, c)
+    if which == "euler_churn":
+        smp = SM.EulerEDMSampler(s_churn=float(gs["s_churn"]), **common)
+        real = torch.randn_like
+        torch.randn_like = lambda x, *a, **k: sampler_noise(x)
+        try:
+            z = smp(denoiser, x_T, cond=cond, uc=uc)
+        finally:
+            torch.randn_like = real
+    else:
+        smp = (SM.DPMPP2SAncestralSampler if which == "dpmpp2s_ancestral" else SM.EulerAncestralSampler)(**common)
+        smp.noise_sampler = sampler_noise
+        z = smp(denoiser, x_T, cond=cond, uc=uc)
+        assert len(draws) == int(gs["steps"])      # the reference draws on every step, also the last (RNG-stream parity)
+    want = torch.from_numpy(gs[which])
+    err = (z.cpu() - want).abs().max().item()
+    print(f"[parity] sgm {which}: max_abs_err={err:.4e} latent_absmax={want.abs().max():.2f}")
+    assert err <= 2e-2 * max(want.abs().max().item(), 1.0)
