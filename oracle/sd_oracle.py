@@ -358,6 +358,13 @@ def _resblock(sd: SD, p: str, x: Tensor, emb: Tensor) -> Tensor:
     return x + h
 
 
+# "einsum": CrossAttentionOriginal (attention.py:611-693), the class the fp32 CPU goldens come from.  "sdpa": the same
+# maths through torch's fused kernel, as the reference's GPU classes do (MemoryEfficientCrossAttention -> xformers
+# attention.py:769-861, sgm CrossAttention -> F.scaled_dot_product_attention sgm/modules/attention.py:507-511); only
+# bench.py's torch-on-GPU baseline switches this.
+ATTENTION_IMPL = "einsum"
+
+
 def _cross_attention(sd: SD, p: str, x: Tensor, context: Optional[Tensor], heads: int,
                      ipa: Optional[Tuple[float, int]] = None) -> Tensor:
     """CrossAttentionOriginal.forward, attention.py:611-693 with no LoRA / mask.  ipa = (ipa_scale, ipa_num_tokens): the
@@ -373,6 +380,10 @@ def _cross_attention(sd: SD, p: str, x: Tensor, context: Optional[Tensor], heads
     v = F.linear(ctx, sd[p + ".to_v.weight"])
     b, n, inner = q.shape
     d = inner // heads
+    if ATTENTION_IMPL == "sdpa" and ipa_ctx is None:
+        h4 = lambda t: t.view(b, -1, heads, d).transpose(1, 2)
+        out = F.scaled_dot_product_attention(h4(q), h4(k), h4(v)).transpose(1, 2).reshape(b, n, inner)
+        return F.linear(out, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
     split = lambda t: t.view(b, -1, heads, d).permute(0, 2, 1, 3).reshape(b * heads, -1, d)
     q, k, v = split(q), split(k), split(v)
     merge = lambda t: t.view(b, heads, n, d).permute(0, 2, 1, 3).reshape(b, n, inner)
@@ -483,6 +494,10 @@ def _vae_attn(sd: SD, p: str, x: Tensor) -> Tensor:
     k = F.conv2d(h_, sd[p + ".k.weight"], sd[p + ".k.bias"])
     v = F.conv2d(h_, sd[p + ".v.weight"], sd[p + ".v.bias"])
     b, c, h, w = q.shape
+    if ATTENTION_IMPL == "sdpa":   # sgm AttnBlock.attention, sgm/modules/diffusionmodules/model.py:180-195
+        t4 = lambda t: t.reshape(b, 1, c, h * w).transpose(2, 3)
+        h_ = F.scaled_dot_product_attention(t4(q), t4(k), t4(v)).transpose(2, 3).reshape(b, c, h, w)
+        return x + F.conv2d(h_, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
     q = q.reshape(b, c, h * w).permute(0, 2, 1)
     k = k.reshape(b, c, h * w)
     w_ = torch.bmm(q, k) * (int(c) ** (-0.5))
