@@ -71,3 +71,18 @@ def build_ldm(ucfg, usd, vcfg=None, vsd=None, device="cuda"):
 def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 2.0) -> float:
     mse = ((a.double() - b.double()) ** 2).mean().item()
     return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+BF16_FACTOR = 4.0
+
+
+def build_dtype() -> str:
+    """'fp16' (default build, the reference's own GPU precision) or 'bf16' (CREMAGE_B200_DTYPE=bf16)."""
+    from cremage_b200 import _lib
+    return _lib.DEFAULT_DTYPE
+
+
+def tol(fp16_value: float) -> float:
+    """Stated tolerance for the running build: bf16 keeps 8 mantissa bits instead of fp16's 11 (unit round-off 8x
+    larger); its bounds are BF16_FACTOR x the fp16 ones."""
+    return fp16_value * (BF16_FACTOR if build_dtype() == "bf16" else 1.0)

@@ -22,20 +22,10 @@ import pytest
 import torch
 
 from oracle import sd_oracle as O
-from tests._models import build_ldm, build_unet, build_vae, gold, psnr, randn
+from tests._models import build_dtype as _dtype
+from tests._models import build_ldm, build_unet, build_vae, gold, psnr, randn, tol
 
 pytestmark = pytest.mark.gpu
-
-BF16_FACTOR = 4.0
-
-
-def _dtype():
-    from cremage_b200 import _lib
-    return _lib.DEFAULT_DTYPE
-
-
-def tol(fp16_value: float) -> float:
-    return fp16_value * (BF16_FACTOR if _dtype() == "bf16" else 1.0)
 
 
 _TABLE = {}
@@ -110,16 +100,17 @@ def test_cfg1_euler20_full_trajectory_and_image(sd15):
         rows.append([i, float(sigmas[i]), err, ref])
     derr = (torch.stack(dens).cpu() - torch.from_numpy(g["denoised"])).abs().amax(dim=(1, 2, 3, 4))
     print("[parity] cfg1 denoised max|d| per step:", " ".join(f"{v:.3f}" for v in derr.tolist()))
-    # the fused (callback-free) path the benchmark runs gives the same final latent
+    # the fused (callback-free) path the benchmark runs: ONE kernel per step for CFG mix + c_out + update + noise, a
+    # different rounding sequence from the callback path above, held to the same bound against the same golden
     it = iter(range(20))
     x_fused = sample_euler_ancestral(wrapper, x_T * sig[0], sig, disable=True, noise_sampler=lambda s, sn: noise[next(it)])
-    assert (x_fused - xf).abs().max().item() <= 1e-3 * max(1.0, want[-1].abs().max().item())
+    ferr, _, _ = _latent_check("cfg1 euler_a final latent, fused path", x_fused.cpu(), want[-1])
     img = ldm.decode_first_stage(x_fused)
     want_img = torch.from_numpy(g["image"].astype(np.float32))
     p = psnr(img.float().cpu(), want_img)
     print(f"[parity] cfg1 decoded 512x512 image: PSNR={p:.1f} dB")
     _record("cfg1_euler20", steps=rows, final_abs=rows[-1][2], final_rel=rows[-1][2] / max(rows[-1][3], 1.0),
-            worst_rel=max(r[2] / max(r[3], 1.0) for r in rows), image_psnr=p)
+            worst_rel=max(r[2] / max(r[3], 1.0) for r in rows), image_psnr=p, fused_final_abs=ferr)
     assert p >= 35.0
 
 
@@ -144,7 +135,7 @@ def test_cfg2_ddim50_full_run(sd15):
     _record("cfg2_ddim50", final_abs=err, final_absmax=ref, final_rel_rms=rms, **rec)
     x2, _ = smp.sample(S=50, batch_size=2, shape=[4, 64, 64], conditioning=cond, eta=0.0, x_T=x_T,
                        unconditional_guidance_scale=7.5, unconditional_conditioning=uncond, verbose=False)
-    assert (x2 - x).abs().max().item() <= 1e-3 * max(1.0, ref)          # callback-free (benchmark) path
+    _latent_check("cfg2 ddim final latent, callback-free path", x2.cpu(), torch.from_numpy(g["final"]))
 
 
 def test_cfg3_vae_decode_64(sd15):
