@@ -26,7 +26,7 @@ def lib_path(dtype: str = "fp16") -> Path:
 LIB_PATH = lib_path("fp16")
 STAMP = PKG_DIR / ".libcremage_b200.stamp"
 
-SOURCES = ["runtime.cu", "igemm.cu", "attention.cu", "norm.cu", "elementwise.cu", "sampler.cu"]
+SOURCES = ["runtime.cu", "igemm.cu", "attention.cu", "attention64.cu", "norm.cu", "elementwise.cu", "sampler.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

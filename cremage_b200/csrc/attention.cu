@@ -23,6 +23,8 @@
 // through 4-D TMA boxes {d, tokens, heads, batch}: the box is 64 columns wide and the tensor map's inner extent is d,
 // so TMA zero-fills the pad columns (d = 40 -> 64) -- no per-head padded copy of Q/K/V exists.
 // Replaces the attention cores at ldm/modules/attention.py:418-423 (Doggettx), :646-657 (Original), :811 (xformers).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "cremage_b200.h"
 
@@ -388,6 +390,12 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
 using namespace cb;
 
+namespace cb {
+int launch_attention64(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, void* out,
+                       int64_t batch, int64_t heads, int64_t nq, int64_t nk, int d, float scale, int nt, int num_sms,
+                       cudaStream_t stream);   // attention64.cu
+}
+
 extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld,
                             void* out, int64_t batch, int64_t heads, int64_t nq, int64_t nk, int d, float scale,
                             cudaStream_t stream) {
@@ -399,6 +407,28 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   const int dpad = (d + 63) / 64 * 64;
   const int64_t bh = batch * heads;
   CB_REQUIRE(bh * ((nq + 127) / 128) < (1LL << 30), "cb_attention: problem too large");
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0, sms = 0;
+    CB_CHECK_CUDA(cudaGetDevice(&dev));
+    CB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    num_sms = sms > 0 ? sms : 148;
+  }
+  if (dpad == 64) {
+    // head dims <= 64 with SHORT key sequences (cross-attention, nk = 77 * k): three query tiles per CTA over 64-row kv
+    // blocks (attention64.cu) -- 0.058 ms against 0.089 ms for bh 128, 4096 x 77, d 40.  For long key sequences the
+    // two-warpgroup kernel below (128-row kv blocks, half as many barrier round trips per exponential) is still the
+    // faster one (0.80 ms against 0.88 ms at 4096 x 4096; profiles/r2_attention64.md).  CB_ATTN64=0 / =2: never / always.
+    static int use64 = -1;
+    if (use64 < 0) {
+      const char* e = getenv("CB_ATTN64");
+      use64 = e ? atoi(e) : 1;
+    }
+    const long long tiles = bh * ((nq + 127) / 128);
+    const int nt = (int)(tiles / num_sms < 3 ? tiles / num_sms : 3);
+    if (nt >= 2 && (use64 == 2 || (use64 == 1 && nk <= 256)))
+      return launch_attention64(q, q_ld, k, k_ld, v, v_ld, out, batch, heads, nq, nk, d, scale, nt, num_sms, stream);
+  }
   CUtensorMap mq, mk, mv;
   uint32_t box[4] = {64, 128, 1, 1};
   {
@@ -438,13 +468,6 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   }
   const int rows_per_item = p.nwg * ATT_BM;
   const long long items = ((nq + rows_per_item - 1) / rows_per_item) * bh;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0, sms = 0;
-    CB_CHECK_CUDA(cudaGetDevice(&dev));
-    CB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    num_sms = sms > 0 ? sms : 148;
-  }
   dim3 grid((unsigned)(items < num_sms ? items : num_sms));   // persistent: one CTA per SM walks the work items
   if (p.use_ones) attention_kernel<true><<<grid, ATT_THREADS, smem, stream>>>(mq, mk, mv, p);
   else attention_kernel<false><<<grid, ATT_THREADS, smem, stream>>>(mq, mk, mv, p);
