@@ -51,6 +51,15 @@ class IGemmDesc(C.Structure):
     ]
 
 
+class IGemmPlan(C.Structure):
+    """Mirror of `cb_igemm_plan_t` (include/cremage_b200.h)."""
+
+    _fields_ = [("tw", C.c_int), ("th", C.c_int), ("tn", C.c_int),
+                ("bn", C.c_int), ("cta_pair", C.c_int), ("nsub", C.c_int), ("ksplit", C.c_int),
+                ("m_tiles", C.c_int64), ("workspace_bytes", C.c_int64),
+                ("gn_fusable", C.c_int), ("gn_rows_per_image", C.c_int64)]
+
+
 _i64, _int, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
 
 # name -> argtypes (every function returns int unless listed in _RESTYPES)
@@ -60,6 +69,9 @@ SIGNATURES = {
     "cb_act_dtype": [],
     "cb_launch_count": [],
     "cb_igemm": [C.POINTER(IGemmDesc), _vp],
+    "cb_igemm_plan": [C.POINTER(IGemmDesc), C.POINTER(IGemmPlan)],
+    "cb_igemm_auto": [C.POINTER(IGemmDesc), _vp, _i64, _vp],
+    "cb_pack_weight": [_vp, _i64, _i64, _i64, _int, _vp, _vp],
     "cb_attention": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _int, _f32, _vp],
     "cb_softmax_rows": [_vp, _int, _i64, _vp, _i64, _i64, _i64, _f32, _vp],
     "cb_pointwise_nchw_to_nhwc": [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _f32, _vp, _vp],

@@ -26,7 +26,7 @@ def lib_path(dtype: str = "fp16") -> Path:
 LIB_PATH = lib_path("fp16")
 STAMP = PKG_DIR / ".libcremage_b200.stamp"
 
-SOURCES = ["runtime.cu", "igemm.cu", "attention.cu", "attention64.cu", "norm.cu", "elementwise.cu", "sampler.cu"]
+SOURCES = ["runtime.cu", "igemm.cu", "attention.cu", "attention64.cu", "plan.cu", "norm.cu", "elementwise.cu", "sampler.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -82,6 +82,26 @@ def build(force: bool = False, verbose: bool = False):
         raise RuntimeError("nvcc failed building libcremage_b200")
     STAMP.write_text(want)
     return paths
+
+
+C_TEST_SRC = REPO_ROOT / "tests" / "c" / "cabi_plan_test.c"
+
+
+def build_c_test(dtype: str = "fp16") -> Path:
+    """gcc -std=c99: the C-only consumer of the C ABI (tests/c/cabi_plan_test.c) linked against the in-tree library and
+    libcudart -- proves the boundary is usable without Python, torch or C++.  Returns the binary path."""
+    out = C_TEST_SRC.with_name("cabi_plan_test" + ("" if dtype == "fp16" else "_" + dtype))
+    lib = lib_path(dtype)
+    if out.exists() and out.stat().st_mtime >= max(C_TEST_SRC.stat().st_mtime, lib.stat().st_mtime):
+        return out
+    cuda = Path(_nvcc()).resolve().parent.parent
+    cmd = ["gcc", "-std=c99", "-Wall", "-I", str(REPO_ROOT / "include"), "-I", str(cuda / "include"), str(C_TEST_SRC), "-o", str(out),
+           "-L", str(PKG_DIR), f"-l:{lib.name}", "-L", str(cuda / "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath,$ORIGIN/../../cremage_b200", f"-Wl,-rpath,{cuda / 'lib64'}"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed building the C ABI test:\n" + r.stdout)
+    return out
 
 
 if __name__ == "__main__":

@@ -423,3 +423,33 @@ extern "C" int cb_image_to_u8(const void* src, int64_t n, int64_t hw, int64_t c_
   CB_LAUNCHED(1);
   return CB_OK;
 }
+
+// ----------------------------------------------------------------------------------------------------------------
+// weight repacking: fp32 [cout][c0 + c1][taps] (OIHW with taps = kh*kw contiguous) -> 16-bit [cout][taps][pad64(c0) | pad64(c1)]
+// ----------------------------------------------------------------------------------------------------------------
+namespace cb {
+__global__ void pack_weight_kernel(const float* __restrict__ w, long long cout, int c0, int c1, int taps, act_t* __restrict__ out) {
+  const int p0 = (c0 + 63) / 64 * 64, p1 = (c1 + 63) / 64 * 64;
+  const long long kcols = (long long)taps * (p0 + p1), total = cout * kcols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long o = i / kcols;
+    const int k = int(i - o * kcols), t = k / (p0 + p1), c = k - t * (p0 + p1);
+    int ci = -1;
+    if (c < p0) { if (c < c0) ci = c; }
+    else if (c - p0 < c1) ci = c0 + (c - p0);
+    out[i] = to_act(ci < 0 ? 0.f : w[(o * (c0 + c1) + ci) * taps + t]);
+  }
+}
+}  // namespace cb
+
+extern "C" int cb_pack_weight(const float* w, int64_t cout, int64_t c0, int64_t c1, int taps, void* out, cudaStream_t stream) {
+  CB_REQUIRE(w && out && cout > 0 && c0 > 0 && c1 >= 0 && taps >= 1 && taps <= 9, "cb_pack_weight: bad arguments");
+  const long long total = cout * (long long)taps * ((c0 + 63) / 64 * 64 + (c1 + 63) / 64 * 64);
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  cb::pack_weight_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), threads, 0, stream>>>(w, cout, (int)c0, (int)c1, taps,
+                                                                                                    (cb::act_t*)out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return cb::CB_OK;
+}

@@ -164,102 +164,22 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor, bn: int) -> Tuple[torch.Tensor,
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# tiling heuristics
+# tiling: decided INSIDE the library (csrc/plan.cu: cb_igemm_plan) -- nothing here chooses a tile
 # ------------------------------------------------------------------------------------------------------------------
-def _pow2_floor(x: int) -> int:
-    return 1 << (x.bit_length() - 1)
-
-
-def _pow2_ceil(x: int) -> int:
-    return 1 << (x - 1).bit_length()
-
-
-def choose_tile(n: int, h: int, w: int) -> Tuple[int, int, int]:
-    """128-row tile {tw, th, tn} over an (n, h, w) pixel grid; overhang is masked by the kernel."""
-    if h == 1 and n == 1:
-        return 128, 1, 1
-    tw = min(128, w & -w)  # largest power of two dividing w
-    th = min(128 // tw, _pow2_ceil(h))
-    tn = 128 // (tw * th)
-    return tw, th, tn
-
-
-NUM_SMS = 148  # B200
-PAIR_DEFAULT = True
-SPLITK_DEFAULT = True
-
-
-def choose_bn(cout_cols: int, m_tiles: int, multiple: int = 32) -> int:
-    """N tile for the persistent kernel (one CTA per SM): minimise rounds x per-tile cost, where a tile costs about
-    bn MMA columns plus a fixed prologue/epilogue share; ties go to the wider tile (fewer A re-reads)."""
-    best = None
-    for bn in (160, 128, 64, 32):
-        if bn % multiple:
-            continue
-        tiles = m_tiles * (-(-cout_cols // bn))
-        cost = (-(-tiles // NUM_SMS)) * (bn + 24)
-        if best is None or cost < best[0]:
-            best = (cost, bn)
-    return best[1]
-
-
-def choose_bn_pair(cout_cols: int, m_tiles: int, multiple: int = 32, splits: Sequence[int] = (1,)) -> Tuple[int, int, int]:
-    """(bn, nsub, ksplit) in CTA-pair mode (74 clusters, each a 256-row tile).  nsub = 2: two N tiles share every A stage
-    (cb_igemm's sub-tile groups, 3 * bn <= 512).  ksplit > 1: K split by tap groups over otherwise idle clusters
-    (fp32 partials + cb_splitk_reduce).  Cost of a round ~ MMA columns of the tile group; tiles narrower than 256
-    columns are shared-memory-fill bound (x1.25), and below 128 columns the single issuing thread cannot keep the
-    tensor core fed, so narrower tiles cost as much as 128; a split adds a fixed per-item and a reduce cost."""
-    best = None
-    m_pairs = (m_tiles + 1) // 2
-    for bn in (256, 160, 128, 64, 32):
-        if bn % multiple:
-            continue
-        n_tiles = -(-cout_cols // bn)
-        for nsub in (2, 1):
-            if nsub == 2 and not (3 * bn <= 512 and n_tiles >= 2):
-                continue
-            groups = -(-n_tiles // nsub)
-            width = nsub * bn
-            per = (nsub * max(bn, 128) + 16) * (1.0 if width >= 256 else 1.25)
-            for ks in splits:
-                items = m_pairs * groups * ks
-                cost = (-(-items // (NUM_SMS // 2))) * (per / ks + (24 if ks > 1 else 0)) + (30 if ks > 1 else 0)
-                if best is None or cost < best[0]:
-                    best = (cost, bn, nsub, ks)
-    return best[1], best[2], best[3]
-
-
-def choose_ksplit_single(tiles: int, num_k: int) -> int:
-    """Split-K factor (1, 3 or 9 tap groups) of a single-CTA 3x3 conv launch with few output tiles (small batch: the
-    8x8 / 16x16 levels have 1..4 M tiles), in units of one K block: rounds over the 148 SMs x K blocks per item, plus a
-    per-split cost for the fp32 partials and the reduce launch.  M = 128, N = 1280, K = 11520: 40 tiles stream 180 K
-    blocks each on 40 SMs; three tap groups put 120 CTAs to work on 60 blocks each."""
-    best_ks, best = 1, None
-    if tiles >= NUM_SMS:      # every SM already has a tile: splitting only adds partial traffic and a reduce launch
-        return 1
-    for ks in (1, 3, 9):
-        cost = (-(-tiles * ks // NUM_SMS)) * (num_k / ks) + (8 * ks if ks > 1 else 0)
-        if best is None or cost < best:
-            best_ks, best = ks, cost
-    return best_ks
-
-
 import os as _os
-# CTA pairs for K >= 1152 (the MMA-bound launches); below that the epilogue dominates.  Env overrides are tuning knobs.
-PAIR_MIN_K_CHUNKS = int(_os.environ.get("CB_PAIR_MIN_K_CHUNKS", "18"))
-PAIR_MIN_M_TILES = 8
-GEGLU_PAIR = int(_os.environ.get("CB_GEGLU_PAIR", "1"))
-GEGLU_BN = int(_os.environ.get("CB_GEGLU_BN", "256"))   # N tile of the fused GEGLU projection (x | gate halves)
-
-
-# GroupNorm statistics fused into the producing launch's epilogue; the GroupNorm is then a fold of the partials + ONE
-# streaming pass (one read + one write per element) through a bulk-copy shared-memory ring.  Decides the VAE decoder
-# (tensors far beyond the 126 MB L2: 2.5 -> 5.0-5.7 TB/s); for the UNet's L2-resident tensors it is a small but repeatable
-# gain over the single-pass cluster kernel (batch 16 step 19.54 -> 19.32 ms, three back-to-back pairs; equal at batch 2),
-# profiles/r1_groupnorm_fused_stats.md -- so every qualifying producer fuses.  Tuning / A-B knobs:
+GEGLU_BN = int(_os.environ.get("CB_GEGLU_BN", "256"))   # N tile of the fused GEGLU projection: fixes the weight-row order
+# read by the library itself (plan.cu); mirrored here only so tools / tests can show and pin them
 GN_FUSE = int(_os.environ.get("CB_GN_FUSE", "1"))
 GN_FUSE_MIN_K_CHUNKS = int(_os.environ.get("CB_GN_FUSE_MIN_K_CHUNKS", "1"))
 GN_FUSE_MIN_BYTES = int(_os.environ.get("CB_GN_FUSE_MIN_BYTES", "0"))
+
+
+def choose_tile(n: int, h: int, w: int) -> Tuple[int, int, int]:
+    """The library's 128-row tile {tw, th, tn} over an (n, h, w) pixel grid (cb_igemm_plan)."""
+    d, plan = IGemmDesc(), _lib.IGemmPlan()
+    d.n, d.h, d.w, d.c0, d.cout, d.taps = n, h, w, 64, 64, 1
+    check(_lib.load().cb_igemm_plan(C.byref(d), C.byref(plan)), "cb_igemm_plan")
+    return plan.tw, plan.th, plan.tn
 
 
 TAPS_1X1 = ([0], [0], [0])
@@ -330,84 +250,68 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         c1 = a1.shape[-1]
     n, h, w = out_grid if out_grid is not None else (a_n, a_h, a_w)
     rows = n * h * w
-    tw, th, tn = choose_tile(n, h, w)
-    m_tiles = (-(-w // tw)) * (-(-h // th)) * (-(-n // tn))
     ncols = 2 * cout if mode == EPI_GEGLU else cout
-    num_k = len(taps[0]) * (ceil64(c0) // 64 + ceil64(c1) // 64)
-    if pair is None:
-        pair = PAIR_DEFAULT and num_k >= PAIR_MIN_K_CHUNKS and m_tiles >= PAIR_MIN_M_TILES
-        if mode == EPI_GEGLU:
-            pair = bool(GEGLU_PAIR) and m_tiles >= PAIR_MIN_M_TILES
-    # split-K (by tap groups) is available to plain 16-bit 3x3 convs; the reduce kernel applies bias / row bias / residual
-    can_split = (mode == EPI_LINEAR and len(taps[0]) == 9 and not out_f32 and act == ACT_NONE and
-                 out_scale == 1.0 and cout % 8 == 0 and (out is None or out.shape[-1] % 8 == 0))
-    if bn is None:
-        if pair:
-            bn, auto_nsub, auto_ks = choose_bn_pair(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32,
-                                                    splits=(1, 3) if (can_split and ksplit is None and SPLITK_DEFAULT) else (1,))
-            if nsub == 0:
-                nsub = auto_nsub
-            if ksplit is None:
-                ksplit = auto_ks
-        else:
-            bn = choose_bn(ncols, m_tiles, 64 if mode == EPI_GEGLU else 32)
-            if can_split and ksplit is None and SPLITK_DEFAULT:
-                ksplit = choose_ksplit_single(m_tiles * (-(-ncols // bn)), num_k)
-    if out_pixel_strides is not None:
-        can_split = False
-    ksplit = ksplit if (ksplit and can_split) else 1
-    gn_part = None
-    if (gn_stats and GN_FUSE and ksplit == 1 and mode == EPI_LINEAR and not out_f32 and act == ACT_NONE and out_scale == 1.0
-            and cout % 8 == 0 and num_k >= GN_FUSE_MIN_K_CHUNKS and 2 * rows * cout >= GN_FUSE_MIN_BYTES and (tw * th) % 32 == 0 and out is None and out_ld is None):
-        bpi = (-(-w // tw)) * (-(-h // th))   # one row of partials per M tile of an image
-        gn_part = torch.empty((n, bpi, 2, cout // 2), dtype=torch.float32, device=a0.device)
-    if out is None:
-        ld = out_ld if out_ld is not None else cout
-        out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
-    ld = out_ld if out_ld is not None else (out.shape[-1] if mode != EPI_HEADS else 0)
+    dw, dh, dn = taps
+    if rowbias is not None:
+        assert rowbias.dtype == torch.float32 and rowbias.stride(-1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+    if residual is not None:
+        assert residual.dtype == ACT and residual.is_contiguous()
+    want_f32 = out_f32 if out is None else (out.dtype == torch.float32)
 
-    final = None
-    if ksplit > 1:   # raw fp32 partials now, epilogue in cb_splitk_reduce
-        final = (out, bias, rowbias, residual, ld)
-        out = torch.empty((ksplit, rows, cout), dtype=torch.float32, device=a0.device)
-        bias = rowbias = residual = None
-        ld = cout
-
+    # the PROBLEM; the tiling fields stay 0 (= the library chooses) unless the caller pins them (tests, tools)
     d = IGemmDesc()
     d.a0, d.c0, d.a0_ld = _p(a0), c0, 0
     d.a1, d.c1, d.a1_ld = _p(a1), c1, 0
     d.a_n, d.a_h, d.a_w = a_n, a_h, a_w
     d.n, d.h, d.w = n, h, w
-    d.tw, d.th, d.tn = tw, th, tn
-    dw, dh, dn = taps
     d.taps = len(dw)
     for i in range(len(dw)):
         d.tap_dw[i], d.tap_dh[i], d.tap_dn[i] = dw[i], dh[i], dn[i]
     d.wgt, d.wgt_rows = _p(wgt), wgt.shape[0]
     d.cout = cout
     d.mode, d.act = mode, act
-    d.bias = _p(bias)
-    d.rowbias, d.rowbias_ld = _p(rowbias), (rowbias.stride(0) if rowbias is not None else 0)
-    if rowbias is not None:
-        assert rowbias.dtype == torch.float32 and rowbias.stride(-1) == 1
-    if bias is not None:
-        assert bias.dtype == torch.float32 and bias.is_contiguous()
-    d.residual, d.res_ld = _p(residual), (residual.shape[-1] if residual is not None else 0)
-    if residual is not None:
-        assert residual.dtype == ACT and residual.is_contiguous()
-    d.out, d.out_ld, d.out_f32 = _p(out), ld, int(out.dtype == torch.float32)
+    d.out_f32 = int(want_f32)
     d.out_scale = out_scale
+    d.out_ld = (out_ld if out_ld is not None else (cout if out is None else out.shape[-1])) if mode != EPI_HEADS else 0
     if heads is not None:
         d.heads_d, d.heads_dpad, d.heads_h, d.heads_tokens, d.heads_which_stride = heads
-    d.bn, d.stages, d.epilogue, d.cta_pair, d.nsub, d.ksplit = bn, stages, epilogue, int(bool(pair)), nsub, ksplit
-    d.gn_partials = _p(gn_part)
-    if gn_table is not None:
-        assert gn_part is None and ksplit == 1 and (tw * th) % 32 == 0
-        d.gn_partials, d.gn_rows_per_image, d.gn_row_offset = _p(gn_table[0]), gn_table[0].shape[1], gn_table[1]
+    d.bn, d.stages, d.epilogue, d.nsub = (bn or 0), stages, epilogue, nsub
+    d.cta_pair = 0 if pair is None else (1 if pair else -1)
+    d.ksplit = 0 if ksplit is None else ksplit
     if out_pixel_strides is not None:
-        assert ksplit == 1 and gn_part is None and residual is None and mode == EPI_LINEAR and not out_f32
+        assert residual is None and mode == EPI_LINEAR and not want_f32
         d.out_w_stride, d.out_h_stride, d.out_n_stride = (int(v) for v in out_pixel_strides)
         d.epilogue = 2   # CB_EPILOGUE_STAGED: the strides live in the TMA-store tensor map
+    plan = _lib.IGemmPlan()
+    check(_lib.load().cb_igemm_plan(C.byref(d), C.byref(plan)), "cb_igemm_plan")
+    d.tw, d.th, d.tn = plan.tw, plan.th, plan.tn
+    bn, pair, ksplit = plan.bn, bool(plan.cta_pair), plan.ksplit
+    d.bn, d.cta_pair, d.nsub, d.ksplit = plan.bn, plan.cta_pair, plan.nsub, plan.ksplit
+
+    gn_part = None
+    if gn_stats and plan.gn_fusable and out is None and out_ld is None:
+        gn_part = torch.empty((n, plan.gn_rows_per_image, 2, cout // 2), dtype=torch.float32, device=a0.device)
+    if out is None:
+        ld = out_ld if out_ld is not None else cout
+        out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
+    ld = out_ld if out_ld is not None else (out.shape[-1] if mode != EPI_HEADS else 0)
+
+    final = None
+    if ksplit > 1:   # raw fp32 partials now, epilogue in cb_splitk_reduce (what cb_igemm_auto does for a non-Python host)
+        final = (out, bias, rowbias, residual, ld)
+        out = torch.empty((plan.workspace_bytes // 4,), dtype=torch.float32, device=a0.device)
+        bias = rowbias = residual = None
+        ld = cout
+    d.bias = _p(bias)
+    d.rowbias, d.rowbias_ld = _p(rowbias), (rowbias.stride(0) if rowbias is not None else 0)
+    d.residual, d.res_ld = _p(residual), (residual.shape[-1] if residual is not None else 0)
+    d.out, d.out_ld, d.out_f32 = _p(out), ld, int(out.dtype == torch.float32)
+    d.gn_partials = _p(gn_part)
+    if gn_table is not None:
+        assert gn_part is None and ksplit == 1 and (plan.tw * plan.th) % 32 == 0
+        d.gn_partials, d.gn_rows_per_image, d.gn_row_offset = _p(gn_table[0]), gn_table[0].shape[1], gn_table[1]
     # algorithmic work of the reference op: 2 * rows * (taps * cin) * cout (GEGLU projects to 2 * cout columns)
     _launch("cb_igemm", lambda: _lib.load().cb_igemm(C.byref(d), _stream()),
             flops=2.0 * rows * len(dw) * (c0 + c1) * ncols if algo_flops is None else algo_flops,

@@ -11,7 +11,9 @@
  *  - every call enqueues work on `stream` and returns immediately (no synchronisation, no allocation ->
  *    CUDA-graph capturable);
  *  - return value: 0 = ok, negative = error (cb_last_error() gives a thread-local message);
- *  - activations are NHWC bf16 ("pixel rows x channels"), statistics / latents / schedules are fp32.
+ *  - activations are NHWC in the build's 16-bit type ("pixel rows x channels": fp16 in libcremage_b200_fp16.so -- the
+ *    default, the reference's own GPU precision -- bf16 in libcremage_b200_bf16.so; cb_act_dtype() tells which; "bf16"
+ *    in the comments below stands for that type), statistics / latents / schedules are fp32.
  */
 #ifndef CREMAGE_B200_H_
 #define CREMAGE_B200_H_
@@ -104,6 +106,31 @@ typedef struct cb_igemm_desc {
 } cb_igemm_desc;
 
 int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
+
+/* Tiling policy inside the library (SURVEY 8b "plan" entries): a host fills the PROBLEM fields of a cb_igemm_desc and
+ * leaves the tiling fields at 0 -- tw/th/tn, bn, nsub, ksplit: 0 = choose; cta_pair: 0 = choose, 1 = CTA pairs,
+ * -1 = single CTAs; ksplit: 1 = never split -- cb_igemm_plan reports what the library would run on the current device:
+ * the 128-row pixel tile, the N tile, CTA pairs (tcgen05 cta_group::2), the dual-N schedule, split-K by tap groups
+ * and the fp32 workspace a split needs; whether the launch can write fused GroupNorm partials and how many rows per
+ * image its partial table has.  Environment knobs: CB_PAIR, CB_PAIR_MIN_K_CHUNKS, CB_GEGLU_PAIR, CB_SPLITK, CB_GN_FUSE,
+ * CB_GN_FUSE_MIN_K_CHUNKS, CB_GN_FUSE_MIN_BYTES. */
+typedef struct cb_igemm_plan_t {
+  int tw, th, tn;
+  int bn, cta_pair, nsub, ksplit;
+  int64_t m_tiles;
+  int64_t workspace_bytes;      /* fp32 [ksplit][rows][cout] partials of a split-K launch, 0 otherwise */
+  int gn_fusable;               /* cb_igemm_desc.gn_partials may be set for this launch */
+  int64_t gn_rows_per_image;    /* rows per image of its partial table: fp32 [n][rows][2][cout/2] */
+} cb_igemm_plan_t;
+int cb_igemm_plan(const cb_igemm_desc* d, cb_igemm_plan_t* plan);
+/* plan + run: cb_igemm with the library's tiling and, for a split-K plan, cb_splitk_reduce applying the descriptor's
+ * bias / row bias / residual.  `workspace` (device, >= cb_igemm_plan().workspace_bytes; may be NULL when that is 0). */
+int cb_igemm_auto(const cb_igemm_desc* d, void* workspace, int64_t workspace_bytes, cudaStream_t stream);
+
+/* weight repacking on the device: fp32 OIHW conv weight (or [O][I] linear weight, kh = kw = 1), input channels split
+ * into two sources c0 | c1 (c1 = 0: one source) -> 16-bit [cout][kh*kw][ceil64(c0) | ceil64(c1)], K-major, zero padded:
+ * the `wgt` layout of cb_igemm_desc.  Done once per checkpoint load. */
+int cb_pack_weight(const float* w, int64_t cout, int64_t c0, int64_t c1, int taps, void* out, cudaStream_t stream);
 
 /* fold the fp32 partials of a split-K cb_igemm in split order (deterministic) and apply the epilogue:
  * out[r][c] = sum_s part[s][r][c] + bias[c] + rowbias[r / rows_per_image][c] + residual[r][c]  -> 16-bit */

@@ -47,7 +47,8 @@ def test_cuda_controlled_unet_vs_reference_golden():
     m.load_state_dict(O.make_weights(O.unet_param_shapes(O.TINY_UNET), seed=100), strict=True)
     m = m.cuda().eval()
     x, t, ctx = x.cuda(), t.cuda(), ctx.cuda()
-    tol = 2e-2 * max(float(np.abs(g["out_all"]).max()), 1.0)
+    from tests._models import tol as _tol
+    tol = _tol(2e-2) * max(float(np.abs(g["out_all"]).max()), 1.0)
 
     lst = [c.cuda() for c in control]
     out_all = m(x, t, context=ctx, control=lst)

@@ -16,7 +16,7 @@ def test_gpu_tier_under_the_bf16_build():
     if os.environ.get("CREMAGE_B200_DTYPE", "fp16").lower() == "bf16":
         pytest.skip("already running under the bf16 build")
     env = dict(os.environ, CREMAGE_B200_DTYPE="bf16", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-p", "no:cacheprovider",
            "--deselect", "tests/test_gpu_bf16_build.py::test_gpu_tier_under_the_bf16_build", "-s"]
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
     tail = r.stdout[-6000:]
