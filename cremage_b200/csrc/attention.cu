@@ -57,6 +57,7 @@ template <bool USE_ONES>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnParams p) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();  // swizzled tiles need a 1024-byte aligned base
@@ -118,6 +119,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // the set-up above overlaps the previous kernel; global memory is only touched from here on
   auto tS = [&](int w) { return tmem_base + uint32_t(w) * 128u; };
   auto tO = [&](int w) { return tmem_base + uint32_t(p.nwg) * 128u + uint32_t(w) * uint32_t(p.dpad); };
   // P: 128 rows x 128 16-bit values = 64 columns; its own region when TMEM has room, else the first half of S
@@ -469,8 +471,8 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   const int rows_per_item = p.nwg * ATT_BM;
   const long long items = ((nq + rows_per_item - 1) / rows_per_item) * bh;
   dim3 grid((unsigned)(items < num_sms ? items : num_sms));   // persistent: one CTA per SM walks the work items
-  if (p.use_ones) attention_kernel<true><<<grid, ATT_THREADS, smem, stream>>>(mq, mk, mv, p);
-  else attention_kernel<false><<<grid, ATT_THREADS, smem, stream>>>(mq, mk, mv, p);
+  if (p.use_ones) (void)cb::launch_k(attention_kernel<true>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
+  else (void)cb::launch_k(attention_kernel<false>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

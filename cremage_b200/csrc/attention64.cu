@@ -77,6 +77,7 @@ template <bool USE_ONES>
 __global__ void __launch_bounds__(A64_THREADS, 1)
 attention64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const Attn64Params p) {
+  pdl_launch_dependents();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   if (base & 1023u) __trap();
@@ -136,6 +137,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // the set-up above overlaps the previous kernel; global memory is only touched from here on
   auto tS = [&](int w) { return tmem_base + uint32_t(w) * 64u; };
   auto tP = [&](int w) { return tmem_base + 192u + uint32_t(w) * 32u; };       // 64 16-bit values = 32 columns
   auto tO = [&](int w) { return tmem_base + 288u + uint32_t(w) * 64u; };
@@ -464,8 +466,8 @@ int launch_attention64(const void* q, int64_t q_ld, const void* k, int64_t k_ld,
   const int rows_per_item = nt * A64_BM;
   const long long items = ((nq + rows_per_item - 1) / rows_per_item) * batch * heads;
   dim3 grid((unsigned)(items < num_sms ? items : num_sms));
-  if (use_ones) attention64_kernel<true><<<grid, A64_THREADS, smem, stream>>>(mq, mk, mv, p);
-  else attention64_kernel<false><<<grid, A64_THREADS, smem, stream>>>(mq, mk, mv, p);
+  if (use_ones) (void)cb::launch_k(attention64_kernel<true>, dim3(grid), dim3(A64_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
+  else (void)cb::launch_k(attention64_kernel<false>, dim3(grid), dim3(A64_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

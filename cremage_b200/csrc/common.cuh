@@ -67,6 +67,37 @@ int make_tmap_act(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                    const uint64_t* strides_elems, const uint32_t* box, int swizzle_bytes = 128);
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (CB_PDL=0 turns it off), signals `launch_dependents` as its first
+// instruction and executes `griddepcontrol.wait` before its first access to global memory.  The next kernel of the
+// stream -- also inside a captured CUDA graph -- is then scheduled onto SMs as they drain and runs its prologue
+// (barrier init, tensor-map prefetch, TMEM allocation, index arithmetic) under the tail of this one; `wait` returns
+// once the whole preceding grid has completed and its writes are visible, so data dependencies are unchanged.
+// What it buys is per-node latency: the small-batch regime (UNet batch 2: ~350 nodes of a few microseconds each).
+// ----------------------------------------------------------------------------------------------
+bool pdl_enabled();   // runtime.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = grid;
+  lc.blockDim = block;
+  lc.dynamicSmemBytes = smem;
+  lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// simple kernels: both at the top
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+#endif
+
+// ----------------------------------------------------------------------------------------------
 // small device utilities
 // ----------------------------------------------------------------------------------------------
 CB_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

@@ -10,6 +10,7 @@ namespace cb {
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, long long n, int c, long long hw, int c_pad, float scale,
                                     act_t* __restrict__ dst) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * hw) return;
   const long long b = i / hw, p = i - b * hw;
@@ -25,6 +26,7 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, long long n, int 
 __global__ void pointwise_nchw_to_nhwc_kernel(const float* __restrict__ src, long long n, int c, long long hw,
                                               const float* __restrict__ w, const float* __restrict__ b, int cout,
                                               int c_pad, float scale, act_t* __restrict__ dst) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * hw) return;
   const long long bi = i / hw, p = i - bi * hw;
@@ -47,6 +49,7 @@ __global__ void pointwise_nchw_to_nhwc_kernel(const float* __restrict__ src, lon
 template <typename T>
 __global__ void add_nchw_to_nhwc_kernel(const act_t* __restrict__ base, const T* __restrict__ ctrl, int c, long long hw,
                                         act_t* __restrict__ dst) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const long long b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -71,6 +74,7 @@ __global__ void add_nchw_to_nhwc_kernel(const act_t* __restrict__ base, const T*
 template <typename T>
 __global__ void nchw_to_nhwc_tiled_kernel(const T* __restrict__ src, int c, long long hw, int c_pad, float scale,
                                           act_t* __restrict__ dst) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const long long b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -91,6 +95,7 @@ __global__ void nchw_to_nhwc_tiled_kernel(const T* __restrict__ src, int c, long
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int c, long long hw, long long c_ld,
                                     float* __restrict__ dst) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const long long b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -111,6 +116,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int c, long long 
 // nearest 2x upsample, one thread per 16-byte channel vector of an OUTPUT pixel
 __global__ void upsample2x_kernel(const uint4* __restrict__ src, long long n, int h, int w, int cv,
                                   uint4* __restrict__ dst) {
+  pdl_prologue();
   const long long total = n * (2LL * h) * (2LL * w) * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = int(i % cv);
@@ -126,6 +132,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ src, long long n, in
 // parity split: dst[2*ph+pw][n][h/2][w/2][c] = src[n][2y+ph][2x+pw][c]
 __global__ void parity_split_kernel(const uint4* __restrict__ src, long long n, int h, int w, int cv,
                                     uint4* __restrict__ dst) {
+  pdl_prologue();
   const long long total = n * h * w * cv;
   const int h2 = h >> 1, w2 = w >> 1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -144,6 +151,7 @@ __global__ void parity_split_kernel(const uint4* __restrict__ src, long long n, 
 // on the host with the reference's own expression so it is bit-identical to the reference's.
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, long long n, int dim,
                                           const float* __restrict__ freqs, act_t* __restrict__ out) {
+  pdl_prologue();
   const int half = dim / 2;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * half) return;
@@ -160,6 +168,7 @@ template <int CIN>
 __global__ void conv3x3_small_cin_kernel(const act_t* __restrict__ src, long long n, int h, int w, int cin_ld,
                                          const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
                                          act_t* __restrict__ out) {
+  pdl_prologue();
   const int cg = cout >> 3;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * h * w * cg) return;
@@ -201,6 +210,7 @@ __global__ void conv3x3_small_cin_kernel(const act_t* __restrict__ src, long lon
 
 __global__ void silu_add_kernel(const act_t* __restrict__ x, const act_t* __restrict__ add,
                                 long long count, act_t* __restrict__ out) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   float v = from_act(x[i]);
@@ -214,6 +224,7 @@ __global__ void silu_add_kernel(const act_t* __restrict__ x, const act_t* __rest
 __global__ void diag_gaussian_kernel(const float* __restrict__ moments, const float* __restrict__ noise, long long n,
                                      long long c, long long hw, float scale, float* __restrict__ mean_out,
                                      float* __restrict__ std_out, float* __restrict__ sample_out) {
+  pdl_prologue();
   const long long total = n * c * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long img = i / (c * hw), rem = i - img * (c * hw);
@@ -230,6 +241,7 @@ __global__ void diag_gaussian_kernel(const float* __restrict__ moments, const fl
 // clamped at 0; neighbours clamped at the last index), fp32 planes [planes][h][w] -> [planes][h*f][w*f]
 __global__ void bilinear_upsample_kernel(const float* __restrict__ src, long long planes, int h, int w, int f,
                                          float* __restrict__ dst) {
+  pdl_prologue();
   const int oh = h * f, ow = w * f;
   const long long total = planes * oh * ow;
   const float rs = 1.f / float(f);
@@ -253,6 +265,7 @@ __global__ void bilinear_upsample_kernel(const float* __restrict__ src, long lon
 
 __global__ void image_to_u8_kernel(const float* __restrict__ src, long long npix, long long c_ld,
                                    uint8_t* __restrict__ dst) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
 #pragma unroll
@@ -275,14 +288,14 @@ extern "C" int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_
   if (c_pad <= 16) {
     const long long total = n * hw;
     const unsigned grid = (unsigned)((total + 255) / 256);
-    if (src_dtype == 0) nchw_to_nhwc_kernel<float><<<grid, 256, 0, stream>>>((const float*)src, n, (int)c, hw, (int)c_pad, scale, D);
-    else if (src_dtype == 1) nchw_to_nhwc_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)src, n, (int)c, hw, (int)c_pad, scale, D);
-    else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)src, n, (int)c, hw, (int)c_pad, scale, D);
+    if (src_dtype == 0) (void)cb::launch_k(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(256), (size_t)(0), stream, (const float*)src, n, (int)c, hw, (int)c_pad, scale, D);
+    else if (src_dtype == 1) (void)cb::launch_k(nchw_to_nhwc_kernel<__half>, dim3(grid), dim3(256), (size_t)(0), stream, (const __half*)src, n, (int)c, hw, (int)c_pad, scale, D);
+    else (void)cb::launch_k(nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(grid), dim3(256), (size_t)(0), stream, (const __nv_bfloat16*)src, n, (int)c, hw, (int)c_pad, scale, D);
   } else {
     dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c_pad + 31) / 32), (unsigned)n), block(32, 8);
-    if (src_dtype == 0) nchw_to_nhwc_tiled_kernel<float><<<grid, block, 0, stream>>>((const float*)src, (int)c, hw, (int)c_pad, scale, D);
-    else if (src_dtype == 1) nchw_to_nhwc_tiled_kernel<__half><<<grid, block, 0, stream>>>((const __half*)src, (int)c, hw, (int)c_pad, scale, D);
-    else nchw_to_nhwc_tiled_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)src, (int)c, hw, (int)c_pad, scale, D);
+    if (src_dtype == 0) (void)cb::launch_k(nchw_to_nhwc_tiled_kernel<float>, dim3(grid), dim3(block), (size_t)(0), stream, (const float*)src, (int)c, hw, (int)c_pad, scale, D);
+    else if (src_dtype == 1) (void)cb::launch_k(nchw_to_nhwc_tiled_kernel<__half>, dim3(grid), dim3(block), (size_t)(0), stream, (const __half*)src, (int)c, hw, (int)c_pad, scale, D);
+    else (void)cb::launch_k(nchw_to_nhwc_tiled_kernel<__nv_bfloat16>, dim3(grid), dim3(block), (size_t)(0), stream, (const __nv_bfloat16*)src, (int)c, hw, (int)c_pad, scale, D);
   }
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
@@ -296,9 +309,9 @@ extern "C" int cb_add_nchw_to_nhwc(const void* base, const void* ctrl, int ctrl_
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
   auto B = (const act_t*)base;
   auto D = (act_t*)dst;
-  if (ctrl_dtype == 0) add_nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(B, (const float*)ctrl, (int)c, hw, D);
-  else if (ctrl_dtype == 1) add_nchw_to_nhwc_kernel<__half><<<grid, block, 0, stream>>>(B, (const __half*)ctrl, (int)c, hw, D);
-  else add_nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(B, (const __nv_bfloat16*)ctrl, (int)c, hw, D);
+  if (ctrl_dtype == 0) (void)cb::launch_k(add_nchw_to_nhwc_kernel<float>, dim3(grid), dim3(block), (size_t)(0), stream, B, (const float*)ctrl, (int)c, hw, D);
+  else if (ctrl_dtype == 1) (void)cb::launch_k(add_nchw_to_nhwc_kernel<__half>, dim3(grid), dim3(block), (size_t)(0), stream, B, (const __half*)ctrl, (int)c, hw, D);
+  else (void)cb::launch_k(add_nchw_to_nhwc_kernel<__nv_bfloat16>, dim3(grid), dim3(block), (size_t)(0), stream, B, (const __nv_bfloat16*)ctrl, (int)c, hw, D);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -310,7 +323,7 @@ extern "C" int cb_pointwise_nchw_to_nhwc(const float* src, int64_t n, int64_t c,
   CB_REQUIRE(src && w && dst && n > 0 && hw > 0, "cb_pointwise_nchw_to_nhwc: bad arguments");
   CB_REQUIRE(c > 0 && c <= 16 && cout > 0 && cout <= c_pad && c_pad <= 16, "cb_pointwise_nchw_to_nhwc: c, cout, c_pad must be <= 16");
   const long long total = n * hw;
-  pointwise_nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, n, (int)c, hw, w, b, (int)cout, (int)c_pad, scale, (act_t*)dst);
+  (void)cb::launch_k(pointwise_nchw_to_nhwc_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), stream, src, n, (int)c, hw, w, b, (int)cout, (int)c_pad, scale, (act_t*)dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -320,8 +333,8 @@ extern "C" int cb_nhwc_to_nchw_f32(const void* src, int src_f32, int64_t n, int6
                                    float* dst, cudaStream_t stream) {
   CB_REQUIRE(src && dst && n > 0 && c > 0 && hw > 0 && c_ld >= c, "cb_nhwc_to_nchw_f32: bad arguments");
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
-  if (src_f32) nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const float*)src, (int)c, hw, c_ld, dst);
-  else nhwc_to_nchw_kernel<act_t><<<grid, block, 0, stream>>>((const act_t*)src, (int)c, hw, c_ld, dst);
+  if (src_f32) (void)cb::launch_k(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(block), (size_t)(0), stream, (const float*)src, (int)c, hw, c_ld, dst);
+  else (void)cb::launch_k(nhwc_to_nchw_kernel<act_t>, dim3(grid), dim3(block), (size_t)(0), stream, (const act_t*)src, (int)c, hw, c_ld, dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -339,7 +352,7 @@ extern "C" int cb_upsample2x_nhwc(const void* src, int64_t n, int64_t h, int64_t
                                   cudaStream_t stream) {
   CB_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "cb_upsample2x_nhwc: bad arguments");
   const long long total = n * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const uint4*)src, n, (int)h, (int)w, (int)(c / 8), (uint4*)dst);
+  (void)cb::launch_k(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, (const uint4*)src, n, (int)h, (int)w, (int)(c / 8), (uint4*)dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -350,7 +363,7 @@ extern "C" int cb_parity_split_nhwc(const void* src, int64_t n, int64_t h, int64
   CB_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && h % 2 == 0 && w % 2 == 0,
              "cb_parity_split_nhwc: bad arguments (even h, w; c %% 8 == 0)");
   const long long total = n * h * w * (c / 8);
-  parity_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const uint4*)src, n, (int)h, (int)w, (int)(c / 8), (uint4*)dst);
+  (void)cb::launch_k(parity_split_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, (const uint4*)src, n, (int)h, (int)w, (int)(c / 8), (uint4*)dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -360,7 +373,7 @@ extern "C" int cb_timestep_embedding(const float* t, int64_t n, int dim, const f
                                      cudaStream_t stream) {
   CB_REQUIRE(t && freqs && out && n > 0 && dim >= 2, "cb_timestep_embedding: bad arguments");
   const long long total = n * (dim / 2);
-  timestep_embedding_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(t, n, dim, freqs, (act_t*)out);
+  (void)cb::launch_k(timestep_embedding_kernel, dim3((unsigned)((total + 127) / 128)), dim3(128), (size_t)(0), stream, t, n, dim, freqs, (act_t*)out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -376,10 +389,10 @@ extern "C" int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64
   auto S = (const act_t*)src;
   auto O = (act_t*)out;
   switch (cin) {
-    case 3: conv3x3_small_cin_kernel<3><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
-    case 4: conv3x3_small_cin_kernel<4><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
-    case 8: conv3x3_small_cin_kernel<8><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
-    case 9: conv3x3_small_cin_kernel<9><<<grid, 256, 0, stream>>>(S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
+    case 3: (void)cb::launch_k(conv3x3_small_cin_kernel<3>, dim3(grid), dim3(256), (size_t)(0), stream, S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
+    case 4: (void)cb::launch_k(conv3x3_small_cin_kernel<4>, dim3(grid), dim3(256), (size_t)(0), stream, S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
+    case 8: (void)cb::launch_k(conv3x3_small_cin_kernel<8>, dim3(grid), dim3(256), (size_t)(0), stream, S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
+    case 9: (void)cb::launch_k(conv3x3_small_cin_kernel<9>, dim3(grid), dim3(256), (size_t)(0), stream, S, n, (int)h, (int)w, (int)cin_ld, wgt, bias, (int)cout, O); break;
     default: CB_REQUIRE(false, "cb_conv3x3_small_cin: cin %d unsupported (3, 4, 8, 9)", cin);
   }
   CB_CHECK_CUDA(cudaGetLastError());
@@ -389,7 +402,7 @@ extern "C" int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64
 
 extern "C" int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream) {
   CB_REQUIRE(x && out && count > 0, "cb_silu_add: bad arguments");
-  silu_add_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>((const act_t*)x, (const act_t*)add, count, (act_t*)out);
+  (void)cb::launch_k(silu_add_kernel, dim3((unsigned)((count + 255) / 256)), dim3(256), (size_t)(0), stream, (const act_t*)x, (const act_t*)add, count, (act_t*)out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -398,7 +411,7 @@ extern "C" int cb_silu_add(const void* x, const void* add, int64_t count, void* 
 extern "C" int cb_diag_gaussian(const float* moments, const float* noise, int64_t n, int64_t c, int64_t hw, float scale,
                                 float* mean_out, float* std_out, float* sample_out, cudaStream_t stream) {
   CB_REQUIRE(moments && n > 0 && c > 0 && hw > 0 && (mean_out || std_out || sample_out), "cb_diag_gaussian: bad arguments");
-  diag_gaussian_kernel<<<grid_for(n * c * hw, 256), 256, 0, stream>>>(moments, noise, n, c, hw, scale == 0.f ? 1.f : scale,
+  (void)cb::launch_k(diag_gaussian_kernel, dim3(grid_for(n * c * hw, 256)), dim3(256), (size_t)(0), stream, moments, noise, n, c, hw, scale == 0.f ? 1.f : scale,
                                                                      mean_out, std_out, sample_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
@@ -409,7 +422,7 @@ extern "C" int cb_bilinear_upsample_f32(const float* src, int64_t planes, int64_
                                        cudaStream_t stream) {
   CB_REQUIRE(src && dst && planes > 0 && h > 0 && w > 0 && factor >= 1, "cb_bilinear_upsample_f32: bad arguments");
   const long long total = planes * h * factor * w * factor;
-  bilinear_upsample_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, planes, (int)h, (int)w, factor, dst);
+  (void)cb::launch_k(bilinear_upsample_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, src, planes, (int)h, (int)w, factor, dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -418,7 +431,7 @@ extern "C" int cb_bilinear_upsample_f32(const float* src, int64_t planes, int64_
 extern "C" int cb_image_to_u8(const void* src, int64_t n, int64_t hw, int64_t c_ld, uint8_t* dst, cudaStream_t stream) {
   CB_REQUIRE(src && dst && n > 0 && hw > 0 && c_ld >= 3, "cb_image_to_u8: bad arguments");
   const long long npix = n * hw;
-  image_to_u8_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>((const float*)src, npix, c_ld, dst);
+  (void)cb::launch_k(image_to_u8_kernel, dim3((unsigned)((npix + 255) / 256)), dim3(256), (size_t)(0), stream, (const float*)src, npix, c_ld, dst);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -429,6 +442,7 @@ extern "C" int cb_image_to_u8(const void* src, int64_t n, int64_t hw, int64_t c_
 // ----------------------------------------------------------------------------------------------------------------
 namespace cb {
 __global__ void pack_weight_kernel(const float* __restrict__ w, long long cout, int c0, int c1, int taps, act_t* __restrict__ out) {
+  pdl_prologue();
   const int p0 = (c0 + 63) / 64 * 64, p1 = (c1 + 63) / 64 * 64;
   const long long kcols = (long long)taps * (p0 + p1), total = cout * kcols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -447,7 +461,7 @@ extern "C" int cb_pack_weight(const float* w, int64_t cout, int64_t c0, int64_t 
   const long long total = cout * (long long)taps * ((c0 + 63) / 64 * 64 + (c1 + 63) / 64 * 64);
   const int threads = 256;
   const long long blocks = (total + threads - 1) / threads;
-  cb::pack_weight_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), threads, 0, stream>>>(w, cout, (int)c0, (int)c1, taps,
+  (void)cb::launch_k(cb::pack_weight_kernel, dim3((unsigned)(blocks < 148 * 16 ? blocks : 148 * 16)), dim3(threads), (size_t)(0), stream, w, cout, (int)c0, (int)c1, taps,
                                                                                                     (cb::act_t*)out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);

@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
              const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
              const __grid_constant__ CUtensorMap mapR, const IGemmKParams p) {
+  pdl_launch_dependents();
   static_assert(!DUAL || TWO, "sub-tile groups exist in pair mode only");
   constexpr int NSUB = DUAL ? 2 : 1;
   constexpr int NACC = DUAL ? 3 : 2;
@@ -422,6 +423,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();   // everything above ran under the previous kernel's tail; from here on global memory is touched
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -897,13 +899,15 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     lc.blockDim = dim3(NUM_THREADS);
     lc.dynamicSmemBytes = smem;
     lc.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    lc.attrs = at; lc.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl_enabled() ? 2 : 1;
     CB_CHECK_CUDA(cudaLaunchKernelEx(&lc, kfn, mapA0, mapA1, mapB, mapO, mapR, p));
   } else {
-    kfn<<<grid, NUM_THREADS, smem, stream>>>(mapA0, mapA1, mapB, mapO, mapR, p);
+    (void)cb::launch_k(kfn, dim3(grid), dim3(NUM_THREADS), (size_t)(smem), stream, mapA0, mapA1, mapB, mapO, mapR, p);
   }
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
@@ -921,6 +925,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
                                      const float* __restrict__ rowbias, long long rowbias_ld, long long rows_per_image,
                                      const act_t* __restrict__ residual, long long res_ld, act_t* __restrict__ out,
                                      long long out_ld) {
+  pdl_prologue();
   const int cv = cout >> 3;
   const long long total = rows * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -968,7 +973,7 @@ extern "C" int cb_splitk_reduce(const float* part, int splits, int64_t rows, int
   const long long total = rows * (cout / 8);
   long long g = (total + 255) / 256;
   if (g > 148LL * 8) g = 148LL * 8;
-  splitk_reduce_kernel<<<(unsigned)g, 256, 0, stream>>>(part, splits, rows * part_ld, rows, (int)cout, part_ld, bias, rowbias,
+  (void)cb::launch_k(splitk_reduce_kernel, dim3((unsigned)g), dim3(256), (size_t)(0), stream, part, splits, rows * part_ld, rows, (int)cout, part_ld, bias, rowbias,
                                                         rowbias_ld, rows_per_image, (const act_t*)residual, res_ld,
                                                         (act_t*)out, out_ld);
   CB_CHECK_CUDA(cudaGetLastError());

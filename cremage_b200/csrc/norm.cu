@@ -69,6 +69,7 @@ __global__ void gn_stats_kernel(const act_t* __restrict__ x0, int c0, const act_
                                 int c1, long long hw, int groups, int P, long long pix_per_cta,
                                 float* __restrict__ stats, float* __restrict__ partials,
                                 unsigned int* __restrict__ counters) {
+  pdl_prologue();
   extern __shared__ float s_part[];  // [2][P][C]
   __shared__ int s_is_last;
   const int C = c0 + c1;
@@ -257,6 +258,7 @@ __global__ void gn_apply_kernel(const act_t* __restrict__ x0, int c0, const act_
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ stats, const float* __restrict__ part0, int S0,
                                 const float* __restrict__ part1, int S1, act_t* __restrict__ out) {
+  pdl_prologue();
   const int C = c0 + c1;
   const int CV = C >> 3;
   const int cv = threadIdx.x % CV;
@@ -308,6 +310,7 @@ gn_apply_tma_kernel(const act_t* __restrict__ x0, int c0, const act_t* __restric
                     int P, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ stats, const float* __restrict__ part0, int S0,
                     const float* __restrict__ part1, int S1, act_t* __restrict__ out) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t gn_ring[];   // [stages][chunk of source 0 | chunk of source 1]
   __shared__ __align__(8) uint64_t s_full[GN_TMA_STAGES];
   constexpr int U = GN_APPLY_UNROLL;
@@ -385,6 +388,7 @@ constexpr int GN_FOLD_THREADS = 256;
 
 __global__ void __launch_bounds__(GN_FOLD_THREADS)
 gn_fold1_kernel(const float* __restrict__ in, int bpi, int W, int S, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ double s_red[GN_FOLD_THREADS];
   const int s = blockIdx.x, n = blockIdx.y;
   const int b_lo = int((long long)s * bpi / S), b_hi = int((long long)(s + 1) * bpi / S);
@@ -431,6 +435,7 @@ __global__ void gn_cluster_kernel(const act_t* __restrict__ x0, int c0, const ac
                                   long long hw, int groups, int gset, int P, int ppc, float eps,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                   act_t* __restrict__ out) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t gn_smem[];
   const int C = c0 + c1;
   const int gs = C / groups;
@@ -552,6 +557,7 @@ template <int MAXV>
 __global__ void layernorm_kernel(const act_t* __restrict__ x, long long rows, int C, float eps,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  act_t* __restrict__ out) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -607,6 +613,7 @@ __global__ void layernorm_kernel(const act_t* __restrict__ x, long long rows, in
 template <bool SRC_F32>
 __global__ void softmax_rows_kernel(const void* __restrict__ src, long long src_ld, act_t* __restrict__ dst,
                                     long long dst_ld, long long cols, float scale) {
+  pdl_prologue();
   extern __shared__ float s_row[];
   __shared__ float red[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
@@ -727,14 +734,14 @@ int launch_gn_apply(const void* x0, int64_t c0, const void* x1, int64_t c1, int6
       cfg = true;
     }
     dim3 grid(gn_apply_ctas(k, GN_TMA_THREADS, smem, n, hw, P), (unsigned)n);
-    k<<<grid, GN_TMA_THREADS, smem, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw, groups, P, eps, gamma,
+    (void)cb::launch_k(k, dim3(grid), dim3(GN_TMA_THREADS), (size_t)(smem), stream, (const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw, groups, P, eps, gamma,
                                               beta, stats, p0, S0, p1, S1, (act_t*)out);
   } else {
     int P = 1;
     const int threads = gn_apply_shape(C, hw, &P);
     auto k = silu ? gn_apply_kernel<true, PARTS> : gn_apply_kernel<false, PARTS>;
     dim3 grid(gn_apply_ctas(k, threads, 0, n, hw, P), (unsigned)n);
-    k<<<grid, threads, 0, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw, groups, P, eps, gamma, beta, stats,
+    (void)cb::launch_k(k, dim3(grid), dim3(threads), (size_t)(0), stream, (const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw, groups, P, eps, gamma, beta, stats,
                                     p0, S0, p1, S1, (act_t*)out);
   }
   CB_CHECK_CUDA(cudaGetLastError());
@@ -797,10 +804,12 @@ extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int
         lc.blockDim = dim3((unsigned)threads);
         lc.dynamicSmemBytes = smem;
         lc.stream = stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = GN_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        lc.attrs = at; lc.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = pdl_enabled() ? 2 : 1;
         CB_CHECK_CUDA(cudaLaunchKernelEx(&lc, gn_cluster_kernel, (const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1,
                                          (long long)hw, groups, gset, P, ppc, eps, gamma, beta, silu, (act_t*)out));
         CB_LAUNCHED(1);
@@ -820,7 +829,7 @@ extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int
     configured = true;
   }
   dim3 grid((unsigned)g.splits, (unsigned)n);
-  gn_stats_kernel<<<grid, g.threads, g.smem, stream>>>((const act_t*)x0, (int)c0, (const act_t*)x1,
+  (void)cb::launch_k(gn_stats_kernel, dim3(grid), dim3(g.threads), (size_t)(g.smem), stream, (const act_t*)x0, (int)c0, (const act_t*)x1,
                                                        (int)c1, hw, groups, g.P, g.pix_per_cta, stats, partials, counters);
   CB_CHECK_CUDA(cudaGetLastError());
   {
@@ -853,12 +862,12 @@ extern "C" int cb_groupnorm_from_partials(const void* x0, int64_t c0, const floa
   int S0 = (int)bpi0, S1 = (int)bpi1, launches = 1;
   float* ws = stats;
   if (bpi0 > GN_PART_ROWS) {
-    gn_fold1_kernel<<<dim3(GN_PART_ROWS, (unsigned)n), GN_FOLD_THREADS, 0, stream>>>(part0, (int)bpi0, (int)c0, GN_PART_ROWS, ws);
+    (void)cb::launch_k(gn_fold1_kernel, dim3(GN_PART_ROWS, (unsigned)n), dim3(GN_FOLD_THREADS), (size_t)0, stream, part0, (int)bpi0, (int)c0, GN_PART_ROWS, ws);
     CB_CHECK_CUDA(cudaGetLastError());
     p0 = ws; S0 = GN_PART_ROWS; ws += (size_t)n * GN_PART_ROWS * c0; ++launches;
   }
   if (c1 > 0 && bpi1 > GN_PART_ROWS) {
-    gn_fold1_kernel<<<dim3(GN_PART_ROWS, (unsigned)n), GN_FOLD_THREADS, 0, stream>>>(part1, (int)bpi1, (int)c1, GN_PART_ROWS, ws);
+    (void)cb::launch_k(gn_fold1_kernel, dim3(GN_PART_ROWS, (unsigned)n), dim3(GN_FOLD_THREADS), (size_t)0, stream, part1, (int)bpi1, (int)c1, GN_PART_ROWS, ws);
     CB_CHECK_CUDA(cudaGetLastError());
     p1 = ws; S1 = GN_PART_ROWS; ++launches;
   }
@@ -881,10 +890,10 @@ extern "C" int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, c
   const int maxv = int((c / 8 + 31) / 32);
   auto X = (const act_t*)x;
   auto O = (act_t*)out;
-  if (maxv <= 2)       layernorm_kernel<2><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
-  else if (maxv <= 4)  layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
-  else if (maxv <= 8)  layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
-  else                 layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(X, rows, (int)c, eps, gamma, beta, O);
+  if (maxv <= 2)       (void)cb::launch_k(layernorm_kernel<2>, dim3(grid), dim3(warps * 32), (size_t)(0), stream, X, rows, (int)c, eps, gamma, beta, O);
+  else if (maxv <= 4)  (void)cb::launch_k(layernorm_kernel<4>, dim3(grid), dim3(warps * 32), (size_t)(0), stream, X, rows, (int)c, eps, gamma, beta, O);
+  else if (maxv <= 8)  (void)cb::launch_k(layernorm_kernel<8>, dim3(grid), dim3(warps * 32), (size_t)(0), stream, X, rows, (int)c, eps, gamma, beta, O);
+  else                 (void)cb::launch_k(layernorm_kernel<16>, dim3(grid), dim3(warps * 32), (size_t)(0), stream, X, rows, (int)c, eps, gamma, beta, O);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -902,8 +911,8 @@ extern "C" int cb_softmax_rows(const void* src, int src_f32, int64_t src_ld, voi
     CB_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  if (src_f32) softmax_rows_kernel<true><<<(unsigned)rows, 256, smem, stream>>>(src, src_ld, (act_t*)dst, dst_ld, cols, scale);
-  else softmax_rows_kernel<false><<<(unsigned)rows, 256, smem, stream>>>(src, src_ld, (act_t*)dst, dst_ld, cols, scale);
+  if (src_f32) (void)cb::launch_k(softmax_rows_kernel<true>, dim3((unsigned)rows), dim3(256), (size_t)(smem), stream, src, src_ld, (act_t*)dst, dst_ld, cols, scale);
+  else (void)cb::launch_k(softmax_rows_kernel<false>, dim3((unsigned)rows), dim3(256), (size_t)(smem), stream, src, src_ld, (act_t*)dst, dst_ld, cols, scale);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;

@@ -3,6 +3,7 @@
 // dependency on libcuda (it must load on a GPU-less host for the symbol tests).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 
 #include "common.cuh"
@@ -18,6 +19,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CB_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 int cuda_fail(cudaError_t e, const char* what) {

@@ -13,6 +13,7 @@
 namespace cb {
 
 __global__ void cfg_scale_input_kernel(const float4* __restrict__ x, long long nvec, float c_in, float4* __restrict__ out) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float4 v = x[i];
     v.x *= c_in; v.y *= c_in; v.z *= c_in; v.w *= c_in;
@@ -44,6 +45,7 @@ template <int V> CB_DEVINL void stv(float* __restrict__ p, long long i, const Vf
 template <int V>
 __global__ void axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float b, long long nvec,
                              float* __restrict__ out) {
+  pdl_prologue();
   CB_VEC_LOOP(i, nvec) {
     const Vf<V> xv = ldv<V>(x, i);
     Vf<V> o;
@@ -63,6 +65,7 @@ __global__ void axpby_kernel(const float* __restrict__ x, float a, const float* 
 template <int V>
 __global__ void cfg_mix_kernel(const float* __restrict__ u, const float* __restrict__ c, float s, long long nvec,
                                float* __restrict__ out) {
+  pdl_prologue();
   CB_VEC_LOOP(i, nvec) {
     const Vf<V> uv = ldv<V>(u, i), cv = ldv<V>(c, i);
     Vf<V> o;
@@ -87,6 +90,7 @@ __global__ void step_euler_ancestral_kernel(const float* __restrict__ x, const f
                                             const float* __restrict__ ec, const float* __restrict__ noise,
                                             long long nvec, EulerA a, float* __restrict__ x_out,
                                             float* __restrict__ den_out) {
+  pdl_prologue();
   CB_VEC_LOOP(i, nvec) {
     const Vf<V> xv = ldv<V>(x, i), av = ldv<V>(eu, i);
     Vf<V> bv = av, nz = av, xn, dn;
@@ -111,6 +115,7 @@ template <int V>
 __global__ void step_dpmpp_2m_kernel(const float* __restrict__ x, const float* __restrict__ eu,
                                      const float* __restrict__ ec, const float* __restrict__ old_den, long long nvec,
                                      Dpm2m a, float* __restrict__ x_out, float* __restrict__ den_out) {
+  pdl_prologue();
   CB_VEC_LOOP(i, nvec) {
     const Vf<V> xv = ldv<V>(x, i), av = ldv<V>(eu, i);
     Vf<V> bv = av, ov = av, xn, dn;
@@ -134,6 +139,7 @@ template <int V>
 __global__ void step_ddim_kernel(const float* __restrict__ x, const float* __restrict__ eu, const float* __restrict__ ec,
                                  const float* __restrict__ noise, long long nvec, Ddim a, float* __restrict__ x_out,
                                  float* __restrict__ x0_out) {
+  pdl_prologue();
   CB_VEC_LOOP(i, nvec) {
     const Vf<V> xv = ldv<V>(x, i), uv = ldv<V>(eu, i), cv = ldv<V>(ec, i);
     Vf<V> nz = uv, xn, x0;
@@ -179,7 +185,7 @@ extern "C" int cb_cfg_scale_input(const float* x, int64_t per_batch, int64_t b, 
   CB_REQUIRE(x && out && per_batch > 0 && b > 0, "cb_cfg_scale_input: bad arguments");
   const long long total = per_batch * b;
   CB_REQUIRE(total % 4 == 0, "cb_cfg_scale_input: element count must be a multiple of 4");
-  cfg_scale_input_kernel<<<ew_grid(total / 4), 256, 0, stream>>>((const float4*)x, total / 4, c_in, (float4*)out);
+  (void)cb::launch_k(cfg_scale_input_kernel, dim3(ew_grid(total / 4)), dim3(256), (size_t)(0), stream, (const float4*)x, total / 4, c_in, (float4*)out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -188,8 +194,8 @@ extern "C" int cb_cfg_scale_input(const float* x, int64_t per_batch, int64_t b, 
 extern "C" int cb_axpby_f32(const float* x, float a, const float* y, float b, int64_t count, float* out,
                             cudaStream_t stream) {
   CB_REQUIRE(x && out && count > 0, "cb_axpby_f32: bad arguments");
-  if (vec4_ok(count, x, y, out)) axpby_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(x, a, y, b, count / 4, out);
-  else axpby_kernel<1><<<ew_grid(count), 256, 0, stream>>>(x, a, y, b, count, out);
+  if (vec4_ok(count, x, y, out)) (void)cb::launch_k(axpby_kernel<4>, dim3(ew_grid(count / 4)), dim3(256), (size_t)(0), stream, x, a, y, b, count / 4, out);
+  else (void)cb::launch_k(axpby_kernel<1>, dim3(ew_grid(count)), dim3(256), (size_t)(0), stream, x, a, y, b, count, out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -198,8 +204,8 @@ extern "C" int cb_axpby_f32(const float* x, float a, const float* y, float b, in
 extern "C" int cb_cfg_mix_f32(const float* uncond, const float* cond, float scale, int64_t count, float* out,
                               cudaStream_t stream) {
   CB_REQUIRE(uncond && cond && out && count > 0, "cb_cfg_mix_f32: bad arguments");
-  if (vec4_ok(count, uncond, cond, out)) cfg_mix_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(uncond, cond, scale, count / 4, out);
-  else cfg_mix_kernel<1><<<ew_grid(count), 256, 0, stream>>>(uncond, cond, scale, count, out);
+  if (vec4_ok(count, uncond, cond, out)) (void)cb::launch_k(cfg_mix_kernel<4>, dim3(ew_grid(count / 4)), dim3(256), (size_t)(0), stream, uncond, cond, scale, count / 4, out);
+  else (void)cb::launch_k(cfg_mix_kernel<1>, dim3(ew_grid(count)), dim3(256), (size_t)(0), stream, uncond, cond, scale, count, out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -212,9 +218,9 @@ extern "C" int cb_step_euler_ancestral(const float* x, const float* eps_u, const
   CB_REQUIRE(x && eps_u && x_out && count > 0 && (is_denoised || eps_c), "cb_step_euler_ancestral: bad arguments");
   EulerA a{cfg_scale, sigma, sigma_down, sigma_up, is_denoised};
   if (vec4_ok(count, x, eps_u, eps_c, noise, x_out, denoised_out))
-    step_euler_ancestral_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(x, eps_u, eps_c, noise, count / 4, a, x_out, denoised_out);
+    (void)cb::launch_k(step_euler_ancestral_kernel<4>, dim3(ew_grid(count / 4)), dim3(256), (size_t)(0), stream, x, eps_u, eps_c, noise, count / 4, a, x_out, denoised_out);
   else
-    step_euler_ancestral_kernel<1><<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, noise, count, a, x_out, denoised_out);
+    (void)cb::launch_k(step_euler_ancestral_kernel<1>, dim3(ew_grid(count)), dim3(256), (size_t)(0), stream, x, eps_u, eps_c, noise, count, a, x_out, denoised_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -227,9 +233,9 @@ extern "C" int cb_step_dpmpp_2m(const float* x, const float* eps_u, const float*
   CB_REQUIRE(x && eps_u && x_out && count > 0 && (is_denoised || eps_c), "cb_step_dpmpp_2m: bad arguments");
   Dpm2m a{cfg_scale, sigma, ratio, em1, c_new, c_old, is_denoised};
   if (vec4_ok(count, x, eps_u, eps_c, old_denoised, x_out, denoised_out))
-    step_dpmpp_2m_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(x, eps_u, eps_c, old_denoised, count / 4, a, x_out, denoised_out);
+    (void)cb::launch_k(step_dpmpp_2m_kernel<4>, dim3(ew_grid(count / 4)), dim3(256), (size_t)(0), stream, x, eps_u, eps_c, old_denoised, count / 4, a, x_out, denoised_out);
   else
-    step_dpmpp_2m_kernel<1><<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, old_denoised, count, a, x_out, denoised_out);
+    (void)cb::launch_k(step_dpmpp_2m_kernel<1>, dim3(ew_grid(count)), dim3(256), (size_t)(0), stream, x, eps_u, eps_c, old_denoised, count, a, x_out, denoised_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
@@ -241,9 +247,9 @@ extern "C" int cb_step_ddim(const float* x, const float* eps_u, const float* eps
   CB_REQUIRE(x && eps_u && eps_c && x_out && count > 0, "cb_step_ddim: bad arguments");
   Ddim a{cfg_scale, sqrt_at, sqrt_one_minus_at, sqrt_aprev, dir_coef, sigma_t};
   if (vec4_ok(count, x, eps_u, eps_c, noise, x_out, pred_x0_out))
-    step_ddim_kernel<4><<<ew_grid(count / 4), 256, 0, stream>>>(x, eps_u, eps_c, noise, count / 4, a, x_out, pred_x0_out);
+    (void)cb::launch_k(step_ddim_kernel<4>, dim3(ew_grid(count / 4)), dim3(256), (size_t)(0), stream, x, eps_u, eps_c, noise, count / 4, a, x_out, pred_x0_out);
   else
-    step_ddim_kernel<1><<<ew_grid(count), 256, 0, stream>>>(x, eps_u, eps_c, noise, count, a, x_out, pred_x0_out);
+    (void)cb::launch_k(step_ddim_kernel<1>, dim3(ew_grid(count)), dim3(256), (size_t)(0), stream, x, eps_u, eps_c, noise, count, a, x_out, pred_x0_out);
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
