@@ -48,6 +48,8 @@ class IGemmDesc(C.Structure):
         ("out_w_stride", C.c_int64), ("out_h_stride", C.c_int64), ("out_n_stride", C.c_int64),
         ("gn_partials", C.c_void_p),
         ("gn_rows_per_image", C.c_int64), ("gn_row_offset", C.c_int64),
+        ("ln_partials_out", C.c_void_p), ("ln_partials_in", C.c_void_p), ("ln_in_slots", C.c_int),
+        ("ln_dim", C.c_int64), ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
     ]
 
 
@@ -57,7 +59,8 @@ class IGemmPlan(C.Structure):
     _fields_ = [("tw", C.c_int), ("th", C.c_int), ("tn", C.c_int),
                 ("bn", C.c_int), ("cta_pair", C.c_int), ("nsub", C.c_int), ("ksplit", C.c_int),
                 ("m_tiles", C.c_int64), ("workspace_bytes", C.c_int64),
-                ("gn_fusable", C.c_int), ("gn_rows_per_image", C.c_int64)]
+                ("gn_fusable", C.c_int), ("gn_rows_per_image", C.c_int64),
+                ("ln_out_slots", C.c_int), ("ln_foldable", C.c_int)]
 
 
 _i64, _int, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
@@ -93,6 +96,7 @@ SIGNATURES = {
     "cb_cfg_scale_input": [_vp, _i64, _i64, _f32, _vp, _vp],
     "cb_axpby_f32": [_vp, _f32, _vp, _f32, _i64, _vp, _vp],
     "cb_cfg_mix_f32": [_vp, _vp, _f32, _i64, _vp, _vp],
+    "cb_blend_mask_f32": [_vp, _vp, _vp, _i64, _i64, _i64, _int, _vp, _vp],
     "cb_step_euler_ancestral": [_vp, _vp, _vp, _int, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
     "cb_step_dpmpp_2m": [_vp, _vp, _vp, _int, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
     "cb_step_ddim": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],

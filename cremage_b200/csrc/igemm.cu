@@ -76,6 +76,16 @@ struct IGemmKParams {
   // and the sum of squares -> gn_part[n][gn_bpi][2][cout/2], gn_bpi = tiles_w * tiles_h (M tiles per image)
   float* gn_part;
   int gn_bpi, gn_row0;   // rows per image of the table, first row of this launch
+  // fused LayerNorm (staged epilogues).  PRODUCER: per output row and (N tile, epilogue half) the sum and the sum of
+  // squares of the 16-bit rounded outputs -> ln_out[row][ln_out_slots][2].  CONSUMER: the A operand is the UN-normalised
+  // row x; with W' = W diag(gamma) as weights, cs[n] = sum_k W'[n, k] and b' = b + W beta the epilogue computes
+  //   LN(x) W^T + b = rstd * (x W'^T - mean * cs) + b'      (mean / rstd of the row from ln_in[row][ln_in_slots][2])
+  float* ln_out;
+  int ln_out_slots;
+  const float* ln_in;
+  int ln_in_slots;
+  float ln_inv_dim, ln_eps;
+  const float* ln_colsum;
 };
 
 // ---- fused GroupNorm statistics -----------------------------------------------------------------------------------
@@ -299,11 +309,15 @@ CB_DEVINL uint4 ld_shared_v4(uint32_t addr) {
 
 // STAGED epilogue of one 32-column chunk: registers (+bias, +per-image bias, +residual read from the panel) -> the
 // 64B-swizzled panel (row = lane, 16-byte piece j at  j ^ ((lane >> 1) & 3)), ready for the TMA store.
+// LayerNorm fold of a staged launch: lnc = the A rows are un-normalised (rstd / rstd*mean of this thread's row in
+// ln_rs / ln_a, column sums 256 floats behind the bias slice); lnp = accumulate this row's sum / sum of squares of the
+// 16-bit outputs into ls / lq.
+struct LnRow { bool lnc, lnp; float rs, a; };
 template <int EPI, bool STATS>
 __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32_t (&v)[32], const uint32_t (&g)[32],
                                              const float* __restrict__ sbx, const float* __restrict__ sbg,
                                              const float* __restrict__ rowb, bool rowb_ok, int col0, uint32_t panel, int lane,
-                                             bool row_ok, float (&V)[32]) {
+                                             bool row_ok, float (&V)[32], const LnRow& ln, float& ls, float& lq) {
   const uint32_t rowaddr = panel + uint32_t(lane) * 64u;
   const uint32_t sw = uint32_t(lane >> 1) & 3u;
 #pragma unroll
@@ -311,17 +325,34 @@ __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32
     float f[8];
     const float4 b0 = *reinterpret_cast<const float4*>(sbx + 8 * j);
     const float4 b1 = *reinterpret_cast<const float4*>(sbx + 8 * j + 4);
-    f[0] = __uint_as_float(v[8 * j + 0]) + b0.x; f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
-    f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
-    f[4] = __uint_as_float(v[8 * j + 4]) + b1.x; f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
-    f[6] = __uint_as_float(v[8 * j + 6]) + b1.z; f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+    if ((EPI == EPI_PLAIN || EPI == EPI_GEGLU) && ln.lnc) {
+      const float4 c0 = *reinterpret_cast<const float4*>(sbx + 256 + 8 * j);
+      const float4 c1 = *reinterpret_cast<const float4*>(sbx + 256 + 8 * j + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaf(ln.rs, __uint_as_float(v[8 * j + e]), fmaf(-ln.a, cc[e], bb[e]));
+    } else {
+      f[0] = __uint_as_float(v[8 * j + 0]) + b0.x; f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
+      f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
+      f[4] = __uint_as_float(v[8 * j + 4]) + b1.x; f[5] = __uint_as_float(v[8 * j + 5]) + b1.y;
+      f[6] = __uint_as_float(v[8 * j + 6]) + b1.z; f[7] = __uint_as_float(v[8 * j + 7]) + b1.w;
+    }
     const uint32_t addr = rowaddr + ((uint32_t(j) ^ sw) << 4);
     if (EPI == EPI_GEGLU) {
       const float4 g0 = *reinterpret_cast<const float4*>(sbg + 8 * j);
       const float4 g1 = *reinterpret_cast<const float4*>(sbg + 8 * j + 4);
       const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      if (ln.lnc) {
+        const float4 c0 = *reinterpret_cast<const float4*>(sbg + 256 + 8 * j);
+        const float4 c1 = *reinterpret_cast<const float4*>(sbg + 256 + 8 * j + 4);
+        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(__uint_as_float(g[8 * j + e]) + gb[e]);
+        for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(fmaf(ln.rs, __uint_as_float(g[8 * j + e]), fmaf(-ln.a, cc[e], gb[e])));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(__uint_as_float(g[8 * j + e]) + gb[e]);
+      }
     }
     if (EPI == EPI_ROWBIAS) {
       if (rowb_ok && col0 + 8 * j + 8 <= p.cout) {
@@ -349,6 +380,15 @@ __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32
     }
     const uint32_t o0 = pack_act2(f[0], f[1]), o1 = pack_act2(f[2], f[3]), o2 = pack_act2(f[4], f[5]), o3 = pack_act2(f[6], f[7]);
     st_shared_v4(addr, o0, o1, o2, o3);
+    if ((EPI == EPI_PLAIN || EPI == EPI_RES) && ln.lnp && row_ok && col0 + 8 * j < p.cout) {
+      const uint32_t ov[4] = {o0, o1, o2, o3};      // the values as the consumer will read them back
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 t = unpack_act2(ov[e]);
+        ls += t.x + t.y;
+        lq = fmaf(t.x, t.x, fmaf(t.y, t.y, lq));
+      }
+    }
     if (STATS) {
       if (row_ok && col0 + 8 * j < p.cout) gn_accum8(V, 8 * j, o0, o1, o2, o3);
       else gn_accum8(V, 8 * j, 0u, 0u, 0u, 0u);
@@ -385,8 +425,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const uint32_t bres_bar = misc + 48u;
   const uint32_t tmem_slot = misc + 56u;
   auto resid_bar = [&](int ew) { return misc + 64u + 8u * uint32_t(ew); };
-  const uint32_t bias_smem = (misc + 64u + 8u * EPI_WARPS + 15u) & ~15u;  // float[3][256]: a sub-tile's bias slice per accumulator slot
-  const uint32_t gn_smem = bias_smem + 3u * 256u * 4u;   // float[2 tiles][8 chunks][4 quarters][32] (only when gn_part)
+  const uint32_t bias_smem = (misc + 64u + 8u * EPI_WARPS + 15u) & ~15u;  // float[3][512]: per accumulator slot a sub-tile's bias slice [256] | LayerNorm column sums [256]
+  const uint32_t gn_smem = bias_smem + 3u * 512u * 4u;   // float[2 tiles][8 chunks][4 quarters][32] (only when gn_part)
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -581,10 +621,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       }
       // stage this tile's bias slice (overlaps the MMAs of this tile); the named barrier also orders the reuse of
       // the slot against the slowest warp's reads two tiles ago
-      float* sb = sbias_all + buf * 256;
+      float* sb = sbias_all + buf * 512;
       for (int c = threadIdx.x - 64; c < p.bn; c += 32 * EPI_WARPS) {
         const int bc = nt * p.bn + c;
         sb[c] = (p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
+        if (p.ln_in != nullptr) sb[256 + c] = bc < p.bias_len ? __ldg(p.ln_colsum + bc) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
       // fused GroupNorm statistics: every warp has stored the previous tile's chunk totals -> write that tile's row
@@ -601,6 +642,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const bool have = (hh * 32 < ocols) && (nt * ocols + hh * 32 < p.cout);
         if (EPI == EPI_RES && have) { mbar_wait(resid_bar(ew), rphase); rphase ^= 1u; }
         const float* rowb = (EPI == EPI_ROWBIAS) ? (p.rowbias + static_cast<long long>(n < p.n_img ? n : 0) * p.rowbias_ld) : nullptr;
+        LnRow ln{p.ln_in != nullptr, p.ln_out != nullptr, 1.f, 0.f};
+        float ls = 0.f, lq = 0.f;
+        if ((EPI == EPI_PLAIN || EPI == EPI_GEGLU) && ln.lnc && row_ok) {
+          // this row's mean / rstd from the producer's partial sums (fixed slot order: deterministic)
+          const float2* ps = reinterpret_cast<const float2*>(p.ln_in) + row * p.ln_in_slots;
+          float sx = 0.f, sq = 0.f;
+          for (int sl = 0; sl < p.ln_in_slots; ++sl) { const float2 t = __ldg(ps + sl); sx += t.x; sq += t.y; }
+          const float mean = sx * p.ln_inv_dim;
+          const float var = fmaxf(fmaf(-mean, mean, sq * p.ln_inv_dim), 0.f);
+          ln.rs = rsqrtf(var + p.ln_eps);
+          ln.a = ln.rs * mean;
+        }
         int k = 0;
         for (int c = hh * 32; c < ocols; c += 64, ++k) {
           const int col0 = nt * ocols + c;
@@ -612,10 +665,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           const uint32_t panel = my_stg + uint32_t(k) * PANEL_BYTES;
           float V[32];
           if (STATS_OK && do_gn) {
-            staged_chunk<EPI, STATS_OK>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane, row_ok, V);
+            staged_chunk<EPI, STATS_OK>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane, row_ok, V, ln, ls, lq);
             gn_store_chunk(V, lane, gtab + (c >> 5) * 128);
           } else {
-            staged_chunk<EPI, false>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane, row_ok, V);
+            staged_chunk<EPI, false>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane, row_ok, V, ln, ls, lq);
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -623,6 +676,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
             tma_store_4d(&mapO, panel, col0, bxw, bxh, bxn);
             tma_store_commit();
           }
+        }
+        if ((EPI == EPI_PLAIN || EPI == EPI_RES) && ln.lnp && row_ok) {
+          // every (N tile, epilogue half) slot of the row is written, also by a half without a chunk (zeros)
+          reinterpret_cast<float2*>(p.ln_out)[row * p.ln_out_slots + nt * 2 + hh] = make_float2(ls, lq);
         }
       } else {
         // split-K: this work item's fp32 partial goes to its own slab of the workspace
@@ -798,6 +855,18 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   } else if (epi == EPI_PLAIN || epi == EPI_RES || epi == EPI_ROWBIAS) {
     staged = tma_ok && (d->epilogue == CB_EPILOGUE_STAGED || (d->epilogue == CB_EPILOGUE_AUTO && num_k <= 48));
   }
+  if (d->ln_partials_out) {
+    CB_REQUIRE(staged && (epi == EPI_PLAIN || epi == EPI_RES) && ksplit == 1,
+               "cb_igemm: LayerNorm partials come from the staged 16-bit epilogue (bias / residual) of an unsplit launch");
+    p.ln_out = d->ln_partials_out;
+    p.ln_out_slots = 2 * p.n_tiles;
+  }
+  if (d->ln_partials_in) {
+    CB_REQUIRE(staged && (epi == EPI_PLAIN || epi == EPI_GEGLU), "cb_igemm: the LayerNorm fold needs a staged plain or GEGLU epilogue");
+    CB_REQUIRE(d->ln_colsum && d->ln_in_slots > 0 && d->ln_dim > 0 && d->bias, "cb_igemm: the LayerNorm fold needs column sums, a bias, the slot count and the row width");
+    p.ln_in = d->ln_partials_in; p.ln_in_slots = d->ln_in_slots; p.ln_colsum = d->ln_colsum;
+    p.ln_inv_dim = 1.f / float(d->ln_dim); p.ln_eps = d->ln_eps;
+  }
   const int ocols = (epi == EPI_GEGLU) ? d->bn / 2 : d->bn;
   p.npan = staged ? (ocols + 63) / 64 : 0;
   p.pbw = d->tw < 32 ? d->tw : 32;
@@ -829,7 +898,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
 
   // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
   //      that N tile gets several M tiles; otherwise stream A and B through the ring
-  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 768 + 64 + (d->gn_partials ? sizeof(float) * 2048 : 0);
+  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 1536 + 64 + (d->gn_partials ? sizeof(float) * 2048 : 0);
   const size_t b_chunk = (size_t)(two ? d->bn / 2 : d->bn) * 128;
   const size_t res_bytes = (size_t)num_k * b_chunk;
   int resident = 0;

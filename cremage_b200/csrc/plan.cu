@@ -157,6 +157,13 @@ extern "C" int cb_igemm_plan(const cb_igemm_desc* d, cb_igemm_plan_t* plan) {
   plan->gn_fusable = (gn_fuse && ksplit == 1 && d->mode == CB_EPI_LINEAR && !d->out_f32 && d->act == CB_ACT_NONE && oscale == 1.f &&
                       d->cout % 8 == 0 && num_k >= gn_min_k && 2 * rows * d->cout >= gn_min_bytes && (tw * th) % 32 == 0 &&
                       !strided && out_ld == d->cout) ? 1 : 0;
+  // the staged (TMA in / TMA out) epilogue is what carries the LayerNorm fold: small-K 16-bit launches (cb_igemm: AUTO
+  // stages num_k <= 48) and every GEGLU launch
+  const bool staged16 = !d->out_f32 && d->act == CB_ACT_NONE && oscale == 1.f && d->cout % 8 == 0 && out_ld % 8 == 0 && ksplit == 1 &&
+                        (d->epilogue == CB_EPILOGUE_STAGED || (d->epilogue == CB_EPILOGUE_AUTO && num_k <= 48));
+  plan->ln_out_slots = (d->mode == CB_EPI_LINEAR && staged16 && !d->rowbias && !strided) ? int(2 * cdiv(ncols, bn)) : 0;
+  plan->ln_foldable = ((d->mode == CB_EPI_LINEAR && staged16 && !d->rowbias && !d->residual) ||
+                       (d->mode == CB_EPI_GEGLU && !d->out_f32 && out_ld % 8 == 0)) ? 1 : 0;
   return CB_OK;
 }
 

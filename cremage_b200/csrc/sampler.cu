@@ -211,6 +211,32 @@ extern "C" int cb_cfg_mix_f32(const float* uncond, const float* cond, float scal
   return CB_OK;
 }
 
+// out = keep * m + (1 - m) * fresh, mask broadcast over the channels when mask_c == 1 (DDIM inpainting,
+// ldm/models/diffusion/ddim.py:171-174: img = img_orig * mask + (1. - mask) * img)
+namespace cb {
+__global__ void blend_mask_kernel(const float* __restrict__ keep, const float* __restrict__ fresh, const float* __restrict__ mask,
+                                  long long total, int c, long long hw, int mask_c, float* __restrict__ out) {
+  pdl_prologue();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long px = i % hw, nc = i / hw;
+    const long long mi = mask_c == 1 ? (nc / c) * hw + px : i;
+    const float m = mask[mi];
+    out[i] = keep[i] * m + (1.f - m) * fresh[i];
+  }
+}
+}  // namespace cb
+
+extern "C" int cb_blend_mask_f32(const float* keep, const float* fresh, const float* mask, int64_t n, int64_t c, int64_t hw,
+                                 int mask_c, float* out, cudaStream_t stream) {
+  CB_REQUIRE(keep && fresh && mask && out && n > 0 && c > 0 && hw > 0 && (mask_c == 1 || mask_c == c), "cb_blend_mask_f32: bad arguments");
+  const long long total = n * c * hw;
+  (void)cb::launch_k(cb::blend_mask_kernel, dim3(ew_grid(total)), dim3(256), (size_t)0, stream, keep, fresh, mask, total, (int)c,
+                     (long long)hw, mask_c, out);
+  CB_CHECK_CUDA(cudaGetLastError());
+  CB_LAUNCHED(1);
+  return CB_OK;
+}
+
 extern "C" int cb_step_euler_ancestral(const float* x, const float* eps_u, const float* eps_c, int is_denoised,
                                        const float* noise, int64_t count, float cfg_scale, float sigma,
                                        float sigma_down, float sigma_up, float* x_out, float* denoised_out,

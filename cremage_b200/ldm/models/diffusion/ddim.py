@@ -59,13 +59,13 @@ class DDIMSampler(object):
                quantize_x0=False, eta=0., mask=None, x0=None, temperature=1., noise_dropout=0., score_corrector=None,
                corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.,
                unconditional_conditioning=None, **kwargs):
-        if mask is not None or quantize_x0 or score_corrector is not None or noise_dropout > 0.:
-            raise NotImplementedError("cremage_b200: DDIM mask / quantize_x0 / score_corrector / noise_dropout are not "
-                                      "on the txt2img path and are not implemented")
+        if quantize_x0 or score_corrector is not None or noise_dropout > 0.:
+            raise NotImplementedError("cremage_b200: DDIM quantize_x0 / score_corrector / noise_dropout are not "
+                                      "on the Stable Diffusion path and are not implemented")
         self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose)
         C, H, W = shape
         size = (batch_size, C, H, W)
-        return self.ddim_sampling(conditioning, size, callback=callback, img_callback=img_callback,
+        return self.ddim_sampling(conditioning, size, callback=callback, img_callback=img_callback, mask=mask, x0=x0,
                                   ddim_use_original_steps=False, temperature=temperature, x_T=x_T,
                                   log_every_t=log_every_t, unconditional_guidance_scale=unconditional_guidance_scale,
                                   unconditional_conditioning=unconditional_conditioning)
@@ -97,6 +97,10 @@ class DDIMSampler(object):
         for i, step in enumerate(iterator):
             index = total_steps - i - 1
             ts = ts_all[i].expand(b)
+            if mask is not None:       # inpainting (:171-174): the known region is re-noised to this step's level
+                assert x0 is not None
+                img_orig = self.model.q_sample(x0, [int(step)])     # host-known step: no device sync
+                img = ops.blend_mask(img_orig, img, mask)
             img, pred_x0 = self._p_sample(img, cond, cc, ts, index, temperature, unconditional_guidance_scale,
                                           want_x0=(img_callback is not None) or index % log_every_t == 0
                                           or index == total_steps - 1)

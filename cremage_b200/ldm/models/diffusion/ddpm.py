@@ -67,6 +67,24 @@ class LatentDiffusion(nn.Module):
     def device(self):
         return self.betas.device
 
+    @torch.no_grad()
+    def q_sample(self, x_start, t, noise=None):
+        """ddpm.py:296-299: sqrt(abar_t) x_0 + sqrt(1 - abar_t) noise, t a per-sample index tensor."""
+        from ... import ops
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        idx = torch.as_tensor(t).reshape(-1).tolist()
+        if len(idx) == 1:
+            idx = idx * x_start.shape[0]
+        sa, so = self.sqrt_alphas_cumprod.cpu(), self.sqrt_one_minus_alphas_cumprod.cpu()
+        x0f, nf = x_start.float().contiguous(), noise.float().contiguous()
+        if all(i == idx[0] for i in idx):
+            out = ops.axpby(x0f, float(sa[idx[0]]), nf, float(so[idx[0]]))
+        else:
+            out = torch.cat([ops.axpby(x0f[j:j + 1].contiguous(), float(sa[i]), nf[j:j + 1].contiguous(), float(so[i]))
+                             for j, i in enumerate(idx)])
+        return out.to(x_start.dtype)
+
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         if isinstance(cond, dict):
             pass

@@ -118,10 +118,15 @@ class FeedForward(PackedModule, LoraBranches):
                 "w2": ops.pack_weight(self._merged(self.net[2].weight, "net_2", device)),
                 "b2": f32(self.net[2].bias, device)}
 
-    def _run(self, x2d: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _run(self, x2d: torch.Tensor, residual: Optional[torch.Tensor] = None, ln=None) -> torch.Tensor:
+        """ln = (LnFold, folded packed w1, folded b1): x2d is the UN-normalised row matrix and the LayerNorm in front of
+        the feed-forward is applied inside the GEGLU projection's epilogue (BasicTransformerBlock._run)."""
         p = self.packed(x2d.device)
-        h = ops.igemm(x2d, p["w1"], self.inner_dim, bias=p["b1"], mode=ops.EPI_GEGLU, bn=GEGLU_BN)
-        return ops.igemm(h, p["w2"], self.dim_out, bias=p["b2"], residual=residual)
+        if ln is not None:
+            h = ops.igemm(x2d, ln[1], self.inner_dim, bias=ln[2], mode=ops.EPI_GEGLU, bn=GEGLU_BN, ln_in=ln[0])
+        else:
+            h = ops.igemm(x2d, p["w1"], self.inner_dim, bias=p["b1"], mode=ops.EPI_GEGLU, bn=GEGLU_BN)
+        return ops.igemm(h, p["w2"], self.dim_out, bias=p["b2"], residual=residual, ln_stats=residual is not None)
 
     def forward(self, x):
         require_cuda(x, "FeedForward.forward")
@@ -176,33 +181,40 @@ class CrossAttention(PackedModule, LoraBranches):
         return p
 
     def _run(self, x2d: torch.Tensor, batch: int, nq: int, ctx2d: Optional[torch.Tensor], nk: int,
-             residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x2d: bf16 [batch*nq, query_dim]; ctx2d: bf16 [batch*nk, context_dim] or None for self-attention."""
+             residual: Optional[torch.Tensor] = None, ln=None) -> torch.Tensor:
+        """x2d: bf16 [batch*nq, query_dim]; ctx2d: bf16 [batch*nk, context_dim] or None for self-attention.
+        ln = (LnFold, folded packed projection weight, folded bias): x2d is the UN-normalised row matrix and the
+        LayerNorm in front of this attention is applied inside the q (self-attention: q | k | v) projection's epilogue.
+        The output (to_out + residual) carries per-row partial sums for the next LayerNorm when the launch can."""
         p = self.packed(x2d.device)
         h, d, inner = self.heads, self.dim_head, self.inner_dim
+        stats = residual is not None
         if ctx2d is None:
             if "wqkv" not in p:
                 raise ValueError("self-attention requested on a CrossAttention built with a different context_dim")
             nk = nq
-            qkv = ops.igemm(x2d, p["wqkv"], 3 * inner)             # [M, q | k | v]: read in place by the attention kernel
+            if ln is not None:
+                qkv = ops.igemm(x2d, ln[1], 3 * inner, bias=ln[2], ln_in=ln[0])
+            else:
+                qkv = ops.igemm(x2d, p["wqkv"], 3 * inner)         # [M, q | k | v]: read in place by the attention kernel
             q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
         else:
             pre = getattr(ctx2d, "_cb_kv", None)      # K/V of this context cached by the UNet across sampler steps
             kvs = pre.get(id(self)) if pre is not None else None
             if kvs is None:
                 kvs = self.compute_kv(ctx2d, batch, nk)
-            q = ops.igemm(x2d, p["wq"], inner)
+            q = ops.igemm(x2d, ln[1], inner, bias=ln[2], ln_in=ln[0]) if ln is not None else ops.igemm(x2d, p["wq"], inner)
             if self.ipa_num_tokens > 0:
                 t_ipa = self.ipa_num_tokens
                 kv, kv2 = kvs
                 a = ops.attention(q, kv[:, :inner], kv[:, inner:], batch, h, nq, nk - t_ipa, d, self.scale)
                 a2 = ops.attention(q, kv2[:, :inner], kv2[:, inner:], batch, h, nq, t_ipa, d, self.scale)
                 y = ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
-                return ops.igemm(a2, p["wo_ipa"], self.query_dim, residual=y)
+                return ops.igemm(a2, p["wo_ipa"], self.query_dim, residual=y, ln_stats=stats)
             kv = kvs[0]
             k, v = kv[:, :inner], kv[:, inner:]
         a = ops.attention(q, k, v, batch, h, nq, nk, d, self.scale)
-        return ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
+        return ops.igemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual, ln_stats=stats)
 
     def compute_kv(self, ctx2d: torch.Tensor, batch: int, nk: int, out=None):
         """K | V projections of the context: ([batch*nk, 2*inner],) -- with IP-Adapter tokens ([batch*(nk-T), 2*inner],
@@ -268,24 +280,53 @@ class BasicTransformerBlock(PackedModule):
         self.dim = dim
 
     def _own_params(self):
-        return [self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias, self.norm3.weight,
-                self.norm3.bias]
+        # the folded packs below depend on the projections' weights (and their LoRA branches) too
+        return list(self.parameters())
 
     def _pack(self, device):
-        return {f"n{i}{k[0]}": f32(getattr(getattr(self, f"norm{i}"), k), device)
-                for i in (1, 2, 3) for k in ("weight", "bias")}
+        """LayerNorm parameters, plus -- for the fused form -- the three consumer projections with gamma folded into the
+        weights and beta into the bias (ops.fold_layernorm): attn1 q|k|v, attn2 q, the GEGLU projection."""
+        p = {f"n{i}{k[0]}": f32(getattr(getattr(self, f"norm{i}"), k), device)
+             for i in (1, 2, 3) for k in ("weight", "bias")}
+        a1, a2, ff = self.attn1, self.attn2, self.ff
+        if not self.disable_self_attn and a1.context_dim == a1.query_dim:
+            w = torch.cat([a1._merged(getattr(a1, "to_" + n).weight, n, device) for n in ("q", "k", "v")], 0)
+            wf, bf, cs = ops.fold_layernorm(w, None, p["n1w"], p["n1b"])
+            p["ln1"] = (ops.pack_weight(wf), bf, cs)
+        wf, bf, cs = ops.fold_layernorm(a2._merged(a2.to_q.weight, "q", device), None, p["n2w"], p["n2b"])
+        p["ln2"] = (ops.pack_weight(wf), bf, cs)
+        wf, bf, _ = ops.fold_layernorm(ff.net[0]._merged(ff.net[0].proj.weight, "proj", device),
+                                       ff.net[0].proj.bias.to(device), p["n3w"], p["n3b"])
+        wq, bq = ops.pack_geglu(wf, bf, GEGLU_BN)          # x / gate rows interleaved per N tile, like FeedForward._pack
+        wp = ops.pack_weight(wq)
+        p["ln3"] = (wp, bq.contiguous(), wp.float().sum(dim=1).contiguous())
+        return p
+
+    def _ln(self, x2d, p, i):
+        """LnFold for norm{i} when the producer of x2d delivered the row statistics, else None."""
+        part = getattr(x2d, "_ln_part", None)
+        key = f"ln{i}"
+        if part is None or key not in p or not ops.LN_FUSE:
+            return None
+        w, b, cs = p[key]
+        return (ops.LnFold(part, self.dim, getattr(self, f"norm{i}").eps, cs), w, b)
 
     def _run(self, x2d: torch.Tensor, batch: int, n: int, ctx2d: Optional[torch.Tensor], nk: int) -> torch.Tensor:
+        """Each LayerNorm is either folded into the GEMM that consumes it (the producer of x2d wrote per-row partial sums:
+        no LayerNorm launch, the token matrix is read once less and written once less) or a stand-alone launch."""
         p = self.packed(x2d.device)
-        h = ops.layernorm(x2d, p["n1w"], p["n1b"], self.norm1.eps)
+        ln = self._ln(x2d, p, 1)
+        h = x2d if ln is not None else ops.layernorm(x2d, p["n1w"], p["n1b"], self.norm1.eps)
         if self.disable_self_attn:
             x2d = self.attn1._run(h, batch, n, ctx2d, nk, residual=x2d)
         else:
-            x2d = self.attn1._run(h, batch, n, None, n, residual=x2d)
-        h = ops.layernorm(x2d, p["n2w"], p["n2b"], self.norm2.eps)
-        x2d = self.attn2._run(h, batch, n, ctx2d, nk, residual=x2d)
-        h = ops.layernorm(x2d, p["n3w"], p["n3b"], self.norm3.eps)
-        return self.ff._run(h, residual=x2d)
+            x2d = self.attn1._run(h, batch, n, None, n, residual=x2d, ln=ln)
+        ln = self._ln(x2d, p, 2)
+        h = x2d if ln is not None else ops.layernorm(x2d, p["n2w"], p["n2b"], self.norm2.eps)
+        x2d = self.attn2._run(h, batch, n, ctx2d, nk, residual=x2d, ln=ln)
+        ln = self._ln(x2d, p, 3)
+        h = x2d if ln is not None else ops.layernorm(x2d, p["n3w"], p["n3b"], self.norm3.eps)
+        return self.ff._run(h, residual=x2d, ln=ln)
 
     def forward(self, x, context=None):
         require_cuda(x, "BasicTransformerBlock.forward")
@@ -361,7 +402,7 @@ class SpatialTransformer(PackedModule, LoraBranches):
         b, hh, ww, c = x.shape
         n = hh * ww
         g = ops.groupnorm(x, p["ng"], p["nb"], self.norm.eps, silu=False)
-        h2d = ops.igemm(g.view(b * n, c), p["wi"], self.inner_dim, bias=p["bi"])
+        h2d = ops.igemm(g.view(b * n, c), p["wi"], self.inner_dim, bias=p["bi"], ln_stats=True)
         for blk in self.transformer_blocks:
             h2d = blk._run(h2d, b, n, ctx2d, nk)
         # rows as a (b, 1, n) pixel grid so that the fused GroupNorm statistics of the output are per image

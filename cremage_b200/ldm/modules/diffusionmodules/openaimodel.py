@@ -527,6 +527,14 @@ class UNetModel(PackedModule):
         if (kv is not None and kv["ctx"] is ctx and kv["ver"] == ctx._version and kv["shape"] == shape
                 and kv["dtype"] == ctx.dtype):
             return kv
+        if (kv is not None and kv["shape"] == shape and kv["dtype"] == ctx.dtype and kv["ctx"].device == ctx.device
+                and kv["ver"] == kv["ctx"]._version            # the cached tensor itself is still what was projected
+                and not torch.cuda.is_current_stream_capturing() and torch.equal(kv["ctx"], ctx)):
+            # a NEW tensor with the SAME content: the reference's own wrapper builds a fresh torch.cat([uc, c]) on every
+            # sampler step (ldm_wrapper_for_k_diffusion.py:67-92).  One compare kernel + a host sync (~30 us) keeps such a
+            # caller on the cached path instead of re-projecting the context through 16 (SDXL: 70) GEMMs per step.
+            kv["ctx"], kv["ver"] = ctx, ctx._version
+            return kv
         n, nk, cdim = shape
         mods = self._kv_modules()
         fresh = ctx.reshape(n * nk, cdim).to(ops.ACT).contiguous()

@@ -227,7 +227,8 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
           stages: int = 0, epilogue: int = 0, pair: Optional[bool] = None, nsub: int = 0,
           ksplit: Optional[int] = None, gn_stats: bool = False,
           out_pixel_strides: Optional[Tuple[int, int, int]] = None,
-          gn_table: Optional[Tuple[torch.Tensor, int]] = None, algo_flops: Optional[float] = None) -> torch.Tensor:
+          gn_table: Optional[Tuple[torch.Tensor, int]] = None, algo_flops: Optional[float] = None,
+          ln_stats: bool = False, ln_in: Optional["LnFold"] = None) -> torch.Tensor:
     """D = A (*) W with fused epilogue. a0/a1: NHWC bf16 [N,H,W,C] (or [M,K]); wgt: packed by pack_weight.
 
     out_grid: (n, h, w) of the output pixel grid if it differs from a0's (stride-2 parity input).
@@ -237,6 +238,11 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     gn_table: (shared partial table [n, rows, 2, cout/2], first row of this launch) -- see conv3x3_up2x.
     gn_stats: the output feeds a GroupNorm -- when the launch qualifies (see `_gn_fusable`) its epilogue also writes
     per-block partial statistics, attached to the returned tensor as `_gn_part` for `groupnorm` to pick up.
+    ln_stats: the output is a residual stream that a LayerNorm will read -- when the launch qualifies (cb_igemm_plan:
+    ln_out_slots > 0) its epilogue also writes per-row partial sums, attached to the returned tensor as `_ln_part`.
+    ln_in: `LnFold` -- a0 is the UN-normalised row matrix and `wgt` / `bias` were folded with the LayerNorm's gamma /
+    beta (`fold_layernorm`); the epilogue applies mean / rstd from the producer's `_ln_part`.  The caller checks
+    `ln_foldable(...)` first; a launch that cannot fold raises.
     """
     _need_cuda(a0, a1, wgt, bias, rowbias, residual, out)
     assert a0.dtype == ACT and wgt.dtype == ACT and a0.is_contiguous() and wgt.is_contiguous()
@@ -293,6 +299,16 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     gn_part = None
     if gn_stats and plan.gn_fusable and out is None and out_ld is None:
         gn_part = torch.empty((n, plan.gn_rows_per_image, 2, cout // 2), dtype=torch.float32, device=a0.device)
+    ln_part = None
+    if ln_stats and plan.ln_out_slots > 0 and LN_FUSE:
+        ln_part = torch.empty((rows, plan.ln_out_slots, 2), dtype=torch.float32, device=a0.device)
+        d.ln_partials_out = _p(ln_part)
+    if ln_in is not None:
+        if not plan.ln_foldable:
+            raise ValueError("igemm: this launch cannot fold a LayerNorm (needs the staged plain / GEGLU epilogue)")
+        assert ln_in.part.shape[0] == rows and ln_in.colsum.dtype == torch.float32 and bias is not None
+        d.ln_partials_in, d.ln_in_slots, d.ln_dim = _p(ln_in.part), ln_in.part.shape[1], ln_in.dim
+        d.ln_eps, d.ln_colsum = ln_in.eps, _p(ln_in.colsum)
     if out is None:
         ld = out_ld if out_ld is not None else cout
         out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
@@ -327,7 +343,35 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
             nbytes=4.0 * ksplit * rows * cout + 2.0 * rows * cout)
     if gn_part is not None:
         out._gn_part = gn_part
+    if ln_part is not None:
+        out._ln_part = ln_part
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused LayerNorm: statistics from the producer's epilogue, gamma / beta folded into the consumer's weights
+# ------------------------------------------------------------------------------------------------------------------
+LN_FUSE = int(_os.environ.get("CB_LN_FUSE", "1"))   # 0: stand-alone cb_layernorm launches (A/B)
+
+
+class LnFold:
+    """What a consumer GEMM needs to apply LayerNorm(x) on the fly: the producer's per-row partial sums of x, the row
+    width, eps and the column sums of the folded weights."""
+
+    def __init__(self, part: torch.Tensor, dim: int, eps: float, colsum: torch.Tensor):
+        self.part, self.dim, self.eps, self.colsum = part, int(dim), float(eps), colsum
+
+
+def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    """[O, I] linear weight (fp32) + LayerNorm affine -> (W' = W diag(gamma) fp32, b' = b + W beta, column sums of the
+    16-bit ROUNDED W').  LN(x) W^T + b = rstd (x W'^T - mean colsum) + b'   (ldm/modules/attention.py:900-912)."""
+    w = w.detach().float()
+    wf = w * gamma.detach().float()[None, :]
+    bf = w @ beta.detach().float()
+    if b is not None:
+        bf = bf + b.detach().float()
+    colsum = wf.to(ACT).float().sum(dim=1)
+    return wf, bf.contiguous(), colsum.contiguous()
 
 
 # nearest-2x upsample + conv3x3 (pad 1) folded: output pixel (2y+a, 2x+b) only sees the 2x2 low-resolution pixels
@@ -624,6 +668,23 @@ def cfg_mix(uncond: torch.Tensor, cond: torch.Tensor, scale: float) -> torch.Ten
     assert uncond.dtype == torch.float32 and cond.dtype == torch.float32 and uncond.is_contiguous() and cond.is_contiguous()
     out = torch.empty_like(uncond)
     _launch("cb_cfg_mix_f32", lambda: _lib.load().cb_cfg_mix_f32(_p(uncond), _p(cond), scale, uncond.numel(), _p(out), _stream()))
+    return out
+
+
+def blend_mask(keep: torch.Tensor, fresh: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """keep * mask + (1 - mask) * fresh over fp32 NCHW latents; mask [n, 1 or c, h, w] (ddim.py:171-174)."""
+    _need_cuda(keep, fresh, mask)
+    n, c, h, w = keep.shape
+    keep, fresh = keep.float().contiguous(), fresh.float().contiguous()
+    mask = mask.to(device=keep.device, dtype=torch.float32)
+    if mask.dim() == 3:
+        mask = mask[:, None]
+    mask = mask.expand(n, mask.shape[1], h, w).contiguous()
+    if mask.shape[1] not in (1, c):
+        raise ValueError(f"mask channels {mask.shape[1]} must be 1 or {c}")
+    out = torch.empty_like(keep)
+    _launch("cb_blend_mask_f32", lambda: _lib.load().cb_blend_mask_f32(_p(keep), _p(fresh), _p(mask), n, c, h * w, mask.shape[1],
+                                                                         _p(out), _stream()))
     return out
 
 

@@ -103,6 +103,19 @@ typedef struct cb_igemm_desc {
   int64_t gn_rows_per_image, gn_row_offset; /* optional: this launch fills rows [gn_row_offset, + its own M tiles per image)
                           * of a table with gn_rows_per_image rows per image (0 = a table of its own): the four parity
                           * launches of a folded upsample conv share one table */
+  /* fused LayerNorm (BasicTransformerBlock norm1/2/3, ldm/modules/attention.py:900-912): the LayerNorm launch and its
+   * read + write of the token matrix disappear.
+   *   producer (the GEMM that writes the residual stream x): ln_partials_out = fp32 [rows][cb_igemm_plan().ln_out_slots][2],
+   *     per row and slot the sum and the sum of squares of the 16-bit outputs (staged epilogue, bias / residual only).
+   *   consumer (the GEMM that reads LayerNorm(x)): A = x itself, weights W' = W diag(gamma), bias b' = b + W beta,
+   *     ln_colsum[n] = sum_k W'[n][k] (of the 16-bit rounded weights), ln_partials_in / ln_in_slots = the producer's
+   *     table, ln_dim = row width, ln_eps; the epilogue computes rstd * (x W'^T - mean * colsum) + b'. */
+  float* ln_partials_out;
+  const float* ln_partials_in;
+  int ln_in_slots;
+  int64_t ln_dim;
+  float ln_eps;
+  const float* ln_colsum;
 } cb_igemm_desc;
 
 int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
@@ -121,6 +134,8 @@ typedef struct cb_igemm_plan_t {
   int64_t workspace_bytes;      /* fp32 [ksplit][rows][cout] partials of a split-K launch, 0 otherwise */
   int gn_fusable;               /* cb_igemm_desc.gn_partials may be set for this launch */
   int64_t gn_rows_per_image;    /* rows per image of its partial table: fp32 [n][rows][2][cout/2] */
+  int ln_out_slots;             /* > 0: cb_igemm_desc.ln_partials_out may be set, fp32 [rows][ln_out_slots][2] */
+  int ln_foldable;              /* cb_igemm_desc.ln_partials_in may be set (staged plain / GEGLU epilogue) */
 } cb_igemm_plan_t;
 int cb_igemm_plan(const cb_igemm_desc* d, cb_igemm_plan_t* plan);
 /* plan + run: cb_igemm with the library's tiling and, for a split-K plan, cb_splitk_reduce applying the descriptor's
@@ -233,6 +248,10 @@ int cb_cfg_scale_input(const float* x, int64_t per_batch, int64_t b, float c_in,
 int cb_axpby_f32(const float* x, float a, const float* y, float b, int64_t count, float* out, cudaStream_t stream);
 /* out = uncond + scale * (cond - uncond)   (ldm_wrapper_for_k_diffusion.py:99) */
 int cb_cfg_mix_f32(const float* uncond, const float* cond, float scale, int64_t count, float* out, cudaStream_t stream);
+/* out = keep * mask + (1 - mask) * fresh over fp32 NCHW latents [n][c][hw]; mask [n][mask_c][hw], mask_c = 1 (broadcast
+ * over the channels) or c.  DDIM inpainting blend, ldm/models/diffusion/ddim.py:171-174. */
+int cb_blend_mask_f32(const float* keep, const float* fresh, const float* mask, int64_t n, int64_t c, int64_t hw, int mask_c,
+                      float* out, cudaStream_t stream);
 /* Euler-ancestral (k_diffusion/sampling.py:147-163): denoised = x - sigma*(eu + s*(ec-eu)) [per half, then mixed];
  *   x' = x + (x-denoised)/sigma*(sigma_down - sigma) + noise*sigma_up ; noise may be NULL (last step) */
 int cb_step_euler_ancestral(const float* x, const float* eps_u, const float* eps_c, int is_denoised, const float* noise,

@@ -168,6 +168,35 @@ def main_sgm():
                         euler_ancestral=ea.numpy(), euler_churn=ec.numpy(), steps=np.int64(steps), s_churn=np.float32(CHURN))
 
 
+def main_ddim_mask():
+    """DDIM inpainting branch (ldm/models/diffusion/ddim.py:171-174): `sample(mask=, x0=)` re-noises the known region with
+    `model.q_sample(x0, ts)` (ddpm.py:296-299, its randn_like injected) and blends before every step."""
+    ref_shim.install()
+    from ldm.models.diffusion.ddim import DDIMSampler
+    cfg = O.TINY_UNET
+    sd = O.make_weights(O.unet_param_shapes(cfg), seed=100)
+    unet = ref_shim.reference_unet(cfg, sd)
+    g = np.load(os.path.join(GOLD, "tiny_sampling.npz"))
+    cond, uncond, x_T = torch.from_numpy(g["cond"]), torch.from_numpy(g["uncond"]), torch.from_numpy(g["x_T"])
+    betas, ac, ac_prev = schedule_tensors()
+    ldm = ref_shim.DuckLDM(unet, betas, ac, ac_prev)
+    DDIMSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
+    x0 = randn(tuple(x_T.shape), 93)
+    mask = (randn((x_T.shape[0], 1, *x_T.shape[2:]), 94) > 0).float()      # 1 = keep the known latent
+    noise = randn((5, *x_T.shape), 95)
+    with torch.no_grad(), injected_randn_like(noise):
+        x, _ = DDIMSampler(ldm).sample(S=5, batch_size=x_T.shape[0], shape=list(x_T.shape[1:]), conditioning=cond, eta=0.0,
+                                       x_T=x_T, mask=mask, x0=x0, unconditional_guidance_scale=float(g["cfg_scale"]),
+                                       unconditional_conditioning=uncond, verbose=False)
+    np.savez_compressed(os.path.join(GOLD, "tiny_ddim_mask.npz"), x0=x0.numpy(), mask=mask.numpy(), noise=noise.numpy(),
+                        final=x.numpy())
+    print("tiny_ddim_mask.npz written; final absmax %.3f" % x.abs().max())
+
+
 if __name__ == "__main__":
-    main_ldm()
-    main_sgm()
+    if "ddim_mask" in sys.argv[1:]:
+        main_ddim_mask()
+    else:
+        main_ldm()
+        main_sgm()
+        main_ddim_mask()

@@ -127,6 +127,14 @@ class DuckLDM:
         self.device = torch.device("cpu")
         self.parameterization = "eps"
 
+    def q_sample(self, x_start, t, noise=None):  # ddpm.py:296-299 (LatentDiffusion itself needs Lightning to import)
+        import torch
+
+        noise = torch.randn_like(x_start) if noise is None else noise
+        sa = torch.sqrt(self.alphas_cumprod)[t].reshape(-1, 1, 1, 1)
+        so = torch.sqrt(1.0 - self.alphas_cumprod)[t].reshape(-1, 1, 1, 1)
+        return sa * x_start + so * noise
+
     def apply_model(self, x, t, cond):  # ddpm.py:926-1039 live branch + DiffusionWrapper 'crossattn' :1517-1519
         import torch
 

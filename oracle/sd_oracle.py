@@ -613,7 +613,8 @@ def sample_dpmpp_2m(model, x: Tensor, sigmas: Tensor, trace: Optional[List[Tenso
 
 def ddim_sample(eps_fn: Callable[[Tensor, Tensor, Tensor], Tensor], alphas_cumprod: Tensor, x_T: Tensor, cond: Tensor,
                 uncond: Tensor, cfg_scale: float, S: int, eta: float = 0.0,
-                trace: Optional[List[Tensor]] = None) -> Tensor:
+                trace: Optional[List[Tensor]] = None, mask: Optional[Tensor] = None, x0: Optional[Tensor] = None,
+                mask_noise: Optional[Sequence[Tensor]] = None) -> Tensor:
     """DDIMSampler.sample -> ddim_sampling -> p_sample_ddim (ldm/models/diffusion/ddim.py:78-190,530-612), eta = 0
     path with classifier-free guidance; integer timesteps (torch.long)."""
     ddim_timesteps = make_ddim_timesteps(S, alphas_cumprod.shape[0])
@@ -626,6 +627,10 @@ def ddim_sample(eps_fn: Callable[[Tensor, Tensor, Tensor], Tensor], alphas_cumpr
     for i, step in enumerate(time_range):
         index = total - i - 1
         ts = torch.full((b,), int(step), device=x_T.device, dtype=torch.long)
+        if mask is not None:  # inpainting, ddim.py:171-174 + LatentDiffusion.q_sample ddpm.py:296-299
+            ac_t = alphas_cumprod[int(step)]
+            img_orig = torch.sqrt(ac_t) * x0 + torch.sqrt(1.0 - ac_t) * mask_noise[i]
+            img = img_orig * mask + (1.0 - mask) * img
         x_in = torch.cat([img] * 2)
         t_in = torch.cat([ts] * 2)
         c_in = torch.cat([uncond, cond])

@@ -313,3 +313,44 @@ def test_conv3x3_after_nearest_upsample_folded(n, h, w, cin, cout):
     # and against the unfolded form on the same kernels (upsample2x + conv3x3): only the weight rounding differs
     ref = ops.igemm(ops.upsample2x(x_nhwc), ops.pack_weight(wt).cuda(), cout, taps=ops.TAPS_3X3, bias=b.cuda())
     _close(out.view(-1, cout), ref)
+
+
+@pytest.mark.parametrize("rows,dim,nout,geglu", [(4096, 320, 960, False), (1000, 640, 640, False), (512, 1280, 320, False),
+                                                 (2048, 320, 1280, True), (300, 640, 2560, True)])
+def test_layernorm_folded_into_producer_and_consumer(rows, dim, nout, geglu):
+    """BasicTransformerBlock's LayerNorm without a LayerNorm launch (ldm/modules/attention.py:900-912): the producer
+    GEMM (+ residual) writes per-row partial sums of its 16-bit output, the consumer GEMM reads the un-normalised rows
+    with gamma folded into its weights and applies rstd * (acc - mean * colsum) + b' in the epilogue."""
+    from cremage_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(rows + dim)
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc)
+    a = r(rows, dim).to(ops.ACT).cuda()
+    res = (r(rows, dim, sc=2.0) + 1.5).to(ops.ACT).cuda()            # residual stream with a non-zero mean
+    w0, b0 = r(dim, dim, sc=dim ** -0.5), r(dim, sc=0.1)
+    gamma, beta = 1.0 + r(dim, sc=0.2), r(dim, sc=0.2)
+    w1, b1 = r(2 * nout if geglu else nout, dim, sc=dim ** -0.5), r(2 * nout if geglu else nout, sc=0.1)
+    x = ops.igemm(a, ops.pack_weight(w0.cuda()), dim, bias=b0.cuda(), residual=res, ln_stats=True)
+    part = getattr(x, "_ln_part", None)
+    assert part is not None and part.shape[0] == rows and part.shape[2] == 2
+    # the partial sums are those of the 16-bit output
+    xs = x.float()
+    assert torch.allclose(part[:, :, 0].sum(1), xs.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(part[:, :, 1].sum(1), (xs * xs).sum(1), rtol=1e-4, atol=1e-2)
+    wf, bf, cs = ops.fold_layernorm(w1.cuda(), b1.cuda(), gamma.cuda(), beta.cuda())
+    ln = ops.LnFold(part, dim, 1e-5, None)
+    if geglu:
+        wq, bq = ops.pack_geglu(wf, bf, ops.GEGLU_BN)
+        wp = ops.pack_weight(wq)
+        ln.colsum = wp.float().sum(dim=1).contiguous()
+        got = ops.igemm(x, wp, nout, bias=bq.contiguous(), mode=ops.EPI_GEGLU, bn=ops.GEGLU_BN, ln_in=ln)
+        y = torch.nn.functional.layer_norm(xs, (dim,), gamma.cuda(), beta.cuda(), 1e-5) @ w1.cuda().t() + b1.cuda()
+        want = y[:, :nout] * torch.nn.functional.gelu(y[:, nout:])
+    else:
+        ln.colsum = cs
+        got = ops.igemm(x, ops.pack_weight(wf), nout, bias=bf, ln_in=ln)
+        want = torch.nn.functional.layer_norm(xs, (dim,), gamma.cuda(), beta.cuda(), 1e-5) @ w1.cuda().t() + b1.cuda()
+    err = (got.float() - want).abs().max().item()
+    ref = want.abs().max().item()
+    print(f"[parity] LayerNorm fold rows={rows} dim={dim} nout={nout} geglu={geglu}: max_abs_err={err:.3e} ref_absmax={ref:.2f}")
+    from tests._models import tol
+    assert err <= tol(2e-2) * max(ref, 1.0)

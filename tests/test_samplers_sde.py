@@ -184,3 +184,30 @@ def test_cuda_front_ends_vs_reference_golden():
     for cls in (K.DpmppSdeSampler, K.Dpmpp2mSdeSampler, K.Dpmpp3mSdeSampler):       # :373-411, default Brownian noise
         x, _ = cls(ldm).sample(S=3, x0=x_T * 14.0, **common)
         assert tuple(x.shape) == (2, 4, 16, 16) and torch.isfinite(x).all()
+
+
+def test_oracle_ddim_inpainting_matches_reference_golden():
+    g, _, sd = _setup()
+    m = gold("tiny_ddim_mask.npz")
+    _, ac, _ = O.alphas_cumprod_from_betas(O.make_beta_schedule_linear())
+    eps = lambda x, t, c: O.unet_forward(sd, O.TINY_UNET, x, t, c)
+    with torch.no_grad():
+        x = O.ddim_sample(eps, ac, torch.from_numpy(g["x_T"]), torch.from_numpy(g["cond"]), torch.from_numpy(g["uncond"]),
+                          float(g["cfg_scale"]), 5, mask=torch.from_numpy(m["mask"]), x0=torch.from_numpy(m["x0"]),
+                          mask_noise=list(torch.from_numpy(m["noise"])))
+    assert np.abs(x.numpy() - m["final"]).max() < 1e-3 * max(1.0, np.abs(m["final"]).max())
+
+
+@pytest.mark.gpu
+def test_cuda_ddim_inpainting_vs_reference_golden():
+    """DDIMSampler.sample(mask=, x0=) (ldm/models/diffusion/ddim.py:171-174): q_sample + masked blend before every step."""
+    from cremage_b200.ldm.models.diffusion.ddim import DDIMSampler
+    g, _, sd = _setup()
+    m = gold("tiny_ddim_mask.npz")
+    ldm, _ = _gpu_wrapper(g, sd)
+    with injected_randn_like(list(torch.from_numpy(m["noise"]).cuda())):
+        x, _ = DDIMSampler(ldm).sample(S=5, batch_size=2, shape=[4, 16, 16], conditioning=torch.from_numpy(g["cond"]).cuda(),
+                                       eta=0.0, x_T=torch.from_numpy(g["x_T"]).cuda(), mask=torch.from_numpy(m["mask"]).cuda(),
+                                       x0=torch.from_numpy(m["x0"]).cuda(), unconditional_guidance_scale=float(g["cfg_scale"]),
+                                       unconditional_conditioning=torch.from_numpy(g["uncond"]).cuda(), verbose=False)
+    _check("DDIMSampler.sample(mask, x0)", x, torch.from_numpy(m["final"]))
