@@ -49,7 +49,7 @@ class IGemmDesc(C.Structure):
         ("gn_partials", C.c_void_p),
         ("gn_rows_per_image", C.c_int64), ("gn_row_offset", C.c_int64),
         ("ln_partials_out", C.c_void_p), ("ln_partials_in", C.c_void_p), ("ln_in_slots", C.c_int),
-        ("ln_dim", C.c_int64), ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
+        ("ln_dim", C.c_int64), ("ln_eps", C.c_float),
     ]
 
 

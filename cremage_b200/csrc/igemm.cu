@@ -78,14 +78,13 @@ struct IGemmKParams {
   int gn_bpi, gn_row0;   // rows per image of the table, first row of this launch
   // fused LayerNorm (staged epilogues).  PRODUCER: per output row and (N tile, epilogue half) the sum and the sum of
   // squares of the 16-bit rounded outputs -> ln_out[row][ln_out_slots][2].  CONSUMER: the A operand is the UN-normalised
-  // row x; with W' = W diag(gamma) as weights, cs[n] = sum_k W'[n, k] and b' = b + W beta the epilogue computes
-  //   LN(x) W^T + b = rstd * (x W'^T - mean * cs) + b'      (mean / rstd of the row from ln_in[row][ln_in_slots][2])
+  // row x; the weights are W'' = W diag(gamma) with every ROW CENTRED (sum_k W''[n, k] = 0), so x W''^T = (x - mean) W'^T,
+  // b' = b + W beta, and the epilogue computes  LN(x) W^T + b = rstd * (x W''^T) + b'   (rstd from ln_in[row][slots][2])
   float* ln_out;
   int ln_out_slots;
   const float* ln_in;
   int ln_in_slots;
   float ln_inv_dim, ln_eps;
-  const float* ln_colsum;
 };
 
 // ---- fused GroupNorm statistics -----------------------------------------------------------------------------------
@@ -309,10 +308,10 @@ CB_DEVINL uint4 ld_shared_v4(uint32_t addr) {
 
 // STAGED epilogue of one 32-column chunk: registers (+bias, +per-image bias, +residual read from the panel) -> the
 // 64B-swizzled panel (row = lane, 16-byte piece j at  j ^ ((lane >> 1) & 3)), ready for the TMA store.
-// LayerNorm fold of a staged launch: lnc = the A rows are un-normalised (rstd / rstd*mean of this thread's row in
-// ln_rs / ln_a, column sums 256 floats behind the bias slice); lnp = accumulate this row's sum / sum of squares of the
-// 16-bit outputs into ls / lq.
-struct LnRow { bool lnc, lnp; float rs, a; };
+// LayerNorm fold of a staged launch: lnc = the A rows are un-normalised and the weights are gamma-folded AND centred
+// (every weight row sums to zero, so the row mean drops out of the product) -- the epilogue only scales by this row's
+// rstd; lnp = accumulate this row's sum / sum of squares of the 16-bit outputs into ls / lq.
+struct LnRow { bool lnc, lnp; float rs; };
 template <int EPI, bool STATS>
 __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32_t (&v)[32], const uint32_t (&g)[32],
                                              const float* __restrict__ sbx, const float* __restrict__ sbg,
@@ -326,12 +325,9 @@ __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32
     const float4 b0 = *reinterpret_cast<const float4*>(sbx + 8 * j);
     const float4 b1 = *reinterpret_cast<const float4*>(sbx + 8 * j + 4);
     if ((EPI == EPI_PLAIN || EPI == EPI_GEGLU) && ln.lnc) {
-      const float4 c0 = *reinterpret_cast<const float4*>(sbx + 256 + 8 * j);
-      const float4 c1 = *reinterpret_cast<const float4*>(sbx + 256 + 8 * j + 4);
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaf(ln.rs, __uint_as_float(v[8 * j + e]), fmaf(-ln.a, cc[e], bb[e]));
+      for (int e = 0; e < 8; ++e) f[e] = fmaf(ln.rs, __uint_as_float(v[8 * j + e]), bb[e]);   // one FMA where the plain form has one add
     } else {
       f[0] = __uint_as_float(v[8 * j + 0]) + b0.x; f[1] = __uint_as_float(v[8 * j + 1]) + b0.y;
       f[2] = __uint_as_float(v[8 * j + 2]) + b0.z; f[3] = __uint_as_float(v[8 * j + 3]) + b0.w;
@@ -344,11 +340,8 @@ __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32
       const float4 g1 = *reinterpret_cast<const float4*>(sbg + 8 * j + 4);
       const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       if (ln.lnc) {
-        const float4 c0 = *reinterpret_cast<const float4*>(sbg + 256 + 8 * j);
-        const float4 c1 = *reinterpret_cast<const float4*>(sbg + 256 + 8 * j + 4);
-        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(fmaf(ln.rs, __uint_as_float(g[8 * j + e]), fmaf(-ln.a, cc[e], gb[e])));
+        for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(fmaf(ln.rs, __uint_as_float(g[8 * j + e]), gb[e]));
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(__uint_as_float(g[8 * j + e]) + gb[e]);
@@ -425,8 +418,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const uint32_t bres_bar = misc + 48u;
   const uint32_t tmem_slot = misc + 56u;
   auto resid_bar = [&](int ew) { return misc + 64u + 8u * uint32_t(ew); };
-  const uint32_t bias_smem = (misc + 64u + 8u * EPI_WARPS + 15u) & ~15u;  // float[3][512]: per accumulator slot a sub-tile's bias slice [256] | LayerNorm column sums [256]
-  const uint32_t gn_smem = bias_smem + 3u * 512u * 4u;   // float[2 tiles][8 chunks][4 quarters][32] (only when gn_part)
+  const uint32_t bias_smem = (misc + 64u + 8u * EPI_WARPS + 15u) & ~15u;  // float[3][256]: a sub-tile's bias slice per accumulator slot
+  const uint32_t gn_smem = bias_smem + 3u * 256u * 4u;   // float[2 tiles][8 chunks][4 quarters][32] (only when gn_part)
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -621,11 +614,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       }
       // stage this tile's bias slice (overlaps the MMAs of this tile); the named barrier also orders the reuse of
       // the slot against the slowest warp's reads two tiles ago
-      float* sb = sbias_all + buf * 512;
+      float* sb = sbias_all + buf * 256;
       for (int c = threadIdx.x - 64; c < p.bn; c += 32 * EPI_WARPS) {
         const int bc = nt * p.bn + c;
         sb[c] = (p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
-        if (p.ln_in != nullptr) sb[256 + c] = bc < p.bias_len ? __ldg(p.ln_colsum + bc) : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
       // fused GroupNorm statistics: every warp has stored the previous tile's chunk totals -> write that tile's row
@@ -642,7 +634,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
         const bool have = (hh * 32 < ocols) && (nt * ocols + hh * 32 < p.cout);
         if (EPI == EPI_RES && have) { mbar_wait(resid_bar(ew), rphase); rphase ^= 1u; }
         const float* rowb = (EPI == EPI_ROWBIAS) ? (p.rowbias + static_cast<long long>(n < p.n_img ? n : 0) * p.rowbias_ld) : nullptr;
-        LnRow ln{p.ln_in != nullptr, p.ln_out != nullptr, 1.f, 0.f};
+        LnRow ln{p.ln_in != nullptr, p.ln_out != nullptr, 1.f};
         float ls = 0.f, lq = 0.f;
         if ((EPI == EPI_PLAIN || EPI == EPI_GEGLU) && ln.lnc && row_ok) {
           // this row's mean / rstd from the producer's partial sums (fixed slot order: deterministic)
@@ -652,7 +644,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           const float mean = sx * p.ln_inv_dim;
           const float var = fmaxf(fmaf(-mean, mean, sq * p.ln_inv_dim), 0.f);
           ln.rs = rsqrtf(var + p.ln_eps);
-          ln.a = ln.rs * mean;
         }
         int k = 0;
         for (int c = hh * 32; c < ocols; c += 64, ++k) {
@@ -863,8 +854,8 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   }
   if (d->ln_partials_in) {
     CB_REQUIRE(staged && (epi == EPI_PLAIN || epi == EPI_GEGLU), "cb_igemm: the LayerNorm fold needs a staged plain or GEGLU epilogue");
-    CB_REQUIRE(d->ln_colsum && d->ln_in_slots > 0 && d->ln_dim > 0 && d->bias, "cb_igemm: the LayerNorm fold needs column sums, a bias, the slot count and the row width");
-    p.ln_in = d->ln_partials_in; p.ln_in_slots = d->ln_in_slots; p.ln_colsum = d->ln_colsum;
+    CB_REQUIRE(d->ln_in_slots > 0 && d->ln_dim > 0 && d->bias, "cb_igemm: the LayerNorm fold needs a bias, the slot count and the row width");
+    p.ln_in = d->ln_partials_in; p.ln_in_slots = d->ln_in_slots;
     p.ln_inv_dim = 1.f / float(d->ln_dim); p.ln_eps = d->ln_eps;
   }
   const int ocols = (epi == EPI_GEGLU) ? d->bn / 2 : d->bn;
@@ -898,7 +889,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
 
   // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
   //      that N tile gets several M tiles; otherwise stream A and B through the ring
-  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 1536 + 64 + (d->gn_partials ? sizeof(float) * 2048 : 0);
+  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 768 + 64 + (d->gn_partials ? sizeof(float) * 2048 : 0);
   const size_t b_chunk = (size_t)(two ? d->bn / 2 : d->bn) * 128;
   const size_t res_bytes = (size_t)num_k * b_chunk;
   int resident = 0;

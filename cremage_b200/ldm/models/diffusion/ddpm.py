@@ -70,7 +70,7 @@ class LatentDiffusion(nn.Module):
     @torch.no_grad()
     def q_sample(self, x_start, t, noise=None):
         """ddpm.py:296-299: sqrt(abar_t) x_0 + sqrt(1 - abar_t) noise, t a per-sample index tensor."""
-        from ... import ops
+        from .... import ops
         if noise is None:
             noise = torch.randn_like(x_start)
         idx = torch.as_tensor(t).reshape(-1).tolist()

@@ -285,21 +285,20 @@ class BasicTransformerBlock(PackedModule):
 
     def _pack(self, device):
         """LayerNorm parameters, plus -- for the fused form -- the three consumer projections with gamma folded into the
-        weights and beta into the bias (ops.fold_layernorm): attn1 q|k|v, attn2 q, the GEGLU projection."""
+        weights (rows centred) and beta into the bias (ops.fold_layernorm): attn1 q|k|v, attn2 q, the GEGLU projection."""
         p = {f"n{i}{k[0]}": f32(getattr(getattr(self, f"norm{i}"), k), device)
              for i in (1, 2, 3) for k in ("weight", "bias")}
         a1, a2, ff = self.attn1, self.attn2, self.ff
         if not self.disable_self_attn and a1.context_dim == a1.query_dim:
             w = torch.cat([a1._merged(getattr(a1, "to_" + n).weight, n, device) for n in ("q", "k", "v")], 0)
-            wf, bf, cs = ops.fold_layernorm(w, None, p["n1w"], p["n1b"])
-            p["ln1"] = (ops.pack_weight(wf), bf, cs)
-        wf, bf, cs = ops.fold_layernorm(a2._merged(a2.to_q.weight, "q", device), None, p["n2w"], p["n2b"])
-        p["ln2"] = (ops.pack_weight(wf), bf, cs)
-        wf, bf, _ = ops.fold_layernorm(ff.net[0]._merged(ff.net[0].proj.weight, "proj", device),
-                                       ff.net[0].proj.bias.to(device), p["n3w"], p["n3b"])
+            wf, bf = ops.fold_layernorm(w, None, p["n1w"], p["n1b"])
+            p["ln1"] = (ops.pack_weight(wf), bf)
+        wf, bf = ops.fold_layernorm(a2._merged(a2.to_q.weight, "q", device), None, p["n2w"], p["n2b"])
+        p["ln2"] = (ops.pack_weight(wf), bf)
+        wf, bf = ops.fold_layernorm(ff.net[0]._merged(ff.net[0].proj.weight, "proj", device),
+                                    ff.net[0].proj.bias.to(device), p["n3w"], p["n3b"])
         wq, bq = ops.pack_geglu(wf, bf, GEGLU_BN)          # x / gate rows interleaved per N tile, like FeedForward._pack
-        wp = ops.pack_weight(wq)
-        p["ln3"] = (wp, bq.contiguous(), wp.float().sum(dim=1).contiguous())
+        p["ln3"] = (ops.pack_weight(wq), bq.contiguous())
         return p
 
     def _ln(self, x2d, p, i):
@@ -308,8 +307,8 @@ class BasicTransformerBlock(PackedModule):
         key = f"ln{i}"
         if part is None or key not in p or not ops.LN_FUSE:
             return None
-        w, b, cs = p[key]
-        return (ops.LnFold(part, self.dim, getattr(self, f"norm{i}").eps, cs), w, b)
+        w, b = p[key]
+        return (ops.LnFold(part, self.dim, getattr(self, f"norm{i}").eps), w, b)
 
     def _run(self, x2d: torch.Tensor, batch: int, n: int, ctx2d: Optional[torch.Tensor], nk: int) -> torch.Tensor:
         """Each LayerNorm is either folded into the GEMM that consumes it (the producer of x2d wrote per-row partial sums:

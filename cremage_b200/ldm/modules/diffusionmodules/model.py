@@ -125,8 +125,9 @@ class ResnetBlock(PackedModule):
 
 class AttnBlock(PackedModule):
     """model.py:157-209: single-head attention over all pixels, head dim = channels (512 in SD): too wide for the
-    fused kernel's TMEM budget, so it runs as tcgen05 GEMMs around a row-softmax kernel, one image at a time:
-      q, k = 1x1(h);  S = q k^T (fp32);  P = softmax(S / sqrt(c)) (bf16);  v^T = Wv h^T;  O = P v + bv;  x + 1x1(O)
+    fused kernel's TMEM budget (S 128 + O 512 columns > 512), so it runs as tcgen05 GEMMs around a row-softmax kernel,
+    one image and one chunk of query rows at a time (the chunk's scores and probabilities stay in L2):
+      q, k = 1x1(h);  S = q k^T (fp32);  P = softmax(S / sqrt(c)) (16-bit);  v^T = Wv h^T;  O = P v + bv;  x + 1x1(O)
     (the value bias is added after the PV product -- exact, softmax rows sum to one)."""
 
     def __init__(self, in_channels):
@@ -159,15 +160,24 @@ class AttnBlock(PackedModule):
         q = ops.igemm(hn.view(n * npx, c), p["wq"], c, bias=p["bq"]).view(n, npx, c)
         k = ops.igemm(hn.view(n * npx, c), p["wk"], c, bias=p["bk"]).view(n, npx, c)
         o = torch.empty((n, npx, c), dtype=ops.ACT, device=x.device)
-        s = torch.empty((npx, npx), dtype=torch.float32, device=x.device)
-        pm = torch.empty((npx, npx), dtype=ops.ACT, device=x.device)
+        # The N x N score matrix never exists: query rows go through S -> softmax -> P V in chunks whose fp32 scores
+        # (<= 32 MiB) and 16-bit probabilities stay in the 126 MB L2 between the three launches.  At 128 x 128 latents
+        # (1024^2 decode: N = 16 384) the full matrix would be 1 GiB of fp32 + 0.5 GiB of P per image.
+        rows_c = npx
+        while rows_c > 128 and rows_c * npx * 4 > (32 << 20) and rows_c % 2 == 0:
+            rows_c //= 2
+        s = torch.empty((rows_c, npx), dtype=torch.float32, device=x.device)
+        pm = torch.empty((rows_c, npx), dtype=ops.ACT, device=x.device)
         vt = torch.empty((c, npx), dtype=ops.ACT, device=x.device)
         scale = float(int(c) ** (-0.5))
         for i in range(n):
-            ops.igemm(q[i], k[i], npx, out=s)                        # S = q k^T, the "weights" operand is k itself
-            ops.softmax_rows(s, scale, out=pm)
             ops.igemm(p["wv_rows"], hn[i], npx, out=vt)              # v^T [c, npx] = Wv h^T
-            ops.igemm(pm, vt, c, bias=p["bv"], out=o[i])             # O = P v + bv
+            for r0 in range(0, npx, rows_c):
+                r1 = min(r0 + rows_c, npx)
+                sc, pc = s[:r1 - r0], pm[:r1 - r0]
+                ops.igemm(q[i][r0:r1], k[i], npx, out=sc)            # S = q k^T, the "weights" operand is k itself
+                ops.softmax_rows(sc, scale, out=pc)
+                ops.igemm(pc, vt, c, bias=p["bv"], out=o[i][r0:r1])  # O = P v + bv
         out = ops.igemm(o.view(n, 1, npx, c), p["wo"], c, bias=p["bo"], residual=x.view(n * npx, c), gn_stats=True)
         return ops.nhwc(out, n, hh, ww, c)
 

@@ -306,9 +306,8 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
     if ln_in is not None:
         if not plan.ln_foldable:
             raise ValueError("igemm: this launch cannot fold a LayerNorm (needs the staged plain / GEGLU epilogue)")
-        assert ln_in.part.shape[0] == rows and ln_in.colsum.dtype == torch.float32 and bias is not None
-        d.ln_partials_in, d.ln_in_slots, d.ln_dim = _p(ln_in.part), ln_in.part.shape[1], ln_in.dim
-        d.ln_eps, d.ln_colsum = ln_in.eps, _p(ln_in.colsum)
+        assert ln_in.part.shape[0] == rows and bias is not None
+        d.ln_partials_in, d.ln_in_slots, d.ln_dim, d.ln_eps = _p(ln_in.part), ln_in.part.shape[1], ln_in.dim, ln_in.eps
     if out is None:
         ld = out_ld if out_ld is not None else cout
         out = torch.empty((rows, ld), dtype=torch.float32 if out_f32 else ACT, device=a0.device)
@@ -356,22 +355,25 @@ LN_FUSE = int(_os.environ.get("CB_LN_FUSE", "1"))   # 0: stand-alone cb_layernor
 
 class LnFold:
     """What a consumer GEMM needs to apply LayerNorm(x) on the fly: the producer's per-row partial sums of x, the row
-    width, eps and the column sums of the folded weights."""
+    width and eps (the affine part and the centring live in the folded weights, `fold_layernorm`)."""
 
-    def __init__(self, part: torch.Tensor, dim: int, eps: float, colsum: torch.Tensor):
-        self.part, self.dim, self.eps, self.colsum = part, int(dim), float(eps), colsum
+    def __init__(self, part: torch.Tensor, dim: int, eps: float):
+        self.part, self.dim, self.eps = part, int(dim), float(eps)
 
 
 def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
-    """[O, I] linear weight (fp32) + LayerNorm affine -> (W' = W diag(gamma) fp32, b' = b + W beta, column sums of the
-    16-bit ROUNDED W').  LN(x) W^T + b = rstd (x W'^T - mean colsum) + b'   (ldm/modules/attention.py:900-912)."""
+    """[O, I] linear weight (fp32) + LayerNorm affine -> (W'', b'):  W' = W diag(gamma),  W'' = W' with every ROW CENTRED
+    (W''[n, :] -= mean(W'[n, :])),  b' = b + W beta.  Then  LN(x) W^T + b = rstd * (x W''^T) + b'  because
+    (x - mean(x) 1) W'^T = x W'^T - mean(x) rowsum(W') = x W''^T   (ldm/modules/attention.py:900-912).  What remains of
+    the mean after rounding W'' to 16 bits is mean(x) * (sum of a row's rounding errors): below the rounding of a
+    stand-alone LayerNorm's 16-bit output (checked in tests/test_gpu_igemm.py)."""
     w = w.detach().float()
     wf = w * gamma.detach().float()[None, :]
+    wf = wf - wf.mean(dim=1, keepdim=True)
     bf = w @ beta.detach().float()
     if b is not None:
         bf = bf + b.detach().float()
-    colsum = wf.to(ACT).float().sum(dim=1)
-    return wf, bf.contiguous(), colsum.contiguous()
+    return wf.contiguous(), bf.contiguous()
 
 
 # nearest-2x upsample + conv3x3 (pad 1) folded: output pixel (2y+a, 2x+b) only sees the 2x2 low-resolution pixels

@@ -107,15 +107,15 @@ typedef struct cb_igemm_desc {
    * read + write of the token matrix disappear.
    *   producer (the GEMM that writes the residual stream x): ln_partials_out = fp32 [rows][cb_igemm_plan().ln_out_slots][2],
    *     per row and slot the sum and the sum of squares of the 16-bit outputs (staged epilogue, bias / residual only).
-   *   consumer (the GEMM that reads LayerNorm(x)): A = x itself, weights W' = W diag(gamma), bias b' = b + W beta,
-   *     ln_colsum[n] = sum_k W'[n][k] (of the 16-bit rounded weights), ln_partials_in / ln_in_slots = the producer's
-   *     table, ln_dim = row width, ln_eps; the epilogue computes rstd * (x W'^T - mean * colsum) + b'. */
+   *   consumer (the GEMM that reads LayerNorm(x)): A = x itself; weights W'' = W diag(gamma) with every row centred
+   *     (W''[n][k] -= mean_k W'[n][k], so x W''^T = (x - mean(x)) W'^T: the row mean needs no separate term), bias
+   *     b' = b + W beta; ln_partials_in / ln_in_slots = the producer's table, ln_dim = row width, ln_eps; the epilogue
+   *     computes rstd * (x W''^T) + b'. */
   float* ln_partials_out;
   const float* ln_partials_in;
   int ln_in_slots;
   int64_t ln_dim;
   float ln_eps;
-  const float* ln_colsum;
 } cb_igemm_desc;
 
 int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream);
