@@ -233,7 +233,7 @@ CB_DEVINL void umma_commit_pair(uint32_t bar) {
 }
 // arrive on the mbarrier at this offset in the pair's leader CTA (from either CTA)
 CB_DEVINL void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
 }
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA reads of a tile written with st.shared)
@@ -375,6 +375,35 @@ CB_DEVINL float gelu_fast_f(float x) {
   const float erf_abs = fmaf(-p * t, e, 1.f);             // erf(|x|/sqrt2)
   const float hx = 0.5f * x;
   return fmaf(copysignf(erf_abs, x), hx, hx);              // 0.5 x (1 + erf)
+}
+
+// f[e] *= gelu(g[e]) for eight gates at once, written stage by stage so that the eight dependency chains are
+// interleaved by construction (two epilogue warps per scheduler cannot hide a serial Horner chain).
+// gelu(g) = 0.5 g (1 + erf(g / sqrt2)) = relu(g) - 0.5 |g| erfc(|g| / sqrt2); erfc by Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7) in the variable w = |g| sqrt(log2(e) / 2), so that exp(-g^2 / 2) = 2^(-w^2); the -0.5 |g| / w
+// factor is folded into the polynomial coefficients.  14 instructions per gate, two of them MUFU.
+CB_DEVINL void geglu_mul8(float (&f)[8], const float (&g)[8]) {
+  float w[8], t[8], ex[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] = fabsf(g[e]) * 0.8493218003f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t[e]) : "f"(fmaf(w[e], 0.2727374809f, 1.f)));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex[e]) : "f"(-w[e] * w[e]));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q[e] = fmaf(-0.6248546950f, t[e], 0.8554778804f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q[e] = fmaf(q[e], t[e], -0.8367933924f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q[e] = fmaf(q[e], t[e], 0.1674846542f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) q[e] = fmaf(q[e], t[e], -0.1500194578f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] *= ex[e];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] *= t[e];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] *= fmaf(q[e], w[e], fmaxf(g[e], 0.f));
 }
 
 CB_DEVINL float warp_sum(float v) {

@@ -36,11 +36,33 @@ constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;   // 320
 constexpr int PANEL_BYTES = 32 * 32 * 2;           // one staged epilogue panel: 32 rows x 32 columns, 16-bit
 constexpr int SMEM_LIMIT = 227 * 1024;
 
+// Division by a launch constant (tile scheduler, tile -> pixel-box coordinates): q = umulhi(n, mul) >> shr, exact for
+// 0 <= n < 2^31 (mul = ceil(2^(31 + ceil_log2 d) / d)); d == 1 is the identity.  Replaces ~100-instruction integer
+// divisions on the per-tile critical path of every role.
+struct FastDiv {
+  uint32_t mul, shr, d;
+  __device__ __forceinline__ int div(int n) const { return d == 1u ? n : int(__umulhi(uint32_t(n), mul) >> shr); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * int(d); }
+};
+static FastDiv make_fastdiv(int d) {
+  FastDiv f{0u, 0u, uint32_t(d)};
+  if (d > 1) {
+    int lg = 0;
+    while ((1ll << lg) < d) ++lg;
+    const int pw = 31 + lg;
+    f.mul = uint32_t(((1ull << pw) + uint64_t(d) - 1) / uint64_t(d));
+    f.shr = uint32_t(pw - 32);
+  }
+  return f;
+}
+
 struct IGemmKParams {
   // rows
   int n_img, H, W;       // output pixel grid
   int TW, TH, TN;        // tile decomposition, TW*TH*TN == 128
   int tiles_w, tiles_h;  // tiles along w / h
+  FastDiv fd_tw, fd_th, fd_work;   // / tiles_w, / tiles_h, / (n_groups * ksplit)
+  int total_work;        // (m_pairs or m_tiles) * n_groups * ksplit
   int m_tiles, n_tiles;  // tile grid
   int two, m_pairs;      // CTA-pair mode (cta_group::2): a cluster of 2 CTAs owns M tiles 2*mp, 2*mp+1 of one N tile
   int nsub, n_groups;    // N sub-tiles that share one A stage (1 or 2), groups of sub-tiles = ceil(n_tiles / nsub)
@@ -150,10 +172,11 @@ struct TileSched {
     // `nt` is the N GROUP index: the group's sub-tiles are n-tiles nt*nsub .. nt*nsub + nsub-1 (see subs());
     // with split-K the K-split index rides in the upper bits: nt = s * n_groups + group (see split() / group())
     if (p.two) {
-      const long long t = (long long)(blockIdx.x >> 1) + (long long)i * (gridDim.x >> 1);
-      if (t >= (long long)p.m_pairs * p.n_groups * p.ksplit) return false;
-      nt = int(t % (p.n_groups * p.ksplit));
-      mt = 2 * int(t / (p.n_groups * p.ksplit)) + int(blockIdx.x & 1);   // may be == m_tiles (odd count): an all-out-of-bounds tile
+      const int t = int(blockIdx.x >> 1) + i * int(gridDim.x >> 1);
+      if (t >= p.total_work) return false;
+      int q;
+      p.fd_work.divmod(t, q, nt);
+      mt = 2 * q + int(blockIdx.x & 1);   // may be == m_tiles (odd count): an all-out-of-bounds tile
       return true;
     }
     if (p.resident_b) {
@@ -161,10 +184,9 @@ struct TileSched {
       mt = int(blockIdx.x) / p.n_tiles + i * p.m_step;
       return mt < p.m_tiles;
     }
-    const long long t = (long long)blockIdx.x + (long long)i * gridDim.x;
-    if (t >= (long long)p.m_tiles * p.n_groups * p.ksplit) return false;
-    nt = int(t % (p.n_groups * p.ksplit));
-    mt = int(t / (p.n_groups * p.ksplit));
+    const int t = int(blockIdx.x) + i * int(gridDim.x);
+    if (t >= p.total_work) return false;
+    p.fd_work.divmod(t, mt, nt);
     return true;
   }
   __device__ __forceinline__ int split(int nt) const { return p.ksplit == 1 ? 0 : nt / p.n_groups; }
@@ -188,7 +210,7 @@ enum : int {
   EPI_COUNT = 6
 };
 
-// 32 accumulator columns [c, c+32) of one row -> global
+// 32 accumulator columns [c, c+32) of one row -> global; sbias = the 32 bias values of this chunk
 template <int EPI, bool STATS>
 __device__ __forceinline__ void epilogue_chunk(const IGemmKParams& p, const uint32_t (&v)[32], const float* __restrict__ sbias,
                                                int nt, int c, int n, long long row, float (&V)[32]) {
@@ -203,8 +225,8 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmKParams& p, const uint
     for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]);
     if (EPI != EPI_GENERIC || col + 8 <= p.cout) {
       {
-        const float4 b0 = *reinterpret_cast<const float4*>(sbias + c + j);
-        const float4 b1 = *reinterpret_cast<const float4*>(sbias + c + j + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + j);
+        const float4 b1 = *reinterpret_cast<const float4*>(sbias + j + 4);
         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
         f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
       }
@@ -265,7 +287,7 @@ __device__ __forceinline__ void epilogue_chunk(const IGemmKParams& p, const uint
       // EPI_GENERIC ragged tail (cout not a multiple of 8, e.g. the 4- and 3-channel output convs): scalar path
       for (int e = 0; e < 8 && col + e < p.cout; ++e) {
         float x = f[e];
-        x += sbias[c + j + e];
+        x += sbias[j + e];
         if (p.rowbias) x += __ldg(p.rowbias + static_cast<long long>(n) * p.rowbias_ld + col + e);
         x = apply_act(x, p.act);
         if (p.residual) x += from_act(p.residual[row * p.res_ld + col + e]);
@@ -282,7 +304,8 @@ template <int EPI, bool STATS>
 __device__ __forceinline__ void epilogue_tile_direct(const IGemmKParams& p, uint32_t trow, const float* __restrict__ sbias,
                                                      int nt, int n, bool row_ok, long long row, int hh, int lane,
                                                      float* __restrict__ gtab) {
-  for (int c = hh * 32; c < p.bn; c += 64) {
+  int k = 0;
+  for (int c = hh * 32; c < p.bn; c += 64, ++k) {
     if (nt * p.bn + c >= p.cout) break;
     uint32_t v[32];
     tmem_ld32(trow + uint32_t(c), v);
@@ -292,17 +315,19 @@ __device__ __forceinline__ void epilogue_tile_direct(const IGemmKParams& p, uint
 #pragma unroll
       for (int i = 0; i < 32; ++i) V[i] = 0.f;
     }
-    if (row_ok) epilogue_chunk<EPI, STATS>(p, v, sbias, nt, c, n, row, V);
+    if (row_ok) epilogue_chunk<EPI, STATS>(p, v, sbias + k * 32, nt, c, n, row, V);
     if (STATS) gn_store_chunk(V, lane, gtab + (c >> 5) * 128);
   }
 }
 
 CB_DEVINL void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  // no "memory" clobber: the panels are touched only through these volatile asms (ordered among themselves and
+  // against the proxy fence), so ordinary loads (the bias slices) may be scheduled across the stores
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
 }
 CB_DEVINL uint4 ld_shared_v4(uint32_t addr) {
   uint4 r;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
 
@@ -339,13 +364,15 @@ __device__ __forceinline__ void staged_chunk(const IGemmKParams& p, const uint32
       const float4 g0 = *reinterpret_cast<const float4*>(sbg + 8 * j);
       const float4 g1 = *reinterpret_cast<const float4*>(sbg + 8 * j + 4);
       const float gb[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float gv[8];
       if (ln.lnc) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(fmaf(ln.rs, __uint_as_float(g[8 * j + e]), gb[e]));
+        for (int e = 0; e < 8; ++e) gv[e] = fmaf(ln.rs, __uint_as_float(g[8 * j + e]), gb[e]);
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] *= gelu_fast_f(__uint_as_float(g[8 * j + e]) + gb[e]);
+        for (int e = 0; e < 8; ++e) gv[e] = __uint_as_float(g[8 * j + e]) + gb[e];
       }
+      geglu_mul8(f, gv);
     }
     if (EPI == EPI_ROWBIAS) {
       if (rowb_ok && col0 + 8 * j + 8 <= p.cout) {
@@ -418,8 +445,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
   const uint32_t bres_bar = misc + 48u;
   const uint32_t tmem_slot = misc + 56u;
   auto resid_bar = [&](int ew) { return misc + 64u + 8u * uint32_t(ew); };
-  const uint32_t bias_smem = (misc + 64u + 8u * EPI_WARPS + 15u) & ~15u;  // float[3][256]: a sub-tile's bias slice per accumulator slot
-  const uint32_t gn_smem = bias_smem + 3u * 256u * 4u;   // float[2 tiles][8 chunks][4 quarters][32] (only when gn_part)
+  const uint32_t bias_smem = (misc + 64u + 8u * EPI_WARPS + 15u) & ~15u;  // float[EPI_WARPS][128]: every epilogue warp stages the bias of its own chunks
+  const uint32_t gn_smem = bias_smem + uint32_t(EPI_WARPS) * 128u * 4u;   // float[2 tiles][8 chunks][4 quarters][32] (only when gn_part)
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -460,7 +487,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {   // (not `lane == 0`: under a divergent branch every UTMALDG / UTCHMMA is wrapped in an ELECT / BRA.U.ANY loop)
       if (p.resident_b) {
         int mt, nt;
         if (sched.get(0, mt, nt)) {
@@ -474,9 +501,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       uint32_t phase = 0;
       int mt, nt;
       for (int i = 0; sched.get(i, mt, nt); ++i) {
-        const int tw = mt % p.tiles_w;
-        const int th = (mt / p.tiles_w) % p.tiles_h;
-        const int tn = mt / (p.tiles_w * p.tiles_h);
+        int tw, th, tn, mrow;
+        p.fd_tw.divmod(mt, mrow, tw);
+        p.fd_th.divmod(mrow, tn, th);
         const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tn * p.TN;
         const int ng = sched.group(nt), ks = sched.split(nt);
         const int subs = sched.subs<NSUB>(ng);
@@ -510,7 +537,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair mode: the leader CTA's thread drives both tensor cores) =====================
-    if (lane == 0 && pair_rank == 0) {
+    if (pair_rank == 0 && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int mt, nt;
@@ -590,18 +617,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       const int ksi = sched.split(ngs);
       const int buf = acc_cnt % NACC;
       const uint32_t use = uint32_t(acc_cnt / NACC);
-      const int tw = mt % p.tiles_w;
-      const int th = (mt / p.tiles_w) % p.tiles_h;
-      const int tn = mt / (p.tiles_w * p.tiles_h);
+      // bias of this warp's chunks, requested first: the load latency overlaps the rest of the tile set-up
+      float bx[4], bg[2] = {0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = hh * 32 + 64 * k;
+        const int bc = nt * p.bn + c + lane;
+        bx[k] = (c < ocols && p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
+        if (GEGLU && k < 2) bg[k] = (c < ocols && bc + ocols < p.bias_len) ? __ldg(p.bias + bc + ocols) : 0.f;
+      }
+      int tw, th, tn, mrow;
+      p.fd_tw.divmod(mt, mrow, tw);
+      p.fd_th.divmod(mrow, tn, th);
       const int n = tn * p.TN + rn, h = th * p.TH + rh, w = tw * p.TW + rw;
       const bool row_ok = (n < p.n_img) && (h < p.H) && (w < p.W);
       const long long row = (static_cast<long long>(n) * p.H + h) * p.W + w;
       const int bxw = tw * p.TW + bw0, bxh = th * p.TH + bh0, bxn = tn * p.TN + bn0;
       if (STAGED) {
-        // the previous tile's TMA stores have finished reading this warp's panels
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        if (EPI == EPI_RES && lane == 0) {
+        // the previous tile's TMA stores have finished reading this warp's panels (without a residual to load into
+        // them the wait moves down to the first write of a panel, behind the accumulator wait and the TMEM load)
+        if (EPI == EPI_RES) {
+          if (elect_one()) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        if (EPI == EPI_RES && elect_one()) {
           int cnt = 0;
           for (int c = hh * 32; c < ocols && nt * ocols + c < p.cout; c += 64) ++cnt;
           if (cnt > 0) {
@@ -612,17 +651,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           }
         }
       }
-      // stage this tile's bias slice (overlaps the MMAs of this tile); the named barrier also orders the reuse of
-      // the slot against the slowest warp's reads two tiles ago
-      float* sb = sbias_all + buf * 256;
-      for (int c = threadIdx.x - 64; c < p.bn; c += 32 * EPI_WARPS) {
-        const int bc = nt * p.bn + c;
-        sb[c] = (p.bias != nullptr && bc < p.bias_len) ? __ldg(p.bias + bc) : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+      // this warp's bias values: chunk k of the warp at [32 k], the GEGLU gate half at [64 + 32 k].  Private to the
+      // warp, so no barrier between the epilogue warps: they drift apart and hide each other's TMEM-load, fence and
+      // store latencies instead of meeting them in lockstep.  (Loaded at the top of the tile, see bx / bg.)
+      float* sb = sbias_all + ew * 128;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sb[k * 32 + lane] = bx[k];
+      if (GEGLU) { sb[64 + lane] = bg[0]; sb[96 + lane] = bg[1]; }
+      __syncwarp();
       // fused GroupNorm statistics: every warp has stored the previous tile's chunk totals -> write that tile's row
       float* gtab = gn_tab + (acc_cnt & 1) * 1024 + q * 32;
       if (STATS_OK && do_gn) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
         if (g_prev_row >= 0) gn_flush_tile(p, gn_tab + ((acc_cnt - 1) & 1) * 1024, ew, lane, g_prev_row, g_prev_img0, g_prev_nt);
         g_prev_row = th * p.tiles_w + tw; g_prev_img0 = tn * p.TN; g_prev_nt = nt;
       }
@@ -653,17 +694,21 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
           tmem_ld32(trow + uint32_t(c), v);
           if (GEGLU) tmem_ld32(trow + uint32_t(ocols + c), g);
           tmem_ld_wait();
+          if (EPI != EPI_RES && k == 0) {
+            if (elect_one()) tma_store_wait_read<0>();
+            __syncwarp();
+          }
           const uint32_t panel = my_stg + uint32_t(k) * PANEL_BYTES;
           float V[32];
           if (STATS_OK && do_gn) {
-            staged_chunk<EPI, STATS_OK>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane, row_ok, V, ln, ls, lq);
+            staged_chunk<EPI, STATS_OK>(p, v, GEGLU ? g : v, sb + k * 32, sb + 64 + k * 32, rowb, n < p.n_img, col0, panel, lane, row_ok, V, ln, ls, lq);
             gn_store_chunk(V, lane, gtab + (c >> 5) * 128);
           } else {
-            staged_chunk<EPI, false>(p, v, GEGLU ? g : v, sb + c, sb + ocols + c, rowb, n < p.n_img, col0, panel, lane, row_ok, V, ln, ls, lq);
+            staged_chunk<EPI, false>(p, v, GEGLU ? g : v, sb + k * 32, sb + 64 + k * 32, rowb, n < p.n_img, col0, panel, lane, row_ok, V, ln, ls, lq);
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {   // elect.sync names the same lane for the same mask every time: it owns the bulk groups
             tma_store_4d(&mapO, panel, col0, bxw, bxh, bxn);
             tma_store_commit();
           }
@@ -688,7 +733,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ 
       asm volatile("bar.sync 1, 256;" ::: "memory");
       gn_flush_tile(p, gn_tab + ((acc_cnt - 1) & 1) * 1024, ew, lane, g_prev_row, g_prev_img0, g_prev_nt);
     }
-    if (STAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (STAGED && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -889,7 +934,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
 
   // ---- schedule: B-stationary when one N tile's whole K extent fits beside a >= 4-stage A ring and every CTA of
   //      that N tile gets several M tiles; otherwise stream A and B through the ring
-  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 768 + 64 + (d->gn_partials ? sizeof(float) * 2048 : 0);
+  const size_t fixed = 1024 + 16 * 12 + 160 + 16 + sizeof(float) * 128 * EPI_WARPS + 64 + (d->gn_partials ? sizeof(float) * 2048 : 0);
   const size_t b_chunk = (size_t)(two ? d->bn / 2 : d->bn) * 128;
   const size_t res_bytes = (size_t)num_k * b_chunk;
   int resident = 0;
@@ -914,6 +959,14 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
   p.stages = stages;
   const size_t smem = (resident ? res_bytes : 0) + (size_t)stages * stage_bytes + staging + fixed;
   CB_REQUIRE(smem <= (size_t)SMEM_LIMIT, "cb_igemm: tile needs %zu bytes of shared memory", smem);
+  {
+    const long long work = (long long)(two ? p.m_pairs : p.m_tiles) * p.n_groups * ksplit;
+    CB_REQUIRE(work < (1ll << 30), "cb_igemm: %lld work items exceed the tile scheduler's range", work);
+    p.total_work = int(work);
+    p.fd_tw = make_fastdiv(p.tiles_w);
+    p.fd_th = make_fastdiv(p.tiles_h);
+    p.fd_work = make_fastdiv(p.n_groups * ksplit);
+  }
   if (two) {
     const long long total = (long long)p.m_pairs * p.n_groups * ksplit;
     const long long clusters = total < g_num_sms / 2 ? total : g_num_sms / 2;
