@@ -126,13 +126,17 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   auto tP = [&](int w) {
     return p.p_alias ? tS(w) : tmem_base + uint32_t(p.nwg) * (128u + uint32_t(p.dpad)) + uint32_t(w) * 64u;
   };
-  auto stage_of = [&](int g) { return g % p.stages; };
-  auto phase_of = [&](int g) { return uint32_t((g / p.stages) & 1); };
+  // position in the K/V ring, advanced block by block (no `% stages` on the issue paths)
+  struct Ring {
+    int st; uint32_t ph;
+    __device__ __forceinline__ void next(int stages) { if (++st == stages) { st = 0; ph ^= 1u; } }
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int it = 0, g = 0;
+    if (elect_one()) {   // (not `lane == 0`: a divergent branch wraps every UTMALDG / UTCHMMA in an ELECT / BRA.U.ANY loop)
+      int it = 0;
+      Ring r{0, 0u};
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const int bh = item_bh(item), q_first = item_q_first(item), nact = item_nact(item);
         const int b_idx = bh / p.heads, h_idx = bh - b_idx * p.heads;
@@ -142,9 +146,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           for (int pn = 0; pn < p.np; ++pn)
             tma_load_4d(sQ + uint32_t(w) * tile_bytes + uint32_t(pn) * PANEL_BYTES, &mapQ, q_full, pn * 64,
                         q_first + w * ATT_BM, h_idx, b_idx);
-        for (int j = 0; j < nblk; ++j, ++g) {
-          const int st = stage_of(g);
-          const uint32_t ph = phase_of(g);
+        for (int j = 0; j < nblk; ++j, r.next(p.stages)) {
+          const int st = r.st;
+          const uint32_t ph = r.ph;
           mbar_wait(k_empty(st), ph ^ 1u);
           mbar_expect_tx(k_full(st), tile_bytes);
           for (int pn = 0; pn < p.np; ++pn)
@@ -161,57 +165,63 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   } else if (warp == 1 || warp == 10) {
     // ===================== MMA issuers (one thread per query tile) =====================
     const int w = (warp == 1) ? 0 : 1;
-    if (lane == 0 && w < p.nwg) {
+    if (w < p.nwg && elect_one()) {
+      // descriptors are 64-bit adds on precomputed bases (start address field = bytes >> 4)
+      const uint64_t qd0 = make_sdesc_sw128(sQ + uint32_t(w) * tile_bytes, 16, 1024), kd0 = make_sdesc_sw128(sK, 16, 1024);
+      const uint64_t vd0 = make_sdesc_sw128(sV, PANEL_BYTES, 1024);
+      const uint32_t ts = tS(w), tp = tP(w), to = tO(w);
+      const int ksteps = p.dpad / 16;
       auto issue_qk = [&](int kstage) {
-        const uint32_t qb = sQ + uint32_t(w) * tile_bytes, kb = sK + uint32_t(kstage) * tile_bytes;
-        const int ksteps = p.dpad / 16;
+        const uint64_t kd = kd0 + uint64_t(kstage) * (tile_bytes >> 4);
         for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t off = uint32_t(ks >> 2) * PANEL_BYTES + uint32_t(ks & 3) * 32u;
-          umma_bf16(tS(w), make_sdesc_sw128(qb + off, 16, 1024), make_sdesc_sw128(kb + off, 16, 1024), p.idesc_qk, ks != 0);
+          const uint64_t off = uint64_t(ks >> 2) * (PANEL_BYTES >> 4) + uint64_t(ks & 3) * 2u;
+          umma_bf16(ts, qd0 + off, kd + off, p.idesc_qk, ks != 0);
         }
       };
       auto issue_pv = [&](int vstage, bool accumulate) {
-        const uint32_t vb = sV + uint32_t(vstage) * tile_bytes;
+        const uint64_t vd = vd0 + uint64_t(vstage) * (tile_bytes >> 4);
+#pragma unroll
         for (int ks = 0; ks < ATT_BN / 16; ++ks) {
-          const uint32_t boff = uint32_t(ks) * 2048u;                                       // V: 16 kv rows = 2 atoms
-          // A = P from TMEM: 16 K-values of a row = 8 columns (two 16-bit values per 32-bit cell)
-          umma_ts(tO(w), tP(w) + uint32_t(ks) * 8u, make_sdesc_sw128(vb + boff, PANEL_BYTES, 1024),
-                  p.idesc_pv, (accumulate || ks != 0) ? 1u : 0u);
+          // V: 16 kv rows = 2 atoms = 2048 bytes; A = P from TMEM: 16 K-values of a row = 8 columns
+          umma_ts(to, tp + uint32_t(ks) * 8u, vd + uint64_t(ks) * (2048u >> 4), p.idesc_pv, (accumulate || ks != 0) ? 1u : 0u);
         }
       };
-      int it = 0, g0 = 0;      // item count of this CTA, global block counter at the start of the item
+      int it = 0;              // item count of this CTA
+      Ring rq{0, 0u}, rv{0, 0u};   // ring positions of the next Q*K^T / the next P*V (both advance nblk per item)
       int cw = 0, aw = 0;      // blocks / items this query tile has been ACTIVE for (phases of its private barriers)
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it, g0 += nblk) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
         const bool active = w < item_nact(item);
         mbar_wait(q_full, uint32_t(it & 1));
         if (!active) {
           // idle tile (ragged last query pair): stay in lockstep with the ring, release every stage it is handed
           mbar_arrive(q_free);
-          for (int j = 0; j < nblk; ++j) {
-            mbar_wait(k_full(stage_of(g0 + j)), phase_of(g0 + j));
-            mbar_arrive(k_empty(stage_of(g0 + j)));
-            mbar_wait(v_ready(stage_of(g0 + j)), phase_of(g0 + j));
-            mbar_arrive(v_empty(stage_of(g0 + j)));
+          for (int j = 0; j < nblk; ++j, rq.next(p.stages), rv.next(p.stages)) {
+            mbar_wait(k_full(rq.st), rq.ph);
+            mbar_arrive(k_empty(rq.st));
+            mbar_wait(v_ready(rv.st), rv.ph);
+            mbar_arrive(v_empty(rv.st));
           }
           continue;
         }
         auto do_qk = [&](int j) {     // Q*K^T of block j: once the scores of this tile's previous block are in registers
           if (cw + j > 0) mbar_wait(s_free(w), uint32_t((cw + j - 1) & 1));
-          mbar_wait(k_full(stage_of(g0 + j)), phase_of(g0 + j));
+          mbar_wait(k_full(rq.st), rq.ph);
           tc_fence_after();
-          issue_qk(stage_of(g0 + j));
+          issue_qk(rq.st);
           umma_commit(s_full(w));
-          umma_commit(k_empty(stage_of(g0 + j)));
+          umma_commit(k_empty(rq.st));
           if (j == nblk - 1) umma_commit(q_free);      // the item's last use of Q
+          rq.next(p.stages);
         };
         auto do_pv = [&](int j) {
           mbar_wait(p_full(w), uint32_t((cw + j) & 1));
-          mbar_wait(v_ready(stage_of(g0 + j)), phase_of(g0 + j));
+          mbar_wait(v_ready(rv.st), rv.ph);
           if (j == 0 && aw > 0) mbar_wait(o_free(w), uint32_t((aw - 1) & 1));   // previous item's O has been read out
           tc_fence_after();
-          issue_pv(stage_of(g0 + j), j > 0);
+          issue_pv(rv.st, j > 0);
           umma_commit(pv_done(w));
-          umma_commit(v_empty(stage_of(g0 + j)));
+          umma_commit(v_empty(rv.st));
+          rv.next(p.stages);
         };
         do_qk(0);
         for (int j = 0; j < nblk; ++j) {
@@ -231,11 +241,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     // ===================== V ones-column warp =====================
     // TMA zero-fills the pad columns of a V tile; column d becomes 1.0 so that P*V also yields the softmax row sum.
     const int pn = p.d >> 6, cw = p.d & 63;
-    int g = 0;
+    Ring rg{0, 0u};
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      for (int j = 0; j < nblk; ++j, ++g) {
-        const int st = stage_of(g);
-        mbar_wait(v_full(st), phase_of(g));
+      for (int j = 0; j < nblk; ++j, rg.next(p.stages)) {
+        const int st = rg.st;
+        mbar_wait(v_full(st), rg.ph);
         if (USE_ONES) {
           const uint32_t tile = sV + uint32_t(st) * tile_bytes + uint32_t(pn) * PANEL_BYTES;
 #ifdef CB_FP16
