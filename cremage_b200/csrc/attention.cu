@@ -427,13 +427,7 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   const int dpad = (d + 63) / 64 * 64;
   const int64_t bh = batch * heads;
   CB_REQUIRE(bh * ((nq + 127) / 128) < (1LL << 30), "cb_attention: problem too large");
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0, sms = 0;
-    CB_CHECK_CUDA(cudaGetDevice(&dev));
-    CB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    num_sms = sms > 0 ? sms : 148;
-  }
+  const int num_sms = sm_count();
   if (dpad == 64) {
     // head dims <= 64 with SHORT key sequences (cross-attention, nk = 77 * k): three query tiles per CTA over 64-row kv
     // blocks (attention64.cu) -- 0.058 ms against 0.089 ms for bh 128, 4096 x 77, d 40.  For long key sequences the
@@ -485,11 +479,11 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   }
   const size_t smem = (size_t)(p.nwg + 2 * p.stages) * p.np * PANEL_BYTES + 384;
   CB_REQUIRE(smem <= 227 * 1024, "cb_attention: needs %zu bytes of shared memory", smem);
-  static thread_local bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured{};
+  if (device_once_needed(configured)) {
     CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    device_once_done(configured);
   }
   const int rows_per_item = p.nwg * ATT_BM;
   const long long items = ((nq + rows_per_item - 1) / rows_per_item) * bh;

@@ -457,11 +457,11 @@ int launch_attention64(const void* q, int64_t q_ld, const void* k, int64_t k_ld,
   p.idesc_pv = make_idesc_f16(128, p.npv, 0, 1);   // B = V is MN-major
   p.out = (act_t*)out;
   const size_t smem = (size_t)A64_TILES * A64_QBYTES + 2 * (size_t)A64_STAGES * A64_KVBYTES + 544;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured{};
+  if (device_once_needed(configured)) {
     CB_CHECK_CUDA(cudaFuncSetAttribute(attention64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CB_CHECK_CUDA(cudaFuncSetAttribute(attention64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    device_once_done(configured);
   }
   const int rows_per_item = nt * A64_BM;
   const long long items = ((nq + rows_per_item - 1) / rows_per_item) * batch * heads;

@@ -76,6 +76,12 @@ int make_tmap_act(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 // What it buys is per-node latency: the small-batch regime (UNet batch 2: ~350 nodes of a few microseconds each).
 // ----------------------------------------------------------------------------------------------
 bool pdl_enabled();   // runtime.cu
+// Per-DEVICE state (runtime.cu).  cudaFuncSetAttribute opt-ins and the SM count belong to the current device, not to the
+// process or the calling thread: a host that drives several GPUs from one process gets each of them configured.
+int sm_count();                          // multiprocessors of the current device (148 on a B200; cached per device)
+struct DeviceOnce { unsigned char done[64]; };
+bool device_once_needed(DeviceOnce& o);  // true until device_once_done() was called for the current device
+void device_once_done(DeviceOnce& o);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t lc{};

@@ -751,7 +751,6 @@ static int pow2_cols(int bn) {
   return c;
 }
 
-static int g_num_sms = 0;
 
 }  // namespace cb
 
@@ -803,12 +802,7 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
     if (rc) return rc;
   }
 
-  if (g_num_sms == 0) {
-    int dev = 0, sms = 0;
-    CB_CHECK_CUDA(cudaGetDevice(&dev));
-    CB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    g_num_sms = sms > 0 ? sms : 148;
-  }
+  const int g_num_sms = sm_count();
 
   IGemmKParams p{};
   p.n_img = (int)d->n; p.H = (int)d->h; p.W = (int)d->w;
@@ -995,14 +989,14 @@ extern "C" int cb_igemm(const cb_igemm_desc* d, cudaStream_t stream) {
         igemm_kernel<EPI_HEADS, false, true, true>},
        {nullptr, igemm_kernel<EPI_PLAIN, true, true, true>, igemm_kernel<EPI_RES, true, true, true>,
         igemm_kernel<EPI_ROWBIAS, true, true, true>, igemm_kernel<EPI_GEGLU, true, true, true>, nullptr}}};
-  static thread_local bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured{};
+  if (device_once_needed(configured)) {
     for (int tw = 0; tw < 3; ++tw)
       for (int st = 0; st < 2; ++st)
         for (int i = 0; i < EPI_COUNT; ++i)
           if (kernels[tw][st][i])
             CB_CHECK_CUDA(cudaFuncSetAttribute(kernels[tw][st][i], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    configured = true;
+    device_once_done(configured);
   }
   const KernelFn kfn = kernels[two ? (p.nsub == 2 ? 2 : 1) : 0][staged ? 1 : 0][epi];
   CB_REQUIRE(kfn != nullptr, "cb_igemm: internal: no kernel for epilogue %d staged %d", epi, (int)staged);

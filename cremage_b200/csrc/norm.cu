@@ -701,9 +701,8 @@ int gn_apply_shape(int64_t C, int64_t hw, int* P) {
 }
 template <typename K>
 unsigned gn_apply_ctas(K kernel, int threads, size_t smem, int64_t n, int64_t hw, int P) {
-  int dev = 0, sms = 148, per_sm = 1;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
+  int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   long long ctas = (long long)sms * per_sm / n;
   const long long chunks = (hw + (long long)GN_APPLY_UNROLL * P - 1) / ((long long)GN_APPLY_UNROLL * P);
@@ -727,11 +726,11 @@ int launch_gn_apply(const void* x0, int64_t c0, const void* x1, int64_t c1, int6
     const int P = GN_TMA_THREADS / CV;
     const size_t smem = (size_t)GN_TMA_STAGES * GN_APPLY_UNROLL * P * C * 2;
     auto k = silu ? gn_apply_tma_kernel<true, PARTS> : gn_apply_tma_kernel<false, PARTS>;
-    static thread_local bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg{};
+    if (device_once_needed(cfg)) {
       CB_CHECK_CUDA(cudaFuncSetAttribute(gn_apply_tma_kernel<true, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       CB_CHECK_CUDA(cudaFuncSetAttribute(gn_apply_tma_kernel<false, PARTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      cfg = true;
+      device_once_done(cfg);
     }
     dim3 grid(gn_apply_ctas(k, GN_TMA_THREADS, smem, n, hw, P), (unsigned)n);
     (void)cb::launch_k(k, dim3(grid), dim3(GN_TMA_THREADS), (size_t)(smem), stream, (const act_t*)x0, (int)c0, (const act_t*)x1, (int)c1, hw, groups, P, eps, gamma,
@@ -794,10 +793,10 @@ extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int
       const int threads = (cvs * P + 31) / 32 * 32;
       if (threads <= 1024) {
         const size_t smem = (size_t)ppc * nch * 2 + sizeof(float) * (2 * (size_t)P * nch + 4 * (size_t)gset) + 16;
-        static thread_local bool cfg = false;
-        if (!cfg) {
+        static DeviceOnce cfg{};
+        if (device_once_needed(cfg)) {
           CB_CHECK_CUDA(cudaFuncSetAttribute(gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-          cfg = true;
+          device_once_done(cfg);
         }
         cudaLaunchConfig_t lc{};
         lc.gridDim = dim3(GN_CLUSTER, (unsigned)(groups / gset), (unsigned)n);
@@ -823,10 +822,10 @@ extern "C" int cb_groupnorm_nhwc(const void* x0, int64_t c0, const void* x1, int
   float* partials = stats + (size_t)n * groups * 2;
   unsigned int* counters = reinterpret_cast<unsigned int*>(partials + (size_t)n * g.splits * groups * 2);
   CB_CHECK_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * n, stream));
-  static thread_local bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured{};
+  if (device_once_needed(configured)) {
     CB_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
+    device_once_done(configured);
   }
   dim3 grid((unsigned)g.splits, (unsigned)n);
   (void)cb::launch_k(gn_stats_kernel, dim3(grid), dim3(g.threads), (size_t)(g.smem), stream, (const act_t*)x0, (int)c0, (const act_t*)x1,
@@ -905,11 +904,11 @@ extern "C" int cb_softmax_rows(const void* src, int src_f32, int64_t src_ld, voi
   CB_REQUIRE(cols > 0 && cols % 8 == 0 && cols <= 48 * 1024, "cb_softmax_rows: cols %lld unsupported (multiple of 8, <= 49152)", (long long)cols);
   CB_REQUIRE(src_ld % 8 == 0 && dst_ld % 8 == 0 && src_ld >= cols && dst_ld >= cols && rows > 0, "cb_softmax_rows: bad ld / rows");
   const size_t smem = sizeof(float) * cols;
-  static thread_local bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured{};
+  if (device_once_needed(configured)) {
     CB_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CB_CHECK_CUDA(cudaFuncSetAttribute(softmax_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    device_once_done(configured);
   }
   if (src_f32) (void)cb::launch_k(softmax_rows_kernel<true>, dim3((unsigned)rows), dim3(256), (size_t)(smem), stream, src, src_ld, (act_t*)dst, dst_ld, cols, scale);
   else (void)cb::launch_k(softmax_rows_kernel<false>, dim3((unsigned)rows), dim3(256), (size_t)(smem), stream, src, src_ld, (act_t*)dst, dst_ld, cols, scale);

@@ -15,17 +15,7 @@ int env_int(const char* name, int dflt) {
   return (e && *e) ? atoi(e) : dflt;
 }
 
-int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
-      sms = v;
-    else
-      sms = 148;   // B200
-  }
-  return sms;
-}
+int num_sms() { return sm_count(); }
 
 long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 int pow2_ceil(long long x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -95,6 +85,29 @@ int choose_ksplit_single(long long tiles, int num_k, int sms) {
   return best_ks;
 }
 
+// (bn, ksplit) of a single-CTA launch with fewer output tiles than SMs (small batch, the 8x8 / 16x16 levels).  Such a
+// launch is bound by how fast each CTA can fill its shared memory -- about 100 GB/s per SM with the ring this kernel
+// has room for (tools/micro/smem_fill_rate.cu, profiles/r2_small_batch.md) -- so the model is bytes per work item
+// (K blocks x (16 KB of A + 128 B x bn of B)) times rounds over the SMs, plus the reduce pass of a split.  Times in us.
+void choose_single_small(long long m_tiles, long long ncols, int num_k, long long rows, int multiple, bool can_split, int sms,
+                         int* bn_out, int* ks_out) {
+  const int cand[5] = {256, 160, 128, 64, 32};
+  const int splits[3] = {1, 3, 9};
+  double best = -1.0;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cand[i];
+    if (bn % multiple) continue;
+    for (int j = 0; j < (can_split ? 3 : 1); ++j) {
+      const int ks = splits[j];
+      const long long items = m_tiles * cdiv(ncols, bn) * ks;
+      const double fill = double(cdiv(items, sms)) * (double(num_k) / ks) * (16384.0 + 128.0 * bn) / 100e3;
+      const double reduce = ks > 1 ? 3.0 + double(ks) * double(rows) * double(ncols) * 8.0 / 3e6 : 0.0;
+      const double cost = fill + reduce + 0.05 * cdiv(ncols, bn);   // ties: the wider tile
+      if (best < 0 || cost < best) { best = cost; *bn_out = bn; *ks_out = ks; }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace cb
 
@@ -128,6 +141,16 @@ extern "C" int cb_igemm_plan(const cb_igemm_desc* d, cb_igemm_plan_t* plan) {
   else if (d->cta_pair < 0) pair = false;
   else if (d->mode == CB_EPI_GEGLU) pair = geglu_pair && m_tiles >= pair_min_m_tiles;
   else pair = pair_default && num_k >= pair_min_k && m_tiles >= pair_min_m_tiles;
+  // small-K linears with a wide output (q|k|v projections, 640-wide to_out / proj): the launch is bound by the epilogue
+  // and by re-reading A once per N tile, both of which a 256-row x 256-column pair tile halves (tools/sweep_plan.py:
+  // 320 -> 960 at 65 536 rows 56 -> 46 us, 640 -> 1920 at 16 384 rows 46 -> 36 us; 320 -> 320 stays single)
+  static const int wide_pair = env_int("CB_PAIR_WIDE_LINEAR", 1);
+  bool wide_linear = false;
+  if (!pair && d->cta_pair == 0 && wide_pair && pair_default && d->taps == 1 && d->mode != CB_EPI_GEGLU && ncols >= 640 &&
+      m_tiles >= pair_min_m_tiles && m_tiles * cdiv(ncols, 256) >= sms) {
+    pair = true;
+    wide_linear = true;
+  }
 
   // split-K (by tap groups) is available to plain 16-bit 3x3 convs; cb_splitk_reduce applies bias / row bias / residual
   bool can_split = d->mode == CB_EPI_LINEAR && d->taps == 9 && !d->out_f32 && d->act == CB_ACT_NONE && oscale == 1.f &&
@@ -135,11 +158,21 @@ extern "C" int cb_igemm_plan(const cb_igemm_desc* d, cb_igemm_plan_t* plan) {
   int bn = d->bn, nsub = d->nsub, ksplit = d->ksplit;
   const int multiple = d->mode == CB_EPI_GEGLU ? 64 : 32;
   if (bn <= 0) {
-    if (pair) {
+    if (pair && wide_linear) {
+      // one 256-column tile per pair unless that pads N by more than a tenth (then two 160-column sub-tiles per A stage)
+      if ((cdiv(ncols, 256) * 256 - ncols) * 10 <= ncols) { bn = 256; if (nsub <= 0) nsub = 1; }
+      else { bn = 160; if (nsub <= 0) nsub = 2; }
+      if (ksplit <= 0) ksplit = 1;
+    } else if (pair) {
       int a_bn = 128, a_nsub = 1, a_ks = 1;
       choose_bn_pair(ncols, m_tiles, multiple, can_split && ksplit <= 0 && split_default, sms, &a_bn, &a_nsub, &a_ks);
       bn = a_bn;
       if (nsub <= 0) nsub = a_nsub;
+      if (ksplit <= 0) ksplit = a_ks;
+    } else if (m_tiles * cdiv(ncols, 64) < sms) {
+      int a_bn = 64, a_ks = 1;
+      choose_single_small(m_tiles, ncols, num_k, rows, multiple, can_split && ksplit <= 0 && split_default, sms, &a_bn, &a_ks);
+      bn = a_bn;
       if (ksplit <= 0) ksplit = a_ks;
     } else {
       bn = choose_bn(ncols, m_tiles, multiple, sms);

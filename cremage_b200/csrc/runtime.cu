@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
+#include <mutex>
 
 #include "common.cuh"
 #include "cremage_b200.h"
@@ -30,6 +31,33 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+static int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+  return (dev >= 0 && dev < 64) ? dev : 0;
+}
+
+int sm_count() {
+  static std::atomic<int> cache[64];
+  const int slot = current_device_slot();
+  int v = cache[slot].load(std::memory_order_relaxed);
+  if (v == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, slot) != cudaSuccess || sms <= 0) {
+      (void)cudaGetLastError();
+      sms = 148;   // B200 (also what the planner assumes on a GPU-less host)
+    }
+    cache[slot].store(sms, std::memory_order_relaxed);
+    v = sms;
+  }
+  return v;
+}
+
+// The opt-ins guarded by these flags are idempotent, so two threads racing through the first call on a device only
+// repeat them; the flag is a plain byte per device.
+bool device_once_needed(DeviceOnce& o) { return reinterpret_cast<std::atomic<unsigned char>&>(o.done[current_device_slot()]).load(std::memory_order_acquire) == 0; }
+void device_once_done(DeviceOnce& o) { reinterpret_cast<std::atomic<unsigned char>&>(o.done[current_device_slot()]).store(1, std::memory_order_release); }
+
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
   return CB_ERR_CUDA;
@@ -41,15 +69,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static EncodeTiledFn resolve_encode() {
   static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
     if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
     else (void)cudaGetLastError();
-  }
+  });
   return fn;
 }
 
