@@ -37,7 +37,7 @@ constexpr int ATT_THREADS = 384;         // TMA warp, issuer (tile 0), 8 softmax
 constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
-  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias, skew;
+  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias;
   float scale_log2;
   uint32_t idesc_qk, idesc_pv, tmem_cols;
   act_t* out;
@@ -274,15 +274,6 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       if (w >= item_nact(item)) continue;
       const int bh = item_bh(item), q_first = item_q_first(item);
       float m_used = -INFINITY, l_run = 0.f;
-      if (w == 1 && p.skew > 0) {
-        // The two warpgroups share each scheduler's MUFU pipe.  Started together they stay in lockstep: both in the
-        // exponential phase (each at half rate), then both in the MUFU-free phase (TMEM load, max, P store, barriers)
-        // with the pipe idle.  Holding the second warpgroup back by about the length of the MUFU-free phase once per
-        // work item interleaves the phases for the rest of the item.
-        const long long t0 = clock64();
-        while (clock64() - t0 < p.skew) {}
-      }
-
       for (int j = 0; j < nblk; ++j) {
         const int c = cw + j;
         mbar_wait(s_full(w), uint32_t(c & 1));
@@ -472,11 +463,6 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   p.idesc_pv = make_idesc_f16(128, dpad, 0, 1);   // B = V is MN-major
   p.tmem_cols = 512u;
   p.out = (act_t*)out;
-  {
-    static int skew = -1;
-    if (skew < 0) { const char* e = getenv("CB_ATTN_SKEW"); skew = e ? atoi(e) : 1200; }   // clocks; measured 0.785 -> 0.770 ms at 4096^2 d 40 (profiles/r2_attention64.md)
-    p.skew = (p.nwg == 2 && nk > 256) ? skew : 0;
-  }
   const size_t smem = (size_t)(p.nwg + 2 * p.stages) * p.np * PANEL_BYTES + 384;
   CB_REQUIRE(smem <= 227 * 1024, "cb_attention: needs %zu bytes of shared memory", smem);
   static DeviceOnce configured{};
