@@ -37,7 +37,7 @@ constexpr int ATT_THREADS = 384;         // TMA warp, issuer (tile 0), 8 softmax
 constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
-  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias;
+  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias, pingpong;
   float scale_log2;
   uint32_t idesc_qk, idesc_pv, tmem_cols;
   act_t* out;
@@ -270,8 +270,21 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
     const uint32_t tSw = tS(w) + lane_off, tOw = tO(w) + lane_off, tPw = tP(w) + lane_off;
     int cw = 0;                                        // blocks this tile has been active for (barrier phases)
+    // Ping-pong of the MUFU sections.  The two warpgroups share each scheduler's MUFU pipe, one warp alone drives 90 %
+    // of it (tools/micro/mufu_rate.cu), and a block's MUFU-free part (S load, row maximum, P store, barriers) is about
+    // as long as its 128 exponentials -- but left alone the two warpgroups drift into the same phase and then both
+    // wait (profiles/r2_attention64.md).  Two named barriers hand the pipe back and forth: a warpgroup enters its
+    // exponentials only when the other one has left them.  An idle tile (ragged last item) still passes the token.
+    const bool pingpong = p.nwg == 2 && p.pingpong;
+    const int bar_mine = 2 + w, bar_other = 2 + (w ^ 1);
+    auto pp_wait = [&]() { if (pingpong) asm volatile("bar.sync %0, 256;" ::"r"(bar_mine) : "memory"); };
+    auto pp_pass = [&]() { if (pingpong) asm volatile("bar.arrive %0, 256;" ::"r"(bar_other) : "memory"); };
+    if (w == 1) pp_pass();                             // warpgroup 0 goes first
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      if (w >= item_nact(item)) continue;
+      if (w >= item_nact(item)) {
+        for (int j = 0; j < nblk; ++j) { pp_wait(); pp_pass(); }
+        continue;
+      }
       const int bh = item_bh(item), q_first = item_q_first(item);
       float m_used = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nblk; ++j) {
@@ -324,20 +337,30 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           }
         }
         float rs = 0.f;
+        // exponent arguments in place (FMA pipe), and the wait for the previous P*V (it read P) BEFORE the MUFU section:
+        // the section below is then straight-line code -- a spin loop in its middle is a basic-block boundary that
+        // kept the second 64 exponentials behind the pack / store of the first 64, with the MUFU pipe idle in between
+#pragma unroll
+        for (int e = 0; e < ATT_BN; ++e) s[e] = __float_as_uint(fmaf(__uint_as_float(s[e]), p.scale_log2, -m_used));
+        if (c > 0) mbar_wait(pv_done(w), uint32_t((c - 1) & 1));
+        pp_wait();
 #pragma unroll
         for (int cc = 0; cc < ATT_BN; cc += 64) {
           uint32_t pk[32];
 #pragma unroll
           for (int e = 0; e < 64; e += 2) {
-            pk[e >> 1] = exp2_pack(__uint_as_float(s[cc + e]), __uint_as_float(s[cc + e + 1]), p.scale_log2, m_used);
+            float e0, e1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(__uint_as_float(s[cc + e])));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(__uint_as_float(s[cc + e + 1])));
+            pk[e >> 1] = pack_act2(e0, e1);
             if (!USE_ONES) {
               const float2 b = unpack_act2(pk[e >> 1]);
               rs += b.x + b.y;
             }
           }
-          if (cc == 0 && c > 0) mbar_wait(pv_done(w), uint32_t((c - 1) & 1));   // the previous P*V has finished reading P
           tmem_st32(tPw + uint32_t(cc >> 1), pk);
         }
+        pp_pass();
         tmem_st_wait();
         if (!USE_ONES) l_run += rs;
         tc_fence_before();
@@ -388,6 +411,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
       }
     }
+    if (w == 0) pp_wait();   // absorbs warpgroup 1's last token so that no barrier is left half-arrived
   }
   tc_fence_before();
   __syncthreads();
@@ -463,6 +487,13 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   p.idesc_pv = make_idesc_f16(128, dpad, 0, 1);   // B = V is MN-major
   p.tmem_cols = 512u;
   p.out = (act_t*)out;
+  {
+    // measured (profiles/r2_attention64.md): helps the 128-column head dims (d 80: 0.090 -> 0.086 ms), costs at d <= 64
+    // (d 40: 0.684 -> 0.718 ms), where the hand-over latency outweighs the overlap it enforces
+    static int pp = -2;
+    if (pp == -2) { const char* e = getenv("CB_ATTN_PINGPONG"); pp = e ? atoi(e) : -1; }
+    p.pingpong = pp >= 0 ? pp : (dpad > 64 ? 1 : 0);
+  }
   const size_t smem = (size_t)(p.nwg + 2 * p.stages) * p.np * PANEL_BYTES + 384;
   CB_REQUIRE(smem <= 227 * 1024, "cb_attention: needs %zu bytes of shared memory", smem);
   static DeviceOnce configured{};
