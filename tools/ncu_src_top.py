@@ -6,9 +6,10 @@ import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-hdr = rows[1]
-ix = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+h0 = next(i for i, r in enumerate(rows) if "# Samples" in r)   # one or two title rows, depending on --print-source
+hdr = rows[h0]
+ix = {h: i for i, h in enumerate(hdr)}   # (duplicate "Source" columns: the last one, the SASS text, wins)
+data = [r for r in rows[h0 + 1:] if len(r) == len(hdr)]
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = {h: 0 for h in stalls}
 total = 0
