@@ -37,7 +37,7 @@ constexpr int ATT_THREADS = 384;         // TMA warp, issuer (tile 0), 8 softmax
 constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
-  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias, pingpong;
+  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias, pingpong, ksteps;
   float scale_log2;
   uint32_t idesc_qk, idesc_pv, tmem_cols;
   act_t* out;
@@ -170,7 +170,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       const uint64_t qd0 = make_sdesc_sw128(sQ + uint32_t(w) * tile_bytes, 16, 1024), kd0 = make_sdesc_sw128(sK, 16, 1024);
       const uint64_t vd0 = make_sdesc_sw128(sV, PANEL_BYTES, 1024);
       const uint32_t ts = tS(w), tp = tP(w), to = tO(w);
-      const int ksteps = p.dpad / 16;
+      const int ksteps = p.ksteps;   // ceil(d / 16): the pad columns are zeros, no K-step beyond the next multiple of 16
       auto issue_qk = [&](int kstage) {
         const uint64_t kd = kd0 + uint64_t(kstage) * (tile_bytes >> 4);
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -484,7 +484,9 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   p.use_ones = dpad > d;                 // spare column d of V carries 1.0 -> O[:, d] = softmax row sum
   p.scale_log2 = scale * 1.4426950408889634f;
   p.idesc_qk = make_idesc_f16(128, 128, 0, 0);
-  p.idesc_pv = make_idesc_f16(128, dpad, 0, 1);   // B = V is MN-major
+  p.ksteps = (d + 15) / 16;
+  // B = V is MN-major; N stops at the next multiple of 16 behind the ones column (d 40: 48 instead of 64 columns)
+  p.idesc_pv = make_idesc_f16(128, p.use_ones ? ((d + 1 + 15) / 16) * 16 : dpad, 0, 1);
   p.tmem_cols = 512u;
   p.out = (act_t*)out;
   {
