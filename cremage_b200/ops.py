@@ -292,6 +292,17 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
         d.epilogue = 2   # CB_EPILOGUE_STAGED: the strides live in the TMA-store tensor map
     plan = _lib.IGemmPlan()
     check(_lib.load().cb_igemm_plan(C.byref(d), C.byref(plan)), "cb_igemm_plan")
+    if ln_stats and LN_FUSE and LN_STAGE_BIG_K and plan.ln_out_slots == 0 and d.epilogue == 0 and plan.ksplit == 1:
+        # a large-K producer of the residual stream (ff.net.2 of a 1280-wide block: K = 5120) would take the direct
+        # epilogue, which carries no row statistics, and the next block's norm1 would fall back to a stand-alone
+        # LayerNorm launch: pin the staged epilogue when that makes the launch a statistics producer
+        d.epilogue = 2
+        plan2 = _lib.IGemmPlan()
+        check(_lib.load().cb_igemm_plan(C.byref(d), C.byref(plan2)), "cb_igemm_plan")
+        if plan2.ln_out_slots > 0 and plan2.ksplit == 1:
+            plan = plan2
+        else:
+            d.epilogue = 0
     d.tw, d.th, d.tn = plan.tw, plan.th, plan.tn
     bn, pair, ksplit = plan.bn, bool(plan.cta_pair), plan.ksplit
     d.bn, d.cta_pair, d.nsub, d.ksplit = plan.bn, plan.cta_pair, plan.nsub, plan.ksplit
@@ -351,6 +362,7 @@ def igemm(a0: torch.Tensor, wgt: torch.Tensor, cout: int, *, a1: Optional[torch.
 # fused LayerNorm: statistics from the producer's epilogue, gamma / beta folded into the consumer's weights
 # ------------------------------------------------------------------------------------------------------------------
 LN_FUSE = int(_os.environ.get("CB_LN_FUSE", "1"))   # 0: stand-alone cb_layernorm launches (A/B)
+LN_STAGE_BIG_K = int(_os.environ.get("CB_LN_STAGE_BIG_K", "1"))   # 0: large-K residual-stream producers keep the direct epilogue
 
 
 class LnFold:
