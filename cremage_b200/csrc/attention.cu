@@ -37,7 +37,7 @@ constexpr int ATT_THREADS = 384;         // TMA warp, issuer (tile 0), 8 softmax
 constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
-  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias, pingpong, ksteps;
+  int nq, nk, d, dpad, np, heads, bh, stages, nwg, use_ones, p_alias, pingpong, ksteps, split_from, total_items;
   float scale_log2;
   uint32_t idesc_qk, idesc_pv, tmem_cols;
   act_t* out;
@@ -86,12 +86,20 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   // persistent CTA: work items (batch*head, query-tile pair) blockIdx.x, + gridDim.x, ...  Barrier phases and the
   // K/V ring position run on GLOBAL counters across items, so the producer prefetches the next item's Q / K / V
   // while the softmax groups still finish the current one, and the per-CTA set-up is paid once.
+  // Items below `split_from` are pairs of query tiles; the pairs that would form a last, mostly empty round over the
+  // CTAs are handed out as single tiles instead (item >= split_from: pair split_from + (item - split_from) / 2, tile
+  // (item - split_from) % 2), so that round costs one tile's time on twice as many SMs (cb_attention decides).
   const int rows_per_item = p.nwg * ATT_BM;
   const int qpairs = (p.nq + rows_per_item - 1) / rows_per_item;
-  const int total_items = qpairs * p.bh;
-  auto item_q_first = [&](int item) { return (item % qpairs) * rows_per_item; };
-  auto item_bh = [&](int item) { return item / qpairs; };
-  auto item_nact = [&](int item) { return (p.nwg == 2 && item_q_first(item) + ATT_BM < p.nq) ? 2 : 1; };
+  const int total_items = p.total_items;
+  auto item_pair = [&](int item) { return item < p.split_from ? item : p.split_from + ((item - p.split_from) >> 1); };
+  auto item_q_first = [&](int item) {
+    return (item_pair(item) % qpairs) * rows_per_item + (item < p.split_from ? 0 : ((item - p.split_from) & 1) * ATT_BM);
+  };
+  auto item_bh = [&](int item) { return item_pair(item) / qpairs; };
+  auto item_nact = [&](int item) {
+    return (p.nwg == 2 && item < p.split_from && item_q_first(item) + ATT_BM < p.nq) ? 2 : 1;
+  };
 
   if (tid == 0) {
     tma_prefetch_desc(&mapQ);
@@ -507,6 +515,20 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   const int rows_per_item = p.nwg * ATT_BM;
   const long long items = ((nq + rows_per_item - 1) / rows_per_item) * bh;
   dim3 grid((unsigned)(items < num_sms ? items : num_sms));   // persistent: one CTA per SM walks the work items
+  // The last round over the CTAs: `left` pairs on `grid` CTAs.  Handed out as 2 * left single tiles it costs one
+  // tile's time (0.73 of a pair's: 2 376 against 3 250 clocks per kv block, profiles/r2_attention64.md) when they
+  // fit one round -- SDXL's 1024-token level is 160 pairs on 148 SMs: 1 + 0.73 instead of 2 rounds.
+  p.split_from = (int)items;
+  p.total_items = (int)items;
+  {
+    static int tail = -1;
+    if (tail < 0) { const char* e = getenv("CB_ATTN_TAIL_SPLIT"); tail = e ? atoi(e) : 1; }
+    const long long left = items % (long long)grid.x;
+    if (tail && p.nwg == 2 && nq % rows_per_item == 0 && left > 0 && 2 * left <= (long long)grid.x) {
+      p.split_from = (int)(items - left);
+      p.total_items = (int)(items + left);
+    }
+  }
   if (p.use_ones) (void)cb::launch_k(attention_kernel<true>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
   else (void)cb::launch_k(attention_kernel<false>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
   CB_CHECK_CUDA(cudaGetLastError());

@@ -34,7 +34,8 @@ def _ref(q, k, v, batch, heads, nq, nk, d, scale):
     (3, 5, 200, 200, 48),      # d a multiple of 16 below 64: row sums in columns 48..63
     (2, 3, 150, 90, 8),        # tiny head dim
     (1, 8, 16384, 16384, 40),  # hires-fix second pass (BASELINE configs[3]): 16 384-token self-attention, 128 kv blocks
-    (2, 20, 1024, 1024, 64),   # SDXL 32x32 level: 20 heads of 64
+    (2, 20, 1024, 1024, 64),   # SDXL 32x32 level: 20 heads of 64; 160 pairs of query tiles: the last round runs as single tiles
+    (20, 8, 512, 512, 80),     # 320 pairs at d 80 (P aliases S, MUFU hand-over between the warpgroups): tail as single tiles
     (2, 10, 4096, 77, 64),     # SDXL cross attention at the 64x64 level
 ])
 @pytest.mark.parametrize("packed_qkv", [False, True])
