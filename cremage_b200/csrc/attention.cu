@@ -461,8 +461,14 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
       const char* e = getenv("CB_ATTN64");
       use64 = e ? atoi(e) : 1;
     }
-    const long long tiles = bh * ((nq + 127) / 128);
-    const int nt = (int)(tiles / num_sms < 3 ? tiles / num_sms : 3);
+    const long long qtiles = (nq + 127) / 128, tiles = bh * qtiles;
+    // two or three query tiles per CTA: rounds over the SMs x (per-item chain ~6 + one unit of MUFU work per tile) --
+    // SDXL's 1024 x 77 level (40 x 8 tiles) is 160 items = two rounds with two tiles, 120 items = one round with three
+    int nt = (int)(tiles / num_sms < 3 ? tiles / num_sms : 3);
+    if (nt == 2) {
+      auto cost = [&](int t) { const long long items = bh * ((qtiles + t - 1) / t); return ((items + num_sms - 1) / num_sms) * (6 + t); };
+      if (cost(3) < cost(2)) nt = 3;
+    }
     if (nt >= 2 && (use64 == 2 || (use64 == 1 && nk <= 256)))
       return launch_attention64(q, q_ld, k, k_ld, v, v_ld, out, batch, heads, nq, nk, d, scale, nt, num_sms, stream);
   }
