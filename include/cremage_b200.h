@@ -12,7 +12,7 @@
  *    CUDA-graph capturable);
  *  - return value: 0 = ok, negative = error (cb_last_error() gives a thread-local message);
  *  - activations are NHWC in the build's 16-bit type ("pixel rows x channels": fp16 in libcremage_b200_fp16.so -- the
- *    default, the reference's own GPU precision -- bf16 in libcremage_b200_bf16.so; cb_act_dtype() tells which; "bf16"
+ *    default, the reference's own GPU precision -- bf16 in libcremage_b200_bf16.so; cb_act_dtype() tells which; "act16"
  *    in the comments below stands for that type), statistics / latents / schedules are fp32.
  */
 #ifndef CREMAGE_B200_H_
@@ -33,7 +33,7 @@ typedef struct CUstream_st* cudaStream_t;
  * ------------------------------------------------------------------------------------------------------------- */
 const char* cb_last_error(void);
 int cb_version(void);
-/* 16-bit storage type this build of the library computes in: 1 = fp16, 2 = bf16 ("bf16" in the comments below
+/* 16-bit storage type this build of the library computes in: 1 = fp16, 2 = bf16 ("act16" in the comments below
  * means this type).  fp16 is the reference's own GPU precision (model.half() + autocast) and the default. */
 int cb_act_dtype(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
@@ -56,7 +56,7 @@ enum { CB_ACT_NONE = 0, CB_ACT_SILU = 1 };
 enum { CB_EPILOGUE_AUTO = 0, CB_EPILOGUE_DIRECT = 1, CB_EPILOGUE_STAGED = 2 };
 
 typedef struct cb_igemm_desc {
-  /* A operand: one or two NHWC bf16 tensors [a_n][a_h][a_w][c] sharing the pixel grid; channels of source 1
+  /* A operand: one or two NHWC act16 tensors [a_n][a_h][a_w][c] sharing the pixel grid; channels of source 1
    * follow those of source 0 in the K order (the UNet skip concat).  A plain [M,K] matrix is n=h=1, w=M. */
   const void* a0; int64_t c0; int64_t a0_ld; /* a0_ld: elements between pixels (0 = c0) */
   const void* a1; int64_t c1; int64_t a1_ld;
@@ -67,7 +67,7 @@ typedef struct cb_igemm_desc {
   /* taps: A box of tap t is read at pixel offset (tap_dw, tap_dh, tap_dn)[t] from the output pixel */
   int taps;
   int tap_dw[9], tap_dh[9], tap_dn[9];
-  /* weights: bf16 [wgt_rows][taps * (ceil64(c0) + ceil64(c1))], K-major, zero padded */
+  /* weights: act16 [wgt_rows][taps * (ceil64(c0) + ceil64(c1))], K-major, zero padded */
   const void* wgt; int64_t wgt_rows;
   int64_t cout;          /* valid output columns (GEGLU: columns of the gated output = wgt_rows / 2) */
   /* epilogue */
@@ -76,9 +76,9 @@ typedef struct cb_igemm_desc {
   const float* bias;     /* [cout] fp32 or NULL (GEGLU: [2*cout], permuted like the weight rows) */
   const float* rowbias;  /* [n][rowbias_ld] fp32 per-image bias (timestep embedding) or NULL */
   int64_t rowbias_ld;
-  const void* residual;  /* bf16 [rows][res_ld] added last, or NULL */
+  const void* residual;  /* act16 [rows][res_ld] added last, or NULL */
   int64_t res_ld;
-  void* out; int64_t out_ld; int out_f32; /* bf16 (0) or fp32 (1) output, row stride out_ld */
+  void* out; int64_t out_ld; int out_f32; /* act16 (0) or fp32 (1) output, row stride out_ld */
   float out_scale;       /* multiplies the final value (0 = 1.0) */
   /* CB_EPI_HEADS: column -> (which, head, j), row -> (batch, token); out[which][batch*heads+head][token][dpad] */
   int heads_d, heads_dpad, heads_h, heads_tokens;
@@ -164,13 +164,13 @@ int cb_splitk_reduce(const float* part, int splits, int64_t rows, int64_t cout, 
 int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t k_ld, const void* v, int64_t v_ld, void* out,
                  int64_t batch, int64_t heads, int64_t nq, int64_t nk, int d, float scale, cudaStream_t stream);
 
-/* row softmax: dst[r][:] = softmax(scale * src[r][:]); src fp32 (src_f32 = 1) or bf16, dst bf16 (may alias a bf16
+/* row softmax: dst[r][:] = softmax(scale * src[r][:]); src fp32 (src_f32 = 1) or act16, dst act16 (may alias a act16
  * src); VAE AttnBlock, ldm/modules/diffusionmodules/model.py:196-198 */
 int cb_softmax_rows(const void* src, int src_f32, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows,
                     int64_t cols, float scale, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * GroupNorm (+SiLU) over NHWC bf16, fp32 statistics; replaces GroupNorm32+SiLU (ldm/modules/diffusionmodules/
+ * GroupNorm (+SiLU) over NHWC act16, fp32 statistics; replaces GroupNorm32+SiLU (ldm/modules/diffusionmodules/
  * util.py:214-216, openaimodel.py:205-207,229-231), Normalize (attention.py:189, model.py:45) + nonlinearity
  * (model.py:40-42).  Two sources = normalise the channel concat without materialising it.
  *   stats: workspace of cb_groupnorm_workspace_bytes(c0 + c1, n, hw, groups) bytes; its first n*groups*2 floats
@@ -192,7 +192,7 @@ int cb_groupnorm_from_partials(const void* x0, int64_t c0, const float* part0, i
                                const float* gamma, const float* beta, int silu, void* out, float* stats,
                                cudaStream_t stream);
 
-/* LayerNorm over the last dim of bf16 [rows][c] (nn.LayerNorm, ldm/modules/attention.py:900-902) */
+/* LayerNorm over the last dim of act16 [rows][c] (nn.LayerNorm, ldm/modules/attention.py:900-902) */
 int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, const float* gamma, const float* beta, void* out,
                  cudaStream_t stream);
 
@@ -204,26 +204,26 @@ int cb_layernorm(const void* x, int64_t rows, int64_t c, float eps, const float*
  * 16-bit (dst may alias base), ctrl NCHW fp32 / fp16 / bf16 (ctrl_dtype 0 / 1 / 2) as the ControlNet returns it */
 int cb_add_nchw_to_nhwc(const void* base, const void* ctrl, int ctrl_dtype, int64_t n, int64_t c, int64_t hw, void* dst,
                         cudaStream_t stream);
-/* NCHW (fp32, or fp16/bf16 when src_dtype = 1/2) -> NHWC bf16 with channel padding to c_pad (zeros), times scale */
+/* NCHW (fp32, or fp16/bf16 when src_dtype = 1/2) -> NHWC act16 with channel padding to c_pad (zeros), times scale */
 int cb_nchw_to_nhwc(const void* src, int src_dtype, int64_t n, int64_t c, int64_t hw, int64_t c_pad, float scale,
                     void* dst, cudaStream_t stream);
 /* 1x1 channel mix fused with the layout change: dst[n][p][co] = sum_ci w[co][ci] * src[n][ci][p] * scale + b[co]
  * (AutoencoderKL.post_quant_conv + the 1/scale_factor of decode_first_stage, ldm/models/autoencoder.py:303,336,
- * ldm/models/diffusion/ddpm.py:794-798); src NCHW fp32, w fp32 [cout][c], dst NHWC bf16 [n][hw][c_pad] */
+ * ldm/models/diffusion/ddpm.py:794-798); src NCHW fp32, w fp32 [cout][c], dst NHWC act16 [n][hw][c_pad] */
 int cb_pointwise_nchw_to_nhwc(const float* src, int64_t n, int64_t c, int64_t hw, const float* w, const float* b,
                               int64_t cout, int64_t c_pad, float scale, void* dst, cudaStream_t stream);
-/* NHWC (bf16, or fp32 when src_f32) [n][hw][c_ld] -> NCHW fp32 [n][c][hw], first c channels */
+/* NHWC (act16, or fp32 when src_f32) [n][hw][c_ld] -> NCHW fp32 [n][c][hw], first c channels */
 int cb_nhwc_to_nchw_f32(const void* src, int src_f32, int64_t n, int64_t c, int64_t hw, int64_t c_ld, float* dst,
                         cudaStream_t stream);
-/* nearest-neighbour 2x upsample NHWC bf16 (F.interpolate(scale_factor=2, 'nearest'), openaimodel.py:120, model.py:61) */
+/* nearest-neighbour 2x upsample NHWC act16 (F.interpolate(scale_factor=2, 'nearest'), openaimodel.py:120, model.py:61) */
 int cb_upsample2x_nhwc(const void* src, int64_t n, int64_t h, int64_t w, int64_t c, void* dst, cudaStream_t stream);
 /* parity split for stride-2 convs: src [n][h][w][c] -> dst [2*ph+pw][n][h/2][w/2][c] */
 int cb_parity_split_nhwc(const void* src, int64_t n, int64_t h, int64_t w, int64_t c, void* dst, cudaStream_t stream);
 /* sinusoidal timestep embedding (ldm/modules/diffusionmodules/util.py:151-171): t fp32 [n], freqs fp32 [dim/2]
- * (host-built with the reference's expression) -> bf16 [n][dim] = [cos(t*f) | sin(t*f)] */
+ * (host-built with the reference's expression) -> act16 [n][dim] = [cos(t*f) | sin(t*f)] */
 int cb_timestep_embedding(const float* t, int64_t n, int dim, const float* freqs, void* out, cudaStream_t stream);
-/* direct 3x3 conv for tiny channel counts (UNet conv_in 4->320, VAE conv_in 4->512): src NHWC bf16 [n][h][w][cin_ld],
- * wgt fp32 [3][3][cin][cout], out NHWC bf16 */
+/* direct 3x3 conv for tiny channel counts (UNet conv_in 4->320, VAE conv_in 4->512): src NHWC act16 [n][h][w][cin_ld],
+ * wgt fp32 [3][3][cin][cout], out NHWC act16 */
 int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64_t w, int cin, int64_t cin_ld, const float* wgt,
                          const float* bias, int64_t cout, void* out, cudaStream_t stream);
 /* DiagonalGaussianDistribution of AutoencoderKL.encode (ldm/modules/distributions/distributions.py:24-37;
@@ -232,7 +232,7 @@ int cb_conv3x3_small_cin(const void* src, int64_t n, int64_t h, int64_t w, int c
  * be NULL, noise NULL = the mode; scale 0 = 1 */
 int cb_diag_gaussian(const float* moments, const float* noise, int64_t n, int64_t c, int64_t hw, float scale,
                      float* mean_out, float* std_out, float* sample_out, cudaStream_t stream);
-/* y = silu(x) or y = silu(x + add) over bf16 vectors (SDXL label_emb path) */
+/* y = silu(x) or y = silu(x + add) over act16 vectors (SDXL label_emb path) */
 int cb_silu_add(const void* x, const void* add, int64_t count, void* out, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
