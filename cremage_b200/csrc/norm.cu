@@ -361,6 +361,12 @@ gn_apply_tma_kernel(const act_t* __restrict__ x0, int c0, const act_t* __restric
         v[u].u[0] = t.x; v[u].u[1] = t.y; v[u].u[2] = t.z; v[u].u[3] = t.w;
       }
     }
+    // The refill below is an ASYNC-proxy write to shared memory that these GENERIC-proxy loads have just read: the
+    // CTA barrier orders the loads against the other threads, not against the bulk-copy engine, so every thread
+    // fences its reads into the async proxy first.  (Without it one 256-byte pixel of a stage was, about once in a
+    // million chunks, read after the next chunk had started to land: one wrong pixel in ~3 % of the 8 x 512 x 512 x 128
+    // calls, tools/gn_repro.py.)
+    fence_proxy_async_smem();
     __syncthreads();   // every thread holds its vectors: the stage may be refilled
     if (threadIdx.x == 0) {
       const long long nx = i + (long long)GN_TMA_STAGES * gridDim.x;

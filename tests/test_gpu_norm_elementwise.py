@@ -221,6 +221,25 @@ def test_streaming_groupnorm_is_bit_reproducible(monkeypatch, n, h, w, c0, c1):
     assert (first.float() - want).abs().max().item() < 3e-2
 
 
+def test_streaming_groupnorm_ring_reuse_at_the_largest_vae_tensor(monkeypatch):
+    """8 x 512 x 512 x 128 (the VAE decoder's last level at batch 8): 32 768 chunks go through the apply pass's
+    bulk-copy ring per call.  The stage refill is an async-proxy write over shared memory that generic-proxy loads have
+    just read; without the proxy fence in front of the CTA barrier about one chunk in a million was read after the
+    next one had started to land -- one wrong pixel in ~1-3 % of the calls (tools/gn_repro.py), far too rare for the
+    small shapes above.  400 calls must agree bit for bit."""
+    from cremage_b200 import ops
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_K_CHUNKS", 1)
+    monkeypatch.setattr(ops, "GN_FUSE_MIN_BYTES", 0)
+    n, h, w, c = 8, 512, 512, 128
+    x = _rand(n, h, w, 64, seed=41).to(ACT).cuda()
+    a = ops.nhwc(_conv_with_stats(ops, x, 64, c, 42), n, h, w, c)
+    assert getattr(a, "_gn_part", None) is not None and a._gn_part.shape[1] > 32   # the folded-table path
+    gamma, beta = _rand(c, seed=2, scale=0.2, shift=1.0).cuda(), _rand(c, seed=3, scale=0.2).cuda()
+    first = ops.groupnorm(a, gamma, beta, 1e-6, True).clone()
+    bad = sum(0 if torch.equal(ops.groupnorm(a, gamma, beta, 1e-6, True), first) else 1 for _ in range(400))
+    assert bad == 0, f"{bad} of 400 repeats differ"
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 128), (1, 32, 32, 128, 64), (3, 8, 8, 64, 320)])
 def test_groupnorm_after_folded_upsample_conv_uses_the_shared_partial_table(monkeypatch, n, h, w, cin, cout):
     """The four parity launches of conv3x3_up2x fill disjoint row ranges of one GroupNorm partial table."""
