@@ -151,6 +151,21 @@ def test_cfg3_vae_decode_64(sd15):
     assert p >= 35.0 and tuple(img.shape) == (2, 3, 512, 512)
 
 
+def test_full_size_decode_and_unet_forward_are_bit_reproducible(sd15):
+    """The same input through the same kernels must give the same bytes (the property the multi-GPU parity line of
+    bench.py rests on): 60 AutoencoderKL decodes of one 8 x 64 x 64 latent batch -- the shape whose GroupNorm ring exposed
+    the cross-proxy race of round 2 -- and 8 UNet forwards of one CFG-doubled batch."""
+    ldm, _ = sd15
+    z = randn((8, 4, 64, 64), 43).cuda()
+    first = ldm.first_stage_model.decode(z).clone()
+    bad = sum(0 if torch.equal(ldm.first_stage_model.decode(z), first) else 1 for _ in range(60))
+    assert bad == 0, f"{bad} of 60 decodes differ"
+    x, t, ctx = randn((4, 4, 64, 64), 44).cuda(), torch.tensor([801., 801., 12., 12.]).cuda(), randn((4, 77, 768), 45).cuda()
+    u0 = ldm.model.diffusion_model(x, t, context=ctx).clone()
+    bad = sum(0 if torch.equal(ldm.model.diffusion_model(x, t, context=ctx), u0) else 1 for _ in range(8))
+    assert bad == 0, f"{bad} of 8 UNet forwards differ"
+
+
 def test_hires_unet_forward_128(sd15):
     """configs[3]: the second pass runs the same UNet at 128x128 -- 16 384-token self-attention at the top level."""
     ldm, _ = sd15
