@@ -79,6 +79,14 @@ def test_plan_runs_without_a_gpu_and_matches_the_measured_policy():
     assert p.cta_pair == 0 and p.ksplit == 1 and (p.tw, p.th, p.tn) == (128, 1, 1)
     p = plan(1, 1, 65536, 320, 320, 1, cta_pair=1, bn=64)   # pinned fields are kept
     assert p.cta_pair == 1 and p.bn == 64
+    # LayerNorm statistics ride on the staged epilogue: AUTO stages small-K launches only, so a K = 5120 producer of the
+    # residual stream (ff.net.2) carries them only when the caller pins the staged form (ops.igemm does, for ln_stats)
+    p = plan(1, 1, 4096, 5120, 1280, 1)
+    assert p.ln_out_slots == 0
+    p = plan(1, 1, 4096, 5120, 1280, 1, epilogue=2)
+    assert p.ln_out_slots > 0 and p.ksplit == 1
+    p = plan(1, 1, 4096, 1280, 1280, 1)
+    assert p.ln_out_slots > 0
 
 
 @pytest.mark.gpu
