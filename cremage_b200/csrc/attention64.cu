@@ -65,11 +65,13 @@ CB_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* v) {
       : "memory");
 }
 
-CB_DEVINL uint32_t exp2_pack64(float s0, float s1, float scale, float m) {
+template <bool SUM>
+CB_DEVINL uint32_t exp2_pack64(float s0, float s1, float scale, float m, float& rs) {
   const float a0 = fmaf(s0, scale, -m), a1 = fmaf(s1, scale, -m);
   float e0, e1;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  if (SUM) rs += e0 + e1;   // explicit row sum (head dim 64: no spare column of V) from the fp32 exponentials
   return pack_act2(e0, e1);
 }
 
@@ -324,11 +326,7 @@ attention64_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 #pragma unroll
             for (int e = 0; e < 32; e += 2) {
               const float x0 = __uint_as_float(half ? sb[e] : sa[e]), x1 = __uint_as_float(half ? sb[e + 1] : sa[e + 1]);
-              pk[e >> 1] = exp2_pack64(x0, x1, p.scale_log2, m);
-              if (!USE_ONES) {
-                const float2 b0 = unpack_act2(pk[e >> 1]);
-                rs += b0.x + b0.y;
-              }
+              pk[e >> 1] = exp2_pack64<!USE_ONES>(x0, x1, p.scale_log2, m, rs);
             }
             tmem_st16(tPw + uint32_t(half * 16), pk);
           }
