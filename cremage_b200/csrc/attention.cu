@@ -9,8 +9,12 @@
 //
 // Warp-specialised, one CTA = up to two 128-row query tiles of one (batch, head) sharing every K/V tile:
 //   warp 0        TMA producer (Q once, K/V ring)
-//   warp 1        TMEM allocator + single-thread MMA issuer of query tile 0      warp 10   MMA issuer of query tile 1
-//   warps 2..5    softmax warpgroup 0 (query tile 0)      warps 6..9    softmax warpgroup 1 (query tile 1)
+//   warp 1        TMEM allocator + single-thread MMA issuer of query tile 0      warp 2    MMA issuer of query tile 1
+//   warp 3        ones column of V
+//   warps 4..7    softmax warpgroup 0 (query tile 0)      warps 8..11   softmax warpgroup 1 (query tile 1)
+// The four control warps are one ALIGNED warpgroup: they hand registers back (`setmaxnreg.dec`) and the softmax
+// warpgroups take them (`setmaxnreg.inc`), so a row's 128 scores + 32 packed P + the temporaries of the exponential
+// section fit without spills and ptxas has room to interleave.
 // Decoupled issue: a warpgroup releases its S tile (s_free) the moment the scores are in registers, so its issuer
 // thread (one per query tile, each with its own blocking wait sequence; K/V stages are released by both) issues
 // Q*K^T of block j+1 while the warpgroup is still exponentiating block j; P*V of block j follows when P is written
@@ -33,7 +37,11 @@ namespace cb {
 constexpr int ATT_BM = 128;             // query rows per warpgroup tile
 constexpr int ATT_BN = 128;             // kv rows per iteration
 constexpr int PANEL_BYTES = 128 * 128;  // [128 rows][64 x 16-bit]
-constexpr int ATT_THREADS = 384;         // TMA warp, issuer (tile 0), 8 softmax warps, issuer (tile 1), V ones-column warp
+constexpr int ATT_THREADS = 384;         // control warpgroup (TMA, two issuers, V ones column) + 8 softmax warps
+// registers per softmax thread after the hand-over (template parameter REGS; the control warps keep (64512 - 256 REGS) / 128):
+// measured per head-dim class, because ptxas schedules the exponential section differently with every budget --
+// d 40: 168 (no hand-over) 0.692 ms, 176 0.682, 184 0.693, 192 0.688, 200 0.760, 224 0.808; d 80: 0.082, 0.081, 0.074, 0.074, 0.075, 0.075
+constexpr int ATT_REGS_D64 = 176, ATT_REGS_WIDE = 192;
 constexpr float RESCALE_TAU = 8.0f;     // rescale O only when the row max grew by more than 2^8 (P <= 256)
 
 struct AttnParams {
@@ -53,7 +61,7 @@ CB_DEVINL uint32_t exp2_pack(float s0, float s1, float scale, float m) {
   return pack_act2(e0, e1);
 }
 
-template <bool USE_ONES>
+template <bool USE_ONES, int REGS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnParams p) {
@@ -140,6 +148,10 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     __device__ __forceinline__ void next(int stages) { if (++st == stages) { st = 0; ph ^= 1u; } }
   };
 
+  if (warp < 4) {
+  // (the register hand-over sits INSIDE the role branches: behind a merge of the two paths ptxas has to assume the
+  // smaller budget for everything that follows)
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"((64512 - 256 * REGS) / 128));
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {   // (not `lane == 0`: a divergent branch wraps every UTMALDG / UTCHMMA in an ELECT / BRA.U.ANY loop)
@@ -170,9 +182,9 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || warp == 2) {
     // ===================== MMA issuers (one thread per query tile) =====================
-    const int w = (warp == 1) ? 0 : 1;
+    const int w = warp - 1;
     if (w < p.nwg && elect_one()) {
       // descriptors are 64-bit adds on precomputed bases (start address field = bytes >> 4)
       const uint64_t qd0 = make_sdesc_sw128(sQ + uint32_t(w) * tile_bytes, 16, 1024), kd0 = make_sdesc_sw128(sK, 16, 1024);
@@ -245,7 +257,7 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         ++aw;
       }
     }
-  } else if (warp == 11) {
+  } else if (warp == 3) {
     // ===================== V ones-column warp =====================
     // TMA zero-fills the pad columns of a V tile; column d becomes 1.0 so that P*V also yields the softmax row sum.
     const int pn = p.d >> 6, cw = p.d & 63;
@@ -270,9 +282,11 @@ attention_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         mbar_arrive(v_ready(st));
       }
     }
+  }
   } else {
     // ===================== softmax warpgroups =====================
-    const int w = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+    const int w = (warp - 4) >> 2;
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
     const int r = quarter * 32 + lane;                 // query row inside the tile == TMEM lane
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
@@ -511,8 +525,21 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
   CB_REQUIRE(smem <= 227 * 1024, "cb_attention: needs %zu bytes of shared memory", smem);
   static DeviceOnce configured{};
   if (device_once_needed(configured)) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true, ATT_REGS_D64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false, ATT_REGS_D64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<true, ATT_REGS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<false, ATT_REGS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // the register hand-over is balanced for a launch at 168 registers per thread (384 x 168 = 128 x control + 256 x
+    // REGS): with any other count the increase would wait for registers nobody releases -- fail loudly instead
+    cudaFuncAttributes fa{};
+    CB_CHECK_CUDA(cudaFuncGetAttributes(&fa, attention_kernel<true, ATT_REGS_D64>));
+    CB_REQUIRE(fa.numRegs == 168, "cb_attention: attention_kernel was compiled to %d registers per thread, the setmaxnreg split assumes 168", fa.numRegs);
+    CB_CHECK_CUDA(cudaFuncGetAttributes(&fa, attention_kernel<true, ATT_REGS_WIDE>));
+    CB_REQUIRE(fa.numRegs == 168, "cb_attention: attention_kernel was compiled to %d registers per thread, the setmaxnreg split assumes 168", fa.numRegs);
+    CB_CHECK_CUDA(cudaFuncGetAttributes(&fa, attention_kernel<false, ATT_REGS_D64>));
+    CB_REQUIRE(fa.numRegs == 168, "cb_attention: attention_kernel was compiled to %d registers per thread, the setmaxnreg split assumes 168", fa.numRegs);
+    CB_CHECK_CUDA(cudaFuncGetAttributes(&fa, attention_kernel<false, ATT_REGS_WIDE>));
+    CB_REQUIRE(fa.numRegs == 168, "cb_attention: attention_kernel was compiled to %d registers per thread, the setmaxnreg split assumes 168", fa.numRegs);
     device_once_done(configured);
   }
   const int rows_per_item = p.nwg * ATT_BM;
@@ -532,8 +559,13 @@ extern "C" int cb_attention(const void* q, int64_t q_ld, const void* k, int64_t 
       p.total_items = (int)(items + left);
     }
   }
-  if (p.use_ones) (void)cb::launch_k(attention_kernel<true>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
-  else (void)cb::launch_k(attention_kernel<false>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
+  if (dpad == 64) {
+    if (p.use_ones) (void)cb::launch_k(attention_kernel<true, ATT_REGS_D64>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
+    else (void)cb::launch_k(attention_kernel<false, ATT_REGS_D64>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
+  } else {
+    if (p.use_ones) (void)cb::launch_k(attention_kernel<true, ATT_REGS_WIDE>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
+    else (void)cb::launch_k(attention_kernel<false, ATT_REGS_WIDE>, dim3(grid), dim3(ATT_THREADS), (size_t)(smem), stream, mq, mk, mv, p);
+  }
   CB_CHECK_CUDA(cudaGetLastError());
   CB_LAUNCHED(1);
   return CB_OK;
