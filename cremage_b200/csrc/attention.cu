@@ -1,7 +1,7 @@
 // Fused flash-style attention for sm_100a:  O = softmax(scale * Q K^T) V, never materialising the score matrix.
 //
 //   S = Q K^T      tcgen05.mma  (A = Q tile [128 x dpad], B = K tile [128 x dpad], both K-major)  -> TMEM
-//   online softmax one thread per query row: tcgen05.ld of S, exp2 (packed 16-bit MUFU in the fp16 build), lazy
+//   online softmax one thread per query row: tcgen05.ld of S, exp2 (fp32 MUFU, one packing convert per pair), lazy
 //                  running-max rescale of the TMEM accumulator, P packed to 16-bit pairs -> TMEM (tcgen05.st)
 //   O += P V       tcgen05.mma  (A = P straight from TMEM, B = V tile in smem, MN-major)           -> TMEM
 // P never touches shared memory: with d = 40 the P round trip (32 KB written + 32 KB read per tile and block) would
@@ -18,8 +18,8 @@
 // Decoupled issue: a warpgroup releases its S tile (s_free) the moment the scores are in registers, so its issuer
 // thread (one per query tile, each with its own blocking wait sequence; K/V stages are released by both) issues
 // Q*K^T of block j+1 while the warpgroup is still exponentiating block j; P*V of block j follows when P is written
-// (p_full) and signals pv_done, which the warpgroup only consults before it overwrites P or rescales O.  In steady state a warpgroup never waits for the
-// tensor core, and the two warpgroups keep the MUFU pipe (the bound for d = 40) busy back to back.
+// (p_full) and signals pv_done, which the warpgroup only consults before it overwrites P or rescales O.  In steady
+// state a warpgroup never waits for the tensor core; the MUFU pipe (the bound for d = 40) is 75 % busy.
 // The softmax row sum is a by-product of the tensor core when the padded head dim has a spare column (dpad > d): a
 // helper warp writes 1.0 into column d of every V tile once its TMA load has landed (the pad columns arrive as
 // zeros), so P*V accumulates sum_j P_ij into O[:, d] at no extra MMA.
